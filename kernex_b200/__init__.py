@@ -1,0 +1,18 @@
+"""kernex_b200 -- B200-native (sm_100a) engine behind the kernex kmap/kscan API.
+
+Public surface = the reference's (``kernex/__init__.py:15-28``): ``kmap``, ``kscan``,
+``smap``, ``sscan`` and the four engine factories ``kernel_map``,
+``offset_kernel_map``, ``kernel_scan``, ``offset_kernel_scan``.
+"""
+
+from .engine import kernel_map, kernel_scan, offset_kernel_map, offset_kernel_scan
+from .errors import EngineUnavailableError, UnsupportedStencilError
+from .interface import kmap, kscan, smap, sscan
+
+__all__ = (
+    "kmap", "kscan", "smap", "sscan",
+    "kernel_map", "kernel_scan", "offset_kernel_map", "offset_kernel_scan",
+    "UnsupportedStencilError", "EngineUnavailableError",
+)
+
+__version__ = "0.1.0"

@@ -1,0 +1,457 @@
+"""The four engine factories of kernex, re-implemented on the B200 CUDA library.
+
+Drop-in for ``kernel_map`` / ``offset_kernel_map`` (``kernex/_src/map.py:61-124,
+127-156``) and ``kernel_scan`` / ``offset_kernel_scan`` (``kernex/_src/scan.py:
+65-115, 118-147``): same positional signature ``(func_map, shape, kernel_size,
+strides, border|offset, relative, kind, kwargs)`` and same ``func_map`` key format
+(``()`` single function, ``[[]]`` match-all, lists of per-dim ``int |
+(start,end[,step]) | inf`` keys), returning ``fn(array, *args, **kwargs)``.
+
+Nothing is computed in Python: the window functions are traced + classified
+(``tracer.py``), described as a ``KxProgram`` and executed by ``libkx_b200.so``
+through the C ABI of ``include/kx_b200.h``.  Arrays may be NumPy arrays (copied
+to the device and back, the end-to-end path) or CUDA ``torch`` tensors (zero
+copy, result stays on the device).  PyTorch is used for device memory, streams
+and autograd plumbing only.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Any, Callable, Sequence
+
+import numpy as np
+
+from . import _lib
+from .errors import EngineUnavailableError, UnsupportedStencilError
+from .tracer import FuncSpec, trace_function
+
+try:
+    import torch
+except Exception as e:  # pragma: no cover
+    raise EngineUnavailableError(f"kernex_b200 needs PyTorch for device memory and streams: {e}")
+
+__all__ = ["kernel_map", "kernel_scan", "offset_kernel_map", "offset_kernel_scan"]
+
+_NP2KX = {np.dtype(np.float32): _lib.KX_F32, np.dtype(np.int32): _lib.KX_I32}
+_KX2TORCH = {_lib.KX_F32: torch.float32, _lib.KX_I32: torch.int32}
+_TORCH2KX = {torch.float32: _lib.KX_F32, torch.int32: _lib.KX_I32}
+
+
+# --------------------------------------------------------------------------- #
+# geometry helpers (kernex/_src/utils.py:93-144,195-202)                        #
+# --------------------------------------------------------------------------- #
+
+
+def calculate_output_shape(shape, kernel_size, strides, border):
+    return tuple((n + lo + hi - k) // s + 1
+                 for n, k, s, (lo, hi) in zip(shape, kernel_size, strides, border, strict=True))
+
+
+def offset_to_border(offset, kernel_size):
+    out = []
+    for item, k in zip(offset, kernel_size):
+        item = (item, item) if isinstance(item, int) else tuple(item)
+        if item < (0, 0):
+            raise ValueError(f"Negative value found, offset={item}")
+        out.append(((k - 1) // 2 - item[0], k // 2 - item[1]))
+    return tuple(out)
+
+
+# --------------------------------------------------------------------------- #
+# array plumbing                                                                #
+# --------------------------------------------------------------------------- #
+
+
+def _require_cuda():
+    if not torch.cuda.is_available():
+        raise EngineUnavailableError(
+            "no CUDA device: kernex_b200 executes on sm_100a only and has no CPU fallback")
+
+
+class _Arr:
+    """An input array moved to the device, remembering how to hand results back."""
+
+    def __init__(self, array):
+        self.was_numpy = not isinstance(array, torch.Tensor)
+        if self.was_numpy:
+            host = np.asarray(array)
+            if host.dtype == np.float64:       # JAX without x64 demotes too
+                host = host.astype(np.float32)
+            elif host.dtype in (np.int64, np.int16, np.int8, np.uint8, np.bool_):
+                host = host.astype(np.int32)
+            if host.dtype not in _NP2KX:
+                raise UnsupportedStencilError(f"dtype {host.dtype} is not supported (float32 / int32 only)")
+            _require_cuda()
+            self.t = torch.from_numpy(np.ascontiguousarray(host)).cuda(non_blocking=True)
+        else:
+            t = array
+            if t.dtype == torch.float64:
+                t = t.float()
+            elif t.dtype == torch.int64:
+                t = t.int()
+            if t.dtype not in _TORCH2KX:
+                raise UnsupportedStencilError(f"dtype {t.dtype} is not supported (float32 / int32 only)")
+            if not t.is_cuda:
+                _require_cuda()
+                t = t.cuda()
+            self.t = t.contiguous()
+        self.kx_dtype = _TORCH2KX[self.t.dtype]
+
+    def give_back(self, t):
+        return t.cpu().numpy() if self.was_numpy else t
+
+
+def _stream_ptr(device):
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+# --------------------------------------------------------------------------- #
+# program construction                                                          #
+# --------------------------------------------------------------------------- #
+
+
+def _key_item(item):
+    it = _lib.KxKeyItem()
+    if isinstance(item, (tuple, list, np.ndarray)):
+        vals = list(item)
+    else:
+        vals = [item]
+    inf = [isinstance(v, float) and math.isinf(v) for v in vals]
+    big = (1 << 62)
+    if len(vals) == 1:
+        if inf[0]:
+            it.kind = _lib.KX_KEY_ANY
+        else:
+            it.kind, it.a = _lib.KX_KEY_EQ, int(vals[0])
+    elif len(vals) in (2, 3):
+        it.kind = _lib.KX_KEY_RANGE if len(vals) == 2 else _lib.KX_KEY_RANGE_STEP
+        it.a = -big if (inf[0] and vals[0] < 0) else (big if inf[0] else int(vals[0]))
+        it.b = big if (inf[1] and vals[1] > 0) else (-big if inf[1] else int(vals[1]))
+        if len(vals) == 3:
+            if inf[2]:
+                raise ValueError("infinite step in a region key")
+            it.step = int(vals[2])
+            if it.step == 0:
+                raise ZeroDivisionError("region key with step 0")
+    else:
+        raise ValueError(f"region key item {item!r} must have 1, 2 or 3 entries")
+    return it
+
+
+class _Program:
+    """Host description of the traced functions -> ``KxProgram``."""
+
+    def __init__(self, specs: Sequence[FuncSpec], key_groups, ndim):
+        if len(specs) > _lib.KX_MAX_FUNCS:
+            raise UnsupportedStencilError(f"at most {_lib.KX_MAX_FUNCS} functions per mesh")
+        self.specs = list(specs)
+        p = _lib.KxProgram()
+        p.n_funcs = len(specs)
+        t = 0
+        self.device_refs = []  # (tap slot, Coef) with weight references
+        for fi, s in enumerate(specs):
+            if t + len(s.taps) > _lib.KX_MAX_TAPS:
+                raise UnsupportedStencilError(f"more than {_lib.KX_MAX_TAPS} taps in one program")
+            f = p.func[fi]
+            f.kind = {"affine": _lib.KX_AFFINE, "max": _lib.KX_REDUCE_MAX, "min": _lib.KX_REDUCE_MIN,
+                      "gather": _lib.KX_GATHER}[s.kind]
+            f.tap_begin = t
+            for ti, tap in enumerate(s.taps):
+                for d in range(ndim):
+                    p.tap_off[t][d] = int(tap[d])
+                if s.kind == "affine":
+                    c = s.coefs[ti]
+                    p.coef[t] = float(c.const)
+                    if not c.is_const:
+                        self.device_refs.append((t, c))
+                else:
+                    p.coef[t] = 1.0
+                t += 1
+            f.tap_end = t
+            if s.kind == "affine":
+                if not s.bias.is_const:
+                    raise UnsupportedStencilError("a device-resident additive term (bias) is not supported")
+                f.bias = float(s.bias.const)
+                f.coef_is_int = int(s.integral)
+            else:
+                f.coef_is_int = 1
+        p.n_taps = t
+        nk = 0
+        if len(specs) > 1:
+            for fi, group in enumerate(key_groups):
+                for key in group:
+                    if nk >= _lib.KX_MAX_KEYS:
+                        raise UnsupportedStencilError(f"more than {_lib.KX_MAX_KEYS} region keys")
+                    k = p.key[nk]
+                    k.func = fi
+                    items = list(key)[:ndim]
+                    k.n_items = len(items)
+                    for d, item in enumerate(items):
+                        k.item[d] = _key_item(item)
+                    nk += 1
+        p.n_keys = nk
+        self.c = p
+
+    def coef_tensor(self, device_args, dtype, device):
+        """Device coefficient table ``const + sum scale * W.flatten()[idx]`` built with
+        torch ops so that autograd reaches the weights."""
+        if not self.device_refs:
+            return None
+        n = self.c.n_taps
+        coef = torch.tensor([self.c.coef[i] for i in range(n)], dtype=dtype, device=device)
+        by_arg: dict[Any, list] = {}
+        for slot, c in self.device_refs:
+            for (arg, flat), scale in c.w.items():
+                by_arg.setdefault(arg, []).append((slot, flat, scale))
+        for arg, refs in by_arg.items():
+            w = device_args[arg]
+            if not w.is_cuda:
+                w = w.to(device)
+            slots = torch.tensor([r[0] for r in refs], dtype=torch.long, device=device)
+            flats = torch.tensor([r[1] for r in refs], dtype=torch.long, device=device)
+            scales = torch.tensor([r[2] for r in refs], dtype=dtype, device=device)
+            coef = coef.index_add(0, slots, w.reshape(-1).to(dtype)[flats] * scales)
+        return coef.contiguous()
+
+
+def _geom(in_shape, out_shape, kernel_size, strides, border, in_dtype, out_dtype):
+    nd = len(in_shape)
+    if nd > _lib.KX_MAX_DIMS:
+        raise UnsupportedStencilError(f"arrays of rank > {_lib.KX_MAX_DIMS} are not supported")
+    g = _lib.KxGeom()
+    g.ndim, g.in_dtype, g.out_dtype = nd, in_dtype, out_dtype
+    for d in range(nd):
+        g.in_shape[d], g.out_shape[d] = int(in_shape[d]), int(out_shape[d])
+        g.ksize[d], g.stride[d] = int(kernel_size[d]), int(strides[d])
+        g.lo[d], g.hi[d] = int(border[d][0]), int(border[d][1])
+    return g
+
+
+def _result_dtype(specs, in_dtype):
+    """JAX's weak-type promotion for the per-window results: taps
+    carry the array dtype, Python numbers are weak; int array + float factor -> f32."""
+    strong = any(s.kind != "affine" or s.taps for s in specs)
+    any_float = any(s.kind == "affine" and s.weak_float for s in specs)
+    if strong:
+        if in_dtype == _lib.KX_I32 and any_float:
+            return _lib.KX_F32
+        return in_dtype
+    return _lib.KX_F32 if any_float else _lib.KX_I32
+
+
+def _trace_all(func_map, kernel_size, relative, a, k):
+    funcs = list(func_map.keys())
+    specs, device_args = [], {}
+    for f in funcs:
+        spec, dev = trace_function(f, kernel_size, relative, a, k)
+        specs.append(spec)
+        device_args.update(dev)
+    return specs, device_args
+
+
+def _validate(shape, kernel_size, strides, border):
+    if not (len(shape) == len(kernel_size) == len(strides) == len(border)):
+        raise ValueError("shape, kernel_size, strides and border must have the same length")
+    if any(s <= 0 for s in strides):
+        raise ValueError(f"strides must be positive, found {strides}")
+    if any(k <= 0 for k in kernel_size):
+        raise ValueError(f"kernel_size must be positive, found {kernel_size}")
+
+
+# --------------------------------------------------------------------------- #
+# autograd (the reference gets this from JAX's transpose rules)     #
+# --------------------------------------------------------------------------- #
+
+
+class _AffineMapFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, coef, geom, prog, out_shape, out_dtype):
+        lib = _lib.load()
+        out = torch.empty(out_shape, dtype=out_dtype, device=x.device)
+        if out.numel():
+            _lib.check(lib.kx_map(C.byref(geom), C.byref(prog.c), _ptr(x), _ptr(coef), 0, _ptr(out), 1,
+                                  _stream_ptr(x.device)))
+        ctx.geom, ctx.prog = geom, prog
+        ctx.save_for_backward(x, coef)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = _lib.load()
+        x, coef = ctx.saved_tensors
+        geom, prog = ctx.geom, ctx.prog
+        g = g.contiguous()
+        dx = dcoef = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(x)
+            _lib.check(lib.kx_map_vjp_input(C.byref(geom), C.byref(prog.c), _ptr(g), _ptr(coef), _ptr(dx),
+                                            _stream_ptr(x.device)))
+        if coef is not None and ctx.needs_input_grad[1]:
+            nbytes = lib.kx_vjp_coef_scratch_bytes(C.byref(geom), C.byref(prog.c))
+            scratch = torch.empty(max(int(nbytes), 4), dtype=torch.uint8, device=x.device)
+            dcoef = torch.empty_like(coef)
+            _lib.check(lib.kx_map_vjp_coef(C.byref(geom), C.byref(prog.c), _ptr(x), _ptr(g), _ptr(scratch),
+                                           _ptr(dcoef), _stream_ptr(x.device)))
+        return dx, dcoef, None, None, None, None
+
+
+# --------------------------------------------------------------------------- #
+# kmap                                                                          #
+# --------------------------------------------------------------------------- #
+
+
+def _run_map(func_map, shape, kernel_size, strides, border, relative, array, a, k):
+    arr = _Arr(array)
+    if tuple(arr.t.shape) != tuple(shape):
+        raise ValueError(f"array shape {tuple(arr.t.shape)} != declared shape {tuple(shape)}")
+    specs, device_args = _trace_all(func_map, kernel_size, relative, a, k)
+    groups = [tuple(v) for v in func_map.values()]
+    out_shape = calculate_output_shape(shape, kernel_size, strides, border)
+    out_shape = tuple(max(o, 0) for o in out_shape)
+    gather = [s for s in specs if s.kind == "gather"]
+    if gather and len(specs) > 1:
+        raise UnsupportedStencilError("vector-valued functions cannot be mixed in a multi-function mesh")
+    out_kx = _result_dtype(specs, arr.kx_dtype)
+    prog = _Program(specs, groups, len(shape))
+    geom = _geom(shape, out_shape, kernel_size, strides, border, arr.kx_dtype, out_kx)
+    full_shape = out_shape + (gather[0].out_shape if gather else ())
+    comp_dtype = _KX2TORCH[out_kx]
+    coef = prog.coef_tensor(device_args, comp_dtype, arr.t.device)
+    needs_grad = torch.is_grad_enabled() and (arr.t.requires_grad or (coef is not None and coef.requires_grad))
+    if needs_grad:
+        if len(specs) != 1 or specs[0].kind != "affine" or out_kx != _lib.KX_F32 or arr.kx_dtype != _lib.KX_F32:
+            raise UnsupportedStencilError("gradients are implemented for single-function float32 affine stencils")
+        out = _AffineMapFn.apply(arr.t, coef, geom, prog, full_shape, comp_dtype)
+    else:
+        lib = _lib.load()
+        out = torch.empty(full_shape, dtype=comp_dtype, device=arr.t.device)
+        if out.numel():
+            _lib.check(lib.kx_map(C.byref(geom), C.byref(prog.c), _ptr(arr.t), _ptr(coef), 0, _ptr(out), 1,
+                                  _stream_ptr(arr.t.device)))
+    return arr, out
+
+
+def kernel_map(func_map: dict, shape, kernel_size, strides, border, relative: bool = False,
+               map_kind: str = "vmap", map_kwargs: dict | None = None) -> Callable:
+    """``kernex.kernel_map`` (``_src/map.py:61-124``).  ``map_kind`` selects a JAX
+    transform in the reference (``vmap``/``lmap``/``pmap``, ``_src/utils.py:25-30``);
+    all three give the same values, so it is validated and otherwise ignored."""
+    if map_kind not in (None, "vmap", "lmap", "pmap"):
+        raise KeyError(map_kind)
+    if map_kwargs:
+        raise UnsupportedStencilError(f"map_kwargs={map_kwargs!r} are JAX transform options with no CUDA meaning")
+    shape, kernel_size, strides = tuple(shape), tuple(kernel_size), tuple(strides)
+    border = tuple(tuple(b) for b in border)
+    _validate(shape, kernel_size, strides, border)
+
+    def call(array, *a, **k):
+        arr, out = _run_map(func_map, shape, kernel_size, strides, border, relative, array, a, k)
+        return arr.give_back(out)
+
+    return call
+
+
+def offset_kernel_map(func_map: dict, shape, kernel_size, strides, offset, relative: bool = False,
+                      map_kind: str = "vmap", map_kwargs: dict | None = None) -> Callable:
+    """``kernex.offset_kernel_map`` (``_src/map.py:127-156``): run the map with the
+    border implied by ``offset`` and write the result into a copy of the input at
+    ``[o0 : n-o1 : s]`` per axis."""
+    shape, kernel_size, strides = tuple(shape), tuple(kernel_size), tuple(strides)
+    offset = [(o, o) if isinstance(o, int) else tuple(o) for o in offset]
+    border = offset_to_border(offset, kernel_size)
+    inner = kernel_map(func_map, shape, kernel_size, strides, border, relative, map_kind, map_kwargs)
+
+    def call(array, *a, **k):
+        arr, res = _run_map(func_map, shape, kernel_size, strides, border, relative, array, a, k)
+        return arr.give_back(_write_back(arr.t, res, shape, strides, offset, "map"))
+
+    del inner
+    return call
+
+
+def _write_back(x, res, shape, strides, offset, what):
+    if tuple(res.shape) > tuple(x.shape):  # lexicographic, as the reference (map.py:152)
+        raise ValueError(f"{what} operation output must be scalar. Found result.shape={tuple(res.shape)}")
+    out = x.clone()
+    sl = tuple(slice(o0, n - o1, s) for n, s, (o0, o1) in zip(shape, strides, offset))
+    if res.numel():
+        out[sl] = res.to(out.dtype)  # strided device-to-device copy (cast as .at[].set does)
+    return out
+
+
+# --------------------------------------------------------------------------- #
+# kscan                                                                         #
+# --------------------------------------------------------------------------- #
+
+
+def _run_scan(func_map, shape, kernel_size, strides, border, relative, reverse, array, a, k):
+    arr = _Arr(array)
+    if tuple(arr.t.shape) != tuple(shape):
+        raise ValueError(f"array shape {tuple(arr.t.shape)} != declared shape {tuple(shape)}")
+    specs, device_args = _trace_all(func_map, kernel_size, relative, a, k)
+    for s in specs:
+        if s.kind == "gather" and s.out_shape != ():
+            raise ValueError("scan operation output must be scalar.")
+    groups = [tuple(v) for v in func_map.values()]
+    out_shape = tuple(max(o, 0) for o in calculate_output_shape(shape, kernel_size, strides, border))
+    prog = _Program(specs, groups, len(shape))
+    # the carried state has the array's dtype; values are cast on write (scan.py:50)
+    geom = _geom(shape, out_shape, kernel_size, strides, border, arr.kx_dtype, arr.kx_dtype)
+    comp = torch.float32 if any(s.kind == "affine" and s.weak_float for s in specs) else arr.t.dtype
+    coef = prog.coef_tensor(device_args, comp, arr.t.device)
+    lib = _lib.load()
+    out = torch.empty(out_shape, dtype=arr.t.dtype, device=arr.t.device)
+    if out.numel():
+        nbytes = int(lib.kx_scan_state_bytes(C.byref(geom)))
+        state = torch.empty(max(nbytes, 4), dtype=torch.uint8, device=arr.t.device)
+        _lib.check(lib.kx_scan(C.byref(geom), C.byref(prog.c), _ptr(arr.t), _ptr(coef), _ptr(state), _ptr(out),
+                               int(bool(reverse)), _stream_ptr(arr.t.device)))
+    return arr, out
+
+
+def _scan_kwargs(scan_kind, scan_kwargs):
+    if scan_kind not in (None, "scan"):
+        raise KeyError(scan_kind)
+    kw = dict(scan_kwargs or {})
+    reverse = bool(kw.pop("reverse", False))
+    kw.pop("unroll", None)  # scheduling hint only
+    if kw:
+        raise UnsupportedStencilError(f"scan_kwargs={kw!r} are JAX transform options with no CUDA meaning")
+    return reverse
+
+
+def kernel_scan(func_map: dict, shape, kernel_size, strides, border, relative: bool = False,
+                scan_kind: str = "scan", scan_kwargs: dict | None = None) -> Callable:
+    """``kernex.kernel_scan`` (``_src/scan.py:65-115``)."""
+    reverse = _scan_kwargs(scan_kind, scan_kwargs)
+    shape, kernel_size, strides = tuple(shape), tuple(kernel_size), tuple(strides)
+    border = tuple(tuple(b) for b in border)
+    _validate(shape, kernel_size, strides, border)
+
+    def call(array, *a, **k):
+        arr, out = _run_scan(func_map, shape, kernel_size, strides, border, relative, reverse, array, a, k)
+        return arr.give_back(out)
+
+    return call
+
+
+def offset_kernel_scan(func_map: dict, shape, kernel_size, strides, offset, relative: bool = False,
+                       scan_kind: str = "scan", scan_kwargs: dict | None = None) -> Callable:
+    """``kernex.offset_kernel_scan`` (``_src/scan.py:118-147``)."""
+    reverse = _scan_kwargs(scan_kind, scan_kwargs)
+    shape, kernel_size, strides = tuple(shape), tuple(kernel_size), tuple(strides)
+    offset = [(o, o) if isinstance(o, int) else tuple(o) for o in offset]
+    border = offset_to_border(offset, kernel_size)
+    _validate(shape, kernel_size, strides, border)
+
+    def call(array, *a, **k):
+        arr, res = _run_scan(func_map, shape, kernel_size, strides, border, relative, reverse, array, a, k)
+        return arr.give_back(_write_back(arr.t, res, shape, strides, offset, "scan"))
+
+    return call
