@@ -97,6 +97,7 @@ typedef struct KxFunc {
   int32_t tap_begin, tap_end;       /* slice of KxProgram.tap_off / coef             */
   int32_t coef_is_int;              /* coefficients & bias are exact integers        */
   double bias;
+  double post_div;                  /* 0 = none; else result = (bias + sum) / post_div (window mean) */
 } KxFunc;
 
 /* The classified window functions of one kmap/kscan call.  Function selection per
@@ -171,16 +172,6 @@ int kx_map_vjp_coef(const KxGeom* geom, const KxProgram* prog, const void* x, co
 int64_t kx_scan_state_bytes(const KxGeom* geom);
 int kx_scan(const KxGeom* geom, const KxProgram* prog, const void* in, const void* coef_dev,
             void* state, void* out, int32_t reverse, void* stream);
-
-/* Row-marching kscan for 2-D time-marching stencils whose input rows >= 1 are dead
- * (README.md:231-266 linear convection): never reads `in` beyond row 0, writes
- * out[nt, nx] only (4 B per lattice update).  Columns [col0, col0+geom.in_shape[1])
- * of a global row of width `global_nx` are produced, so a rank of an axis-1 domain
- * decomposition calls it on its own slab; `left_halo`, when non-null, supplies the
- * values of the `halo_w` columns left of col0 for every row (device, [nt, halo_w]).
- * Returns KX_ERR_UNSUPPORTED when the dependency analysis does not allow it. */
-int kx_scan_rowmarch(const KxGeom* geom, const KxProgram* prog, const void* in_row0,
-                     int64_t col0, int64_t global_nx, void* out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -56,6 +56,7 @@ class KxFunc(C.Structure):
         ("tap_end", C.c_int32),
         ("coef_is_int", C.c_int32),
         ("bias", C.c_double),
+        ("post_div", C.c_double),
     ]
 
 

@@ -1,0 +1,175 @@
+// extern "C" entry points of libkx_b200 (declared in include/kx_b200.h): validation and
+// dispatch to the kernel templates.  Every entry point only enqueues on `stream`.
+#include "kx_internal.cuh"
+
+using namespace kx;
+
+namespace {
+
+int validate(const KxGeom* g, const KxProgram* p) {
+  if (!g || !p) return fail(KX_ERR_INVALID, "null geometry / program");
+  if (g->ndim < 1 || g->ndim > KX_MAX_DIMS) return fail(KX_ERR_INVALID, "ndim=%d outside [1,%d]", g->ndim, KX_MAX_DIMS);
+  if ((g->in_dtype != KX_F32 && g->in_dtype != KX_I32) || (g->out_dtype != KX_F32 && g->out_dtype != KX_I32))
+    return fail(KX_ERR_INVALID, "unknown dtype in=%d out=%d", g->in_dtype, g->out_dtype);
+  for (int d = 0; d < g->ndim; ++d) {
+    if (g->in_shape[d] < 0 || g->ksize[d] < 1 || g->stride[d] < 1)
+      return fail(KX_ERR_INVALID, "axis %d: shape=%lld ksize=%d stride=%d", d, (long long)g->in_shape[d], g->ksize[d],
+                  g->stride[d]);
+    int64_t span = g->in_shape[d] + g->lo[d] + g->hi[d] - g->ksize[d];
+    int64_t expect = span >= 0 ? span / g->stride[d] + 1 : 0;
+    if (expect < 0) expect = 0;
+    if (g->out_shape[d] != expect)
+      return fail(KX_ERR_INVALID, "axis %d: out_shape=%lld but (n+lo+hi-k)/s+1=%lld", d, (long long)g->out_shape[d],
+                  (long long)expect);
+  }
+  if (p->n_funcs < 1 || p->n_funcs > KX_MAX_FUNCS) return fail(KX_ERR_INVALID, "n_funcs=%d", p->n_funcs);
+  if (p->n_taps < 0 || p->n_taps > KX_MAX_TAPS) return fail(KX_ERR_INVALID, "n_taps=%d", p->n_taps);
+  if (p->n_keys < 0 || p->n_keys > KX_MAX_KEYS) return fail(KX_ERR_INVALID, "n_keys=%d", p->n_keys);
+  for (int f = 0; f < p->n_funcs; ++f) {
+    const KxFunc& fn = p->func[f];
+    if (fn.kind < KX_AFFINE || fn.kind > KX_GATHER) return fail(KX_ERR_INVALID, "function %d: kind=%d", f, fn.kind);
+    if (fn.tap_begin < 0 || fn.tap_end < fn.tap_begin || fn.tap_end > p->n_taps)
+      return fail(KX_ERR_INVALID, "function %d: taps [%d,%d) of %d", f, fn.tap_begin, fn.tap_end, p->n_taps);
+    if (fn.kind != KX_AFFINE && fn.tap_end == fn.tap_begin)
+      return fail(KX_ERR_INVALID, "function %d: reduce / gather needs at least one tap", f);
+    for (int t = fn.tap_begin; t < fn.tap_end; ++t)
+      for (int d = 0; d < g->ndim; ++d)
+        if (p->tap_off[t][d] < 0 || p->tap_off[t][d] >= g->ksize[d])
+          return fail(KX_ERR_INVALID, "tap %d axis %d: offset %d outside the window [0,%d)", t, d, p->tap_off[t][d],
+                      g->ksize[d]);
+  }
+  for (int k = 0; k < p->n_keys; ++k) {
+    if (p->key[k].func < 0 || p->key[k].func >= p->n_funcs || p->key[k].n_items < 0 || p->key[k].n_items > g->ndim)
+      return fail(KX_ERR_INVALID, "region key %d is malformed", k);
+    if (k > 0 && p->key[k].func < p->key[k - 1].func)
+      return fail(KX_ERR_INVALID, "region keys must be grouped by function in insertion order");
+  }
+  if (p->n_funcs > 1)
+    for (int f = 0; f < p->n_funcs; ++f)
+      if (p->func[f].kind == KX_GATHER && p->func[f].tap_end - p->func[f].tap_begin != 1)
+        return fail(KX_ERR_INVALID, "vector-valued functions cannot be part of a multi-function program");
+  return KX_OK;
+}
+
+void fill_map_args(MapArgs& a, const KxGeom& g, const KxProgram& p, const void* in, const void* coef_dev,
+                   int64_t coef_batch_stride, void* out, int64_t batch) {
+  memset(&a, 0, sizeof(a));
+  a.g = g;
+  a.in = in;
+  a.coef_dev = coef_dev;
+  a.out = out;
+  a.n_win = prod(g.out_shape, g.ndim);
+  a.in_elems = prod(g.in_shape, g.ndim);
+  a.fn_elems = (p.n_funcs == 1 && p.func[0].kind == KX_GATHER) ? p.func[0].tap_end - p.func[0].tap_begin : 1;
+  a.out_batch_stride = a.n_win * a.fn_elems;
+  a.coef_batch_stride = coef_batch_stride;
+  a.batch = batch;
+  int64_t pitch = 1;
+  for (int d = g.ndim - 1; d >= 0; --d) {
+    a.out_pitch[d] = pitch;
+    pitch *= g.out_shape[d];
+  }
+  a.out_base = 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int kx_abi_version(void) { return KX_ABI_VERSION; }
+const char* kx_last_error(void) { return err_buf(); }
+uint64_t kx_launch_count(void) { return launch_counter().load(); }
+const char* kx_last_kernel(void) { return last_kernel_name(); }
+
+int kx_map(const KxGeom* geom, const KxProgram* prog, const void* in, const void* coef_dev, int64_t coef_batch_stride,
+           void* out, int64_t batch, void* stream) {
+  int rc = validate(geom, prog);
+  if (rc) return rc;
+  if (batch < 1) return fail(KX_ERR_INVALID, "batch=%lld", (long long)batch);
+  if (!in || !out) return fail(KX_ERR_INVALID, "null device pointer");
+  MapArgs a;
+  fill_map_args(a, *geom, *prog, in, coef_dev, coef_batch_stride, out, batch);
+  if (a.n_win == 0) return KX_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  rc = try_stencil2d(a, *prog, s);
+  if (rc != KX_ERR_UNSUPPORTED) return rc;
+  rc = try_stencil3d(a, *prog, s);
+  if (rc != KX_ERR_UNSUPPORTED) return rc;
+  rc = try_patch(a, *prog, s);
+  if (rc != KX_ERR_UNSUPPORTED) return rc;
+  return launch_generic_map(a, *prog, s);
+}
+
+int kx_map_offset(const KxGeom* geom, const KxProgram* prog, const void* in, const void* coef_dev,
+                  const int32_t* off0, void* out, void* stream) {
+  int rc = validate(geom, prog);
+  if (rc) return rc;
+  if (!in || !out || !off0) return fail(KX_ERR_INVALID, "null pointer");
+  if (geom->in_dtype != geom->out_dtype)
+    return fail(KX_ERR_INVALID, "offset maps write into a copy of the input: dtypes must agree");
+  for (int f = 0; f < prog->n_funcs; ++f)
+    if (prog->func[f].kind == KX_GATHER && prog->func[f].tap_end - prog->func[f].tap_begin != 1)
+      return fail(KX_ERR_INVALID, "offset map output must be scalar");
+  MapArgs a;
+  fill_map_args(a, *geom, *prog, in, coef_dev, 0, out, 1);
+  if (a.n_win == 0) return KX_OK;
+  // window j of axis d lands at input coordinate off0[d] + j*stride[d] of the copy
+  int64_t pitch = 1;
+  a.out_base = 0;
+  for (int d = geom->ndim - 1; d >= 0; --d) {
+    a.out_pitch[d] = pitch * geom->stride[d];
+    a.out_base += pitch * off0[d];
+    if (off0[d] < 0 || off0[d] + (geom->out_shape[d] - 1) * (int64_t)geom->stride[d] >= geom->in_shape[d])
+      return fail(KX_ERR_INVALID, "axis %d: offset write-back leaves the array", d);
+    pitch *= geom->in_shape[d];
+  }
+  a.fn_elems = 1;
+  return launch_generic_map(a, *prog, (cudaStream_t)stream);
+}
+
+int kx_map_vjp_input(const KxGeom* geom, const KxProgram* prog, const void* g, const void* coef_dev, void* dx,
+                     void* stream) {
+  int rc = validate(geom, prog);
+  if (rc) return rc;
+  if (prog->n_funcs != 1 || prog->func[0].kind != KX_AFFINE || geom->in_dtype != KX_F32 || geom->out_dtype != KX_F32)
+    return fail(KX_ERR_UNSUPPORTED, "VJP is implemented for single-function float32 AFFINE programs");
+  if (!g || !dx) return fail(KX_ERR_INVALID, "null device pointer");
+  return launch_generic_vjp_input(*geom, *prog, g, coef_dev, dx, (cudaStream_t)stream);
+}
+
+int64_t kx_vjp_coef_scratch_bytes(const KxGeom* geom, const KxProgram* prog) {
+  if (!geom || !prog) return 0;
+  return generic_vjp_coef_scratch_bytes(*geom, *prog);
+}
+
+int kx_map_vjp_coef(const KxGeom* geom, const KxProgram* prog, const void* x, const void* g, void* scratch,
+                    void* dcoef, void* stream) {
+  int rc = validate(geom, prog);
+  if (rc) return rc;
+  if (prog->n_funcs != 1 || prog->func[0].kind != KX_AFFINE || geom->in_dtype != KX_F32 || geom->out_dtype != KX_F32)
+    return fail(KX_ERR_UNSUPPORTED, "VJP is implemented for single-function float32 AFFINE programs");
+  if (!x || !g || !scratch || !dcoef) return fail(KX_ERR_INVALID, "null device pointer");
+  return launch_generic_vjp_coef(*geom, *prog, x, g, scratch, dcoef, (cudaStream_t)stream);
+}
+
+int64_t kx_scan_state_bytes(const KxGeom* geom) {
+  if (!geom || geom->ndim < 1 || geom->ndim > KX_MAX_DIMS) return 0;
+  return scan_state_elems(*geom) * 4;
+}
+
+int kx_scan(const KxGeom* geom, const KxProgram* prog, const void* in, const void* coef_dev, void* state, void* out,
+            int32_t reverse, void* stream) {
+  int rc = validate(geom, prog);
+  if (rc) return rc;
+  if (geom->in_dtype != geom->out_dtype) return fail(KX_ERR_INVALID, "kscan returns the carried dtype");
+  for (int f = 0; f < prog->n_funcs; ++f)
+    if (prog->func[f].kind == KX_GATHER && prog->func[f].tap_end - prog->func[f].tap_begin != 1)
+      return fail(KX_ERR_INVALID, "scan operation output must be scalar");
+  if (!in || !out || !state) return fail(KX_ERR_INVALID, "null device pointer");
+  cudaStream_t s = (cudaStream_t)stream;
+  rc = try_scan_rowmarch(*geom, *prog, in, coef_dev, out, reverse, s);
+  if (rc != KX_ERR_UNSUPPORTED) return rc;
+  return launch_generic_scan(*geom, *prog, in, coef_dev, state, out, reverse, s);
+}
+
+}  // extern "C"

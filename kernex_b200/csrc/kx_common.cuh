@@ -1,0 +1,101 @@
+// Shared host/device helpers of libkx_b200 (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "../../include/kx_b200.h"
+
+namespace kx {
+
+// ---- thread-local diagnostics (no shared mutable state across host threads) ----
+inline char* err_buf() {
+  static thread_local char buf[512] = {0};
+  return buf;
+}
+inline const char*& last_kernel_name() {
+  static thread_local const char* name = "";
+  return name;
+}
+inline std::atomic<uint64_t>& launch_counter() {
+  static std::atomic<uint64_t> n{0};
+  return n;
+}
+
+inline int fail(int status, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(err_buf(), 512, fmt, ap);
+  va_end(ap);
+  return status;
+}
+
+#define KX_CUDA_CHECK(expr)                                                                 \
+  do {                                                                                      \
+    cudaError_t _e = (expr);                                                                \
+    if (_e != cudaSuccess)                                                                  \
+      return ::kx::fail(KX_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), \
+                        __FILE__, __LINE__);                                                \
+  } while (0)
+
+inline int after_launch(const char* name) {
+  last_kernel_name() = name;
+  launch_counter().fetch_add(1, std::memory_order_relaxed);
+  cudaError_t e = cudaPeekAtLastError();
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return fail(KX_ERR_CUDA, "launch of %s failed: %s", name, cudaGetErrorString(e));
+  }
+  return KX_OK;
+}
+
+inline int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+      n = 148;  // B200
+  }
+  return n;
+}
+
+inline int64_t prod(const int64_t* v, int n) {
+  int64_t p = 1;
+  for (int i = 0; i < n; ++i) p *= v[i];
+  return p;
+}
+
+// ---- device helpers ----
+template <typename T>
+struct Cast;
+template <>
+struct Cast<float> {
+  __device__ __forceinline__ static float from(double v) { return (float)v; }
+};
+template <>
+struct Cast<int32_t> {
+  __device__ __forceinline__ static int32_t from(double v) { return (int32_t)(long long)v; }
+};
+
+// wrap-around int32 multiply-add (signed overflow is UB in C++, defined here)
+__device__ __forceinline__ int32_t mad_wrap(int32_t c, int32_t v, int32_t acc) {
+  return (int32_t)((uint32_t)c * (uint32_t)v + (uint32_t)acc);
+}
+__device__ __forceinline__ float mad_wrap(float c, float v, float acc) { return fmaf(c, v, acc); }
+
+// streaming (read-once / write-once) vector accesses: keep L1 for the halo re-reads
+__device__ __forceinline__ float4 ldg_stream4(const float* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p));
+  return r;
+}
+
+}  // namespace kx

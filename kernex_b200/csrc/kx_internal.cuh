@@ -1,0 +1,76 @@
+// Internal launcher interfaces shared by the translation units of libkx_b200.
+#pragma once
+
+#include "kx_common.cuh"
+
+namespace kx {
+
+// Device-side form of KxProgram with coefficients already in the compute type.
+template <typename TC>
+struct DevProgram {
+  int32_t n_funcs, n_keys, n_taps, ndim;
+  struct Func {
+    int32_t kind, tap_begin, tap_end;
+    TC bias;
+    float post_div;
+  } func[KX_MAX_FUNCS];
+  KxKey key[KX_MAX_KEYS];
+  int16_t tap_off[KX_MAX_TAPS][KX_MAX_DIMS];
+  TC coef[KX_MAX_TAPS];
+};
+
+template <typename TC>
+inline void make_dev_program(const KxProgram& p, int ndim, DevProgram<TC>& d) {
+  d.n_funcs = p.n_funcs;
+  d.n_keys = p.n_keys;
+  d.n_taps = p.n_taps;
+  d.ndim = ndim;
+  for (int f = 0; f < p.n_funcs; ++f) {
+    d.func[f].kind = p.func[f].kind;
+    d.func[f].tap_begin = p.func[f].tap_begin;
+    d.func[f].tap_end = p.func[f].tap_end;
+    d.func[f].bias = (TC)p.func[f].bias;
+    d.func[f].post_div = (float)p.func[f].post_div;
+  }
+  for (int k = 0; k < p.n_keys; ++k) d.key[k] = p.key[k];
+  for (int t = 0; t < p.n_taps; ++t) {
+    for (int a = 0; a < KX_MAX_DIMS; ++a) d.tap_off[t][a] = p.tap_off[t][a];
+    d.coef[t] = (TC)p.coef[t];
+  }
+}
+
+struct MapArgs {
+  KxGeom g;
+  const void* in;
+  const void* coef_dev;
+  void* out;
+  int64_t n_win;               // windows per batch item
+  int64_t in_elems;            // input elements per batch item
+  int64_t out_batch_stride;    // output elements per batch item
+  int64_t coef_batch_stride;
+  int64_t batch;
+  int64_t out_pitch[KX_MAX_DIMS];  // element pitch of the window index along each axis
+  int64_t out_base;
+  int32_t fn_elems;            // 1, or n_taps for KX_GATHER
+};
+
+// generic (any rank <= 4, stride, border, multi-function) kernels -- kx_generic.cu
+int launch_generic_map(const MapArgs& a, const KxProgram& prog, cudaStream_t s);
+int launch_generic_vjp_input(const KxGeom& g, const KxProgram& prog, const void* gout, const void* coef_dev,
+                             void* dx, cudaStream_t s);
+int64_t generic_vjp_coef_scratch_bytes(const KxGeom& g, const KxProgram& prog);
+int launch_generic_vjp_coef(const KxGeom& g, const KxProgram& prog, const void* x, const void* gout,
+                            void* scratch, void* dcoef, cudaStream_t s);
+int64_t scan_state_elems(const KxGeom& g);
+int launch_generic_scan(const KxGeom& g, const KxProgram& prog, const void* in, const void* coef_dev,
+                        void* state, void* out, int reverse, cudaStream_t s);
+
+// fast paths; each returns KX_ERR_UNSUPPORTED (without touching the error string)
+// when its template does not cover the request so the caller can fall through
+int try_stencil2d(const MapArgs& a, const KxProgram& prog, cudaStream_t s);
+int try_stencil3d(const MapArgs& a, const KxProgram& prog, cudaStream_t s);
+int try_patch(const MapArgs& a, const KxProgram& prog, cudaStream_t s);
+int try_scan_rowmarch(const KxGeom& g, const KxProgram& prog, const void* in, const void* coef_dev,
+                      void* out, int reverse, cudaStream_t s);
+
+}  // namespace kx

@@ -178,6 +178,7 @@ class _Program:
                 if not s.bias.is_const:
                     raise UnsupportedStencilError("a device-resident additive term (bias) is not supported")
                 f.bias = float(s.bias.const)
+                f.post_div = float(s.post_div)
                 f.coef_is_int = int(s.integral)
             else:
                 f.coef_is_int = 1

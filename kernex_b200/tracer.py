@@ -99,12 +99,21 @@ class Coef:
 class Affine:
     """Scalar symbolic value ``bias + sum_t coef_t * x[tap_t]`` (taps in patch coords)."""
 
-    __slots__ = ("terms", "bias")
+    __slots__ = ("terms", "bias", "post_div")
     __array_priority__ = 1000
 
-    def __init__(self, terms=None, bias=None):
+    def __init__(self, terms=None, bias=None, post_div=None):
         self.terms: dict[tuple, Coef] = terms or {}
         self.bias: Coef = bias if bias is not None else Coef(0)
+        # ``value / d`` kept as a true division while it is the last operation (window
+        # mean: sum then divide, like jnp.mean); folded into the coefficients otherwise
+        self.post_div = post_div
+
+    def _folded(self):
+        if self.post_div is None:
+            return self
+        c = Coef(1.0 / self.post_div)
+        return Affine({k: v.mul(c) for k, v in self.terms.items()}, self.bias.mul(c))
 
     # -- construction helpers -- #
     @staticmethod
@@ -132,14 +141,15 @@ class Affine:
         return not self.terms
 
     def is_single_tap(self):
-        if len(self.terms) != 1 or not self.bias.is_zero():
+        if len(self.terms) != 1 or not self.bias.is_zero() or self.post_div is not None:
             return False
         (c,) = self.terms.values()
         return c.is_const and c.const == 1
 
     # -- arithmetic -- #
     def _add(self, other, sign):
-        other = Affine.lift(other)
+        other = Affine.lift(other)._folded()
+        self = self._folded()
         terms = dict(self.terms)
         for k, c in other.terms.items():
             terms[k] = terms[k].add(c, sign) if k in terms else (c if sign == 1 else c.scale(-1))
@@ -163,10 +173,11 @@ class Affine:
         return self
 
     def _scale(self, c: Coef):
+        self = self._folded()
         return Affine({k: v.mul(c) for k, v in self.terms.items()}, self.bias.mul(c))
 
     def __mul__(self, o):
-        o = Affine.lift(o)
+        o = Affine.lift(o)._folded()
         if o.is_constant:
             return self._scale(o.bias)
         if self.is_constant:
@@ -182,6 +193,8 @@ class Affine:
         d = o.bias.const
         if d == 0:
             raise ZeroDivisionError("window function divides by zero")
+        if self.post_div is None and self.terms:
+            return Affine(dict(self.terms), self.bias, post_div=float(d))
         return self._scale(Coef(1.0 / d))
 
     def __rtruediv__(self, o):
@@ -510,7 +523,7 @@ def _np_dot(a, b, **kw):
     a, b = _obj(a), _obj(b)
     if a.ndim != 1 or b.ndim != 1:
         raise UnsupportedStencilError("np.dot on the window is only supported for 1-D operands")
-    return SymArray(a * b).sum() if False else _dispatch_ufunc(np.multiply, "__call__", (SymArray(a), SymArray(b)), {}).sum()
+    return _dispatch_ufunc(np.multiply, "__call__", (SymArray(a), SymArray(b)), {}).sum()
 
 
 @_implements(np.tensordot)
@@ -563,6 +576,7 @@ class FuncSpec:
     bias: Coef = field(default_factory=lambda: Coef(0))
     out_shape: tuple = ()           # trailing result axes (gather)
     weak_float: bool = False        # a Python/NumPy float took part (int input -> f32 result)
+    post_div: float = 0.0           # result = (bias + sum) / post_div when non-zero
 
     @property
     def device_coefs(self):
@@ -570,7 +584,7 @@ class FuncSpec:
 
     @property
     def integral(self):
-        return all(c.is_integral() for c in self.coefs) and self.bias.is_integral()
+        return all(c.is_integral() for c in self.coefs) and self.bias.is_integral() and not self.post_div
 
 
 def trace_function(func: Callable, kernel_size, relative: bool, args=(), kwargs=None):
@@ -624,7 +638,8 @@ def classify(result, kernel_size) -> FuncSpec:
             taps.append(t)
             coefs.append(c)
         weak_float = any(isinstance(c.const, float) for c in coefs + [result.bias]) or \
-            any(not c.is_const for c in coefs + [result.bias])
-        return FuncSpec(kind="affine", taps=taps, coefs=coefs, bias=result.bias, weak_float=weak_float)
+            any(not c.is_const for c in coefs + [result.bias]) or result.post_div is not None
+        return FuncSpec(kind="affine", taps=taps, coefs=coefs, bias=result.bias, weak_float=weak_float,
+                        post_div=float(result.post_div or 0.0))
     raise UnsupportedStencilError(
         f"window function returned {type(result).__name__}; expected a scalar / array built from window elements")
