@@ -81,7 +81,12 @@ class KernelInterface:
     def _named(self, func, ksize):
         if self.named_axis is None:
             return func
-        return named_axis_wrapper(kernel_size=ksize, named_axis=self.named_axis)(func)
+        # one wrapper object per (function, kernel size): keeps the engine's plan cache warm
+        cache = self.__dict__.setdefault("_named_cache", {})
+        key = (func, tuple(ksize))
+        if key not in cache:
+            cache[key] = named_axis_wrapper(kernel_size=ksize, named_axis=self.named_axis)(func)
+        return cache[key]
 
     def _wrap_mesh(self, array, *a, **k):
         shape = tuple(array.shape)

@@ -11,6 +11,7 @@ import pytest
 import catalog
 import golden_io
 from oracle import kx_oracle as ko
+from oracle_iface import OracleIface as _OracleIface
 
 OPS = {
     "kernel_map": ko.kernel_map,
@@ -97,31 +98,6 @@ def test_reference_on_shim_cases(kind):
         np.testing.assert_array_equal(got, want, err_msg=str(spec))
         n += 1
     assert n > 100
-
-
-class _OracleIface:
-    """Minimal mesh front-end over the oracle (region assignment -> func_map)."""
-
-    def __init__(self, inplace, kernel_size, padding=0, relative=False, named_axis=None, strides=1):
-        self.inplace, self.kernel_size, self.relative = inplace, kernel_size, relative
-        self.padding, self.named_axis, self.strides = padding, named_axis, strides
-        self.container = {}
-
-    def __setitem__(self, index, func):
-        self.container[func] = [*self.container.get(func, []), index]
-
-    def __call__(self, x):
-        from kernex_b200.named_axis import named_axis_wrapper
-        border = ko.resolve_padding(self.padding, self.kernel_size)
-        fmap = {}
-        for fn, idx in self.container.items():
-            keys = [ko.normalize_index(i, x.shape) for i in idx]
-            if self.named_axis is not None:
-                fn = named_axis_wrapper(self.kernel_size, self.named_axis)(fn)
-            fmap[fn] = keys
-        op = ko.kernel_scan if self.inplace else ko.kernel_map
-        strides = (self.strides,) * x.ndim if isinstance(self.strides, int) else self.strides
-        return op(fmap, x.shape, self.kernel_size, strides, border, self.relative)(x)
 
 
 @pytest.mark.parametrize("name", list(catalog.MESH_SCENARIOS))
