@@ -5,9 +5,6 @@ namespace kx {
 #ifndef KX_HAVE_STENCIL3D
 int try_stencil3d(const MapArgs&, const KxProgram&, cudaStream_t) { return KX_ERR_UNSUPPORTED; }
 #endif
-#ifndef KX_HAVE_PATCH
-int try_patch(const MapArgs&, const KxProgram&, cudaStream_t) { return KX_ERR_UNSUPPORTED; }
-#endif
 #ifndef KX_HAVE_ROWMARCH
 int try_scan_rowmarch(const KxGeom&, const KxProgram&, const void*, const void*, void*, int, cudaStream_t) {
   return KX_ERR_UNSUPPORTED;

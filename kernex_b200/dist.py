@@ -1,0 +1,165 @@
+"""Axis-0 slab decomposition of kmap stencils over several GPUs (one process per GPU).
+
+The reference has no multi-device path beyond ``pmap`` with one *window* per device
+(``kernex/_src/utils.py:28``).  Windows of a kmap are independent, so a large grid
+shards naturally into row slabs: rank ``r`` owns ``rows_per_rank`` rows
+of a global ``(world*rows_per_rank, ...)`` array, and applying a stencil whose window
+spans ``k0`` rows needs ``(k0-1)//2`` rows from the rank above and ``k0//2`` rows from
+the rank below.  Axis-0 halos of a C-contiguous array are themselves contiguous, so they
+travel with plain ``isend/irecv`` (NCCL over NVLink on GPUs, gloo in the CPU tests) --
+no pack kernel.  Per step:
+
+    side stream : post irecv/isend of the halo rows
+    main stream : interior launch (windows that touch no halo)     <- overlaps the exchange
+    main stream : wait for the halos, two O(halo)-row strip launches
+
+:class:`SlabLayout` is pure geometry (testable on CPU), :func:`exchange_halos` is the
+only communication, :class:`SlabStencil` glues them to the CUDA engine.
+"""
+
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import torch
+import torch.distributed as dist
+
+__all__ = ["SlabLayout", "exchange_halos", "SlabStencil"]
+
+
+@dataclass(frozen=True)
+class Piece:
+    """One launch: stencil applied to ``ext[in0:in1]`` with axis-0 border ``border0``
+    writes local output rows ``[out0, out1)``."""
+
+    in0: int
+    in1: int
+    border0: tuple
+    out0: int
+    out1: int
+    needs_halo: bool
+
+
+class SlabLayout:
+    """Geometry of one rank's slab for a stride-1 stencil with ``k0`` rows per window and
+    global axis-0 border ``(lo, hi)``.
+
+    The rank keeps an *extended* buffer ``ext = [top halo | own rows | bottom halo]``
+    (halos absent at the global edges).  Output rows are assigned to the rank that owns
+    the window's centre row; rows produced purely by global padding go to the edge ranks.
+    """
+
+    def __init__(self, rank: int, world: int, rows: int, k0: int, border0=(0, 0)):
+        if rows < k0:
+            raise ValueError(f"rows_per_rank={rows} must be >= the window height {k0}")
+        self.rank, self.world, self.rows, self.k0 = rank, world, rows, k0
+        self.lo, self.hi = int(border0[0]), int(border0[1])
+        if self.lo < 0 or self.hi < 0:
+            raise ValueError("slab decomposition needs a non-negative axis-0 border")
+        self.first, self.last = rank == 0, rank == world - 1
+        self.halo_top = 0 if self.first else (k0 - 1) // 2
+        self.halo_bot = 0 if self.last else k0 // 2
+        self.ext_rows = self.halo_top + rows + self.halo_bot
+        # what the neighbours need from me
+        self.send_up = 0 if self.first else k0 // 2          # my first rows -> bottom halo of rank-1
+        self.send_down = 0 if self.last else (k0 - 1) // 2   # my last rows  -> top halo of rank+1
+        pieces = []
+        lo_eff = self.lo if self.first else 0
+        hi_eff = self.hi if self.last else 0
+        if world == 1:
+            n_out = rows + self.lo + self.hi - k0 + 1
+            pieces.append(Piece(0, rows, (self.lo, self.hi), 0, max(n_out, 0), False))
+            self.pieces, self.out_rows = pieces, max(n_out, 0)
+            return
+        # top strip: every window that touches the top halo (or the global top padding)
+        top_in = self.halo_top + k0 - 1
+        top_cnt = max(top_in + lo_eff - k0 + 1, 0)
+        # bottom strip: windows touching the bottom halo (or the global bottom padding)
+        bot_in = self.halo_bot + k0 - 1
+        bot_cnt = max(bot_in + hi_eff - k0 + 1, 0)
+        mid_cnt = rows - k0 + 1
+        o = 0
+        if top_cnt:
+            pieces.append(Piece(0, top_in, (lo_eff, 0), o, o + top_cnt, not self.first))
+        o += top_cnt
+        pieces.append(Piece(self.halo_top, self.halo_top + rows, (0, 0), o, o + mid_cnt, False))
+        o += mid_cnt
+        if bot_cnt:
+            pieces.append(Piece(self.ext_rows - bot_in, self.ext_rows, (0, hi_eff), o, o + bot_cnt, not self.last))
+        o += bot_cnt
+        self.pieces, self.out_rows = pieces, o
+
+    @property
+    def own(self):
+        return slice(self.halo_top, self.halo_top + self.rows)
+
+
+def exchange_halos(ext: torch.Tensor, layout: SlabLayout, group=None):
+    """Post the halo traffic of one step; returns the list of outstanding requests."""
+    ops = []
+    r, ht, hb, R = layout.rank, layout.halo_top, layout.halo_bot, layout.rows
+    if not layout.first:
+        ops.append(dist.P2POp(dist.irecv, ext[0:ht], r - 1, group))
+        ops.append(dist.P2POp(dist.isend, ext[ht:ht + layout.send_up], r - 1, group))
+    if not layout.last:
+        ops.append(dist.P2POp(dist.irecv, ext[ht + R:ht + R + hb], r + 1, group))
+        ops.append(dist.P2POp(dist.isend, ext[ht + R - layout.send_down:ht + R], r + 1, group))
+    ops = [op for op in ops if op.tensor.numel() > 0]
+    return dist.batch_isend_irecv(ops) if ops else []
+
+
+class SlabStencil:
+    """A kmap applied to a row-slab-decomposed global array on CUDA."""
+
+    def __init__(self, func, kernel_size, relative, rows_per_rank, width=None, device=None, padding="valid",
+                 trailing_shape=None, group=None):
+        from .engine import PreparedMap
+        from .resolve import resolve_padding
+
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.device = device or torch.device("cuda", torch.cuda.current_device())
+        kernel_size = tuple(kernel_size)
+        trailing = tuple(trailing_shape) if trailing_shape is not None else (int(width),)
+        border = resolve_padding(padding, kernel_size)
+        self.layout = SlabLayout(self.rank, self.world, rows_per_rank, kernel_size[0], border[0])
+        L = self.layout
+        self.ext = torch.zeros((L.ext_rows,) + trailing, dtype=torch.float32, device=self.device)
+        strides = (1,) * len(kernel_size)
+        self.maps = []
+        out_trailing = None
+        for p in L.pieces:
+            shape = (p.in1 - p.in0,) + trailing
+            pm = PreparedMap({func: ()}, shape, kernel_size, strides, (p.border0,) + tuple(border[1:]), relative)
+            self.maps.append((p, pm))
+            out_trailing = tuple(pm.out_shape[1:])
+        self.out = torch.empty((L.out_rows,) + out_trailing, dtype=torch.float32, device=self.device)
+        self.local_windows = int(self.out.numel())
+        self.side = torch.cuda.Stream(device=self.device)
+
+    def fill_random(self, generator=None):
+        self.ext[self.layout.own].normal_(generator=generator)
+
+    def set_local(self, rows: torch.Tensor):
+        self.ext[self.layout.own].copy_(rows)
+
+    def step(self):
+        main = torch.cuda.current_stream(self.device)
+        reqs = []
+        if self.world > 1:
+            self.side.wait_stream(main)  # own rows written by earlier work on `main` must be visible
+            with torch.cuda.stream(self.side):
+                reqs = exchange_halos(self.ext, self.layout, self.group)
+        for p, pm in self.maps:          # interior first: overlaps the exchange
+            if not p.needs_halo:
+                pm(self.ext[p.in0:p.in1], out=self.out[p.out0:p.out1])
+        if reqs:
+            with torch.cuda.stream(self.side):
+                for r in reqs:
+                    r.wait()
+            main.wait_stream(self.side)
+        for p, pm in self.maps:
+            if p.needs_halo:
+                pm(self.ext[p.in0:p.in1], out=self.out[p.out0:p.out1])
+        return self.out

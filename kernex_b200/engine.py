@@ -374,6 +374,37 @@ def _run_map(func_map, shape, kernel_size, strides, border, relative, array, a, 
     return arr, out
 
 
+class PreparedMap:
+    """A kmap traced once for a fixed geometry, launched on caller-owned CUDA tensors
+    (optionally into a caller-owned output).  This is what the slab decomposition
+    (``dist.py``) and the pipelined host path use to issue many launches of sub-slabs
+    without re-tracing; it is the same ``kx_map`` call as :func:`kernel_map`."""
+
+    def __init__(self, func_map, shape, kernel_size, strides, border, relative, dtype=None, args=(), kwargs=None):
+        dtype = torch.float32 if dtype is None else dtype
+        self.shape = tuple(int(v) for v in shape)
+        self.in_dtype = dtype
+        plan = _map_plan(func_map, self.shape, tuple(kernel_size), tuple(strides),
+                         tuple(tuple(b) for b in border), relative, _TORCH2KX[dtype], tuple(args), kwargs or {})
+        self.specs, self.device_args, self.out_kx, self.prog, self.geom, self.out_shape = plan
+        self.out_dtype = _KX2TORCH[self.out_kx]
+        self._lib = _lib.load()
+
+    def __call__(self, x, out=None, coef=None):
+        if tuple(x.shape) != self.shape or x.dtype != self.in_dtype or not x.is_cuda or not x.is_contiguous():
+            raise ValueError(f"PreparedMap expects a contiguous CUDA tensor {self.shape} {self.in_dtype}")
+        if out is None:
+            out = torch.empty(self.out_shape, dtype=self.out_dtype, device=x.device)
+        elif tuple(out.shape) != tuple(self.out_shape) or out.dtype != self.out_dtype or not out.is_contiguous():
+            raise ValueError(f"PreparedMap output must be contiguous {self.out_shape} {self.out_dtype}")
+        if coef is None:
+            coef = self.prog.coef_tensor(self.device_args, self.out_dtype, x.device)
+        if out.numel():
+            _lib.check(self._lib.kx_map(C.byref(self.geom), C.byref(self.prog.c), _ptr(x), _ptr(coef), 0, _ptr(out),
+                                        1, _stream_ptr(x.device)))
+        return out
+
+
 def kernel_map(func_map: dict, shape, kernel_size, strides, border, relative: bool = False,
                map_kind: str = "vmap", map_kwargs: dict | None = None) -> Callable:
     """``kernex.kernel_map`` (``_src/map.py:61-124``).  ``map_kind`` selects a JAX
@@ -388,10 +419,28 @@ def kernel_map(func_map: dict, shape, kernel_size, strides, border, relative: bo
     _validate(shape, kernel_size, strides, border)
 
     def call(array, *a, **k):
+        piped = _try_host_pipeline(func_map, shape, kernel_size, strides, border, relative, array, a, k)
+        if piped is not None:
+            return piped
         arr, out = _run_map(func_map, shape, kernel_size, strides, border, relative, array, a, k)
         return arr.give_back(out)
 
     return call
+
+
+def _try_host_pipeline(func_map, shape, kernel_size, strides, border, relative, array, a, k):
+    """Large pinned host arrays: overlap H2D / kernel / D2H over row slabs (hostpipe.py)."""
+    if isinstance(array, torch.Tensor) or not isinstance(array, np.ndarray) or array.nbytes < (64 << 20):
+        return None
+    from . import hostpipe
+    if tuple(array.shape) != tuple(shape) or not array.flags.c_contiguous:
+        return None
+    t_host = torch.from_numpy(array)
+    if not hostpipe.eligible(array, t_host, strides, a, k):
+        return None
+    _require_cuda()
+    out = hostpipe.pipelined_map(func_map, shape, kernel_size, strides, border, relative, t_host)
+    return None if out is None else out.numpy()
 
 
 def offset_kernel_map(func_map: dict, shape, kernel_size, strides, offset, relative: bool = False,
