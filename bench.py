@@ -102,6 +102,14 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def host_threads():
+    """All host threads this process may use (torchrun exports OMP_NUM_THREADS=1: ignore it)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
+
+
 def host_grid(rows, seed=0):
     rng = np.random.default_rng(seed)
     return rng.standard_normal((rows, N), dtype=np.float32)
@@ -110,14 +118,14 @@ def host_grid(rows, seed=0):
 def cpu_baseline(x_host, repeats=3):
     """Oracle port (OpenMP C restatement of the reference algorithm) on the host cores."""
     from oracle import kx_oracle_c as kc
-    threads = kc.max_threads()
+    threads = host_threads()
     out = np.empty((x_host.shape[0] - 2, N - 2), dtype=np.float32)
     ksz, st, bd = (3, 3), (1, 1), ((0, 0), (0, 0))
-    kc.affine_map(x_host, ksz, st, bd, TAPS, COEFS, out=out)  # warm-up (page faults)
+    kc.affine_map(x_host, ksz, st, bd, TAPS, COEFS, out=out, nthreads=threads)  # warm-up (page faults)
     best = float("inf")
     for _ in range(repeats):
         t0 = time.perf_counter()
-        kc.affine_map(x_host, ksz, st, bd, TAPS, COEFS, out=out)
+        kc.affine_map(x_host, ksz, st, bd, TAPS, COEFS, out=out, nthreads=threads)
         best = min(best, time.perf_counter() - t0)
     return out.size / best / 1e9, threads, out
 
@@ -131,13 +139,13 @@ def run_reference(args):
     out = np.empty((N - 2, N - 2), dtype=np.float32)
     ksz, st, bd = (3, 3), (1, 1), ((0, 0), (0, 0))
     for _ in range(max(args.warmup, 1)):
-        kc.affine_map(x, ksz, st, bd, TAPS, COEFS, out=out)
+        kc.affine_map(x, ksz, st, bd, TAPS, COEFS, out=out, nthreads=host_threads())
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        kc.affine_map(x, ksz, st, bd, TAPS, COEFS, out=out)
+        kc.affine_map(x, ksz, st, bd, TAPS, COEFS, out=out, nthreads=host_threads())
     dt = time.perf_counter() - t0
     glups = out.size * args.steps / dt / 1e9
-    threads = kc.max_threads()
+    threads = host_threads()
     line = {
         "impl": "reference", "metric": METRIC, "value": glups, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,

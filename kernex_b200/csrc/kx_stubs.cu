@@ -2,9 +2,6 @@
 // generic kernels run.  Each is replaced by a real translation unit as it lands.
 #include "kx_internal.cuh"
 namespace kx {
-#ifndef KX_HAVE_STENCIL3D
-int try_stencil3d(const MapArgs&, const KxProgram&, cudaStream_t) { return KX_ERR_UNSUPPORTED; }
-#endif
 #ifndef KX_HAVE_ROWMARCH
 int try_scan_rowmarch(const KxGeom&, const KxProgram&, const void*, const void*, void*, int, cudaStream_t) {
   return KX_ERR_UNSUPPORTED;

@@ -154,12 +154,14 @@ class SlabStencil:
         for p, pm in self.maps:          # interior first: overlaps the exchange
             if not p.needs_halo:
                 pm(self.ext[p.in0:p.in1], out=self.out[p.out0:p.out1])
-        if reqs:
-            with torch.cuda.stream(self.side):
-                for r in reqs:
-                    r.wait()
+        # the O(halo)-row strips run on the side stream right behind the receives, i.e.
+        # concurrently with the tail of the interior launch; `main` joins at the end
+        with torch.cuda.stream(self.side):
+            for r in reqs:
+                r.wait()
+            for p, pm in self.maps:
+                if p.needs_halo:
+                    pm(self.ext[p.in0:p.in1], out=self.out[p.out0:p.out1])
+        if self.world > 1:
             main.wait_stream(self.side)
-        for p, pm in self.maps:
-            if p.needs_halo:
-                pm(self.ext[p.in0:p.in1], out=self.out[p.out0:p.out1])
         return self.out

@@ -127,3 +127,103 @@ def test_laplacian_full_size_properties(kex):
         _check_affine(y[r0:r0 + 64].cpu().numpy(), band, (3, 3), (1, 1), ((0, 0), (0, 0)), taps, coefs)
     del x, y
     torch.cuda.empty_cache()
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_stencil3d_random_geometry(kex, seed):
+    rng = np.random.default_rng(3000 + seed)
+    ks = [(3, 3, 3), (2, 2, 2), (3, 3, 3), (5, 5, 5)][seed % 4]
+    star = seed % 4 in (2, 3)
+    d = int(rng.integers(ks[0], 14))
+    h = int(rng.integers(ks[1], 40))
+    w = int(rng.integers(ks[2], 150))
+    if seed % 3 == 0:
+        w = (w // 4 + 1) * 4
+    border = tuple((int(rng.integers(-1, 3)), int(rng.integers(-1, 3))) for _ in range(3))
+    if any(o <= 0 for o in ko.output_shape((d, h, w), ks, (1, 1, 1), border)):
+        border = ((0, 0),) * 3
+    c = tuple((k - 1) // 2 for k in ks)
+    all_taps = list(itertools.product(*[range(k) for k in ks]))
+    if star:
+        taps = [t for t in all_taps if sum(int(t[i] == c[i]) for i in range(3)) >= 2]
+    else:
+        taps = [t for t in all_taps if rng.random() < 0.8] or [c]
+    if seed % 2:
+        x = rng.standard_normal((d, h, w)).astype(np.float32)
+        coefs = [float(v) for v in rng.standard_normal(len(taps))]
+        bias = -0.5
+    else:
+        x = rng.integers(-1000, 1000, (d, h, w)).astype(np.int32)
+        coefs = [int(v) or 2 for v in rng.integers(-9, 10, len(taps))]
+        bias = 0
+
+    def fn(v):
+        acc = bias
+        for t, cf in zip(taps, coefs):
+            acc = acc + cf * v[t]
+        return acc
+
+    got = kex.kernel_map({fn: ()}, (d, h, w), ks, (1, 1, 1), border, False)(x)
+    assert _last_kernel() == "stencil3d_kernel"
+    _check_affine(got, x, ks, (1, 1, 1), border, taps, coefs, bias)
+
+
+def test_conv_as_kmap_config3a_shape(kex):
+    """README conv example / BASELINE config 3a at reduced size: kernel (C,3,3), padding
+    (valid, same, same), runtime weights on the device, vs the oracle (fp32 tolerance)."""
+    rng = np.random.default_rng(11)
+    C, H, W = 3, 70, 132
+    x = rng.standard_normal((C, H, W)).astype(np.float32)
+    w = rng.standard_normal((C, 3, 3)).astype(np.float32)
+    conv = kex.kmap(kernel_size=(C, 3, 3), padding=("valid", "same", "same"))(lambda v, w: np.sum(v * w))
+    taps = list(itertools.product(range(C), range(3), range(3)))
+    b = ((0, 0), (1, 1), (1, 1))
+    got_host_w = conv(x, w)                                   # weights known on the host
+    assert _last_kernel() == "stencil3d_kernel" and got_host_w.shape == (1, H, W)
+    _check_affine(got_host_w, x, (C, 3, 3), (1, 1, 1), b, taps, [float(w[t]) for t in taps])
+    got_dev_w = conv(torch.from_numpy(x).cuda(), torch.from_numpy(w).cuda())   # device weights
+    assert _last_kernel() == "stencil3d_kernel"
+    _check_affine(got_dev_w.cpu().numpy(), x, (C, 3, 3), (1, 1, 1), b, taps, [float(w[t]) for t in taps])
+
+
+def test_patch_extraction_fast_path(kex):
+    """README get_3x3_patches / BASELINE config 3b semantics, bit exact."""
+    rng = np.random.default_rng(5)
+    for shape, ks, pad in [((37, 53), (3, 3), "same"), ((64, 64), (3, 3), "valid"), ((1000,), (3,), "same"),
+                           ((9, 10, 11), (2, 3, 2), "same")]:
+        x = rng.standard_normal(shape).astype(np.float32)
+        for relative in (False, True):
+            got = kex.kmap(kernel_size=ks, padding=pad, relative=relative)(lambda v: v)(x)
+            assert _last_kernel() == "patch_kernel"
+            border = ko.resolve_padding(pad, ks)
+            want = ko.patch_map(x, ks, (1,) * len(ks), border, relative)
+            np.testing.assert_array_equal(got, want)
+    xi = np.arange(1, 26, dtype=np.int32).reshape(5, 5)
+    p = kex.kmap(kernel_size=(3, 3), padding="same")(lambda v: v)(xi)
+    np.testing.assert_array_equal(p[0, 0], [[0, 0, 0], [0, 1, 2], [0, 6, 7]])   # README.md:183-186
+
+
+def test_weight_gradient_matches_oracle(kex):
+    """tests/test_interface.py:345-348: d/dw sum(conv(x, w)) and d/dx, fp32, atol 1e-3 there."""
+    rng = np.random.default_rng(9)
+    C, H = 3, 16
+    x = rng.standard_normal((C, H, H)).astype(np.float32)
+    w = rng.standard_normal((C, 3, 3)).astype(np.float32)
+    xt = torch.from_numpy(x).cuda().requires_grad_()
+    wt = torch.from_numpy(w).cuda().requires_grad_()
+    conv = kex.kmap(kernel_size=(C, 3, 3), padding=("valid", "same", "same"))(lambda v, w: np.sum(v * w))
+    g = torch.from_numpy(rng.standard_normal((1, H, H)).astype(np.float32)).cuda()
+    y = conv(xt, wt)
+    (y * g).sum().backward()
+    b = ((0, 0), (1, 1), (1, 1))
+    dw = ko.weight_grad(x, g.cpu().numpy(), (C, 3, 3), (1, 1, 1), b)
+    np.testing.assert_allclose(wt.grad.cpu().numpy(), dw, rtol=1e-4, atol=1e-4)
+    # dx = flipped-tap stencil of g: compare against finite structure via float64 numpy
+    dx = np.zeros_like(x, dtype=np.float64)
+    gp = np.pad(g.cpu().numpy()[0].astype(np.float64), 1)
+    for c in range(C):
+        for a in range(3):
+            for bb in range(3):
+                # x[c, i+a-1, j+bb-1] contributes w[c,a,bb] to out[i,j]
+                dx[c] += w[c, a, bb] * gp[2 - a:2 - a + H, 2 - bb:2 - bb + H]
+    np.testing.assert_allclose(xt.grad.cpu().numpy(), dx, rtol=1e-4, atol=1e-4)
