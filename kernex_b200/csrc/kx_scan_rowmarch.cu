@@ -1,0 +1,273 @@
+// Fast path for kscan: 2-D time-marching stencils (README.md:231-266 linear convection,
+// BASELINE config 4).
+//
+// The reference runs kscan as ONE lax.scan over all nt*nx windows carrying the padded
+// array (kernex/_src/scan.py:97-113).  When every window function reads only the row
+// ABOVE the cell it writes (centre-relative row offset -1) the sweep order inside a row
+// is irrelevant: row n is a pure function of row n-1, which was fully produced earlier
+// in the sweep, and -- with 'same'-style borders on both axes -- the input array is never
+// read at all (row -1 and the side columns are the zero pad, every other cell is
+// overwritten before it is read).  The kernel is then WRITE-only: 4 B per lattice update.
+//
+// Temporal blocking: one launch advances kT rows.  A block owns a contiguous span of
+// columns plus a redundant halo of kT*R columns per side that shrinks by R per row (the
+// dependency cone), so blocks never talk to each other inside a launch; the next launch
+// re-reads only the last row.  Inside a block each thread keeps its 4*G columns of the
+// current row in registers, rows are exchanged through a double-buffered shared-memory
+// line (one barrier per row), and each row is written with 128-bit streaming stores.
+//
+// F[slice] = fn regions (kernex/_src/utils.py:338-382 selection rule) are resolved per
+// thread into per-column coefficient registers (bias, a[-2..2]) whenever the marching row
+// crosses a row breakpoint of the region keys, so the inner loop is branch-free FMAs and
+// constants (boundary / initial conditions) are just "all a = 0".
+#include "kx_internal.cuh"
+
+namespace kx {
+
+namespace {
+
+constexpr int kRMThreads = 256;
+constexpr int kT = 64;          // rows per launch
+constexpr int kMaxR = 2;        // |column offset| supported
+constexpr int kMaxRowIv = 16;
+
+struct RMFunc {
+  float bias;
+  float a[2 * kMaxR + 1];       // coefficient of prev[i + d], d = -kMaxR..kMaxR
+};
+
+struct RMArgs {
+  float* out;
+  int64_t nx;
+  int nt;
+  int n0, n1;                   // rows advanced by this launch
+  int own;                      // owned columns per block (multiple of 4)
+  int halo_l, halo_r;           // redundant columns per side (multiples of 4)
+  int n_funcs, n_keys;
+  int n_breaks;
+  int row_break[kMaxRowIv + 1]; // sorted row breakpoints, row_break[0] = 0
+  RMFunc func[KX_MAX_FUNCS];
+  KxKey key[KX_MAX_KEYS];
+};
+
+__device__ __forceinline__ int rm_select(const RMArgs& a, int64_t row, int64_t col) {
+  if (a.n_funcs <= 1) return 0;
+  for (int k = a.n_keys - 1; k >= 0; --k) {
+    const KxKey& key = a.key[k];
+    bool ok = true;
+    for (int d = 0; d < key.n_items; ++d) {
+      const KxKeyItem& it = key.item[d];
+      const int64_t c = d == 0 ? row : col;
+      bool m = true;
+      if (it.kind == KX_KEY_EQ) m = (c == it.a);
+      else if (it.kind == KX_KEY_RANGE) m = (it.a <= c) && (c < it.b);
+      else if (it.kind == KX_KEY_RANGE_STEP) m = (it.a <= c) && (c < it.b) && (c % it.step == 0);
+      ok = ok && m;
+    }
+    if (ok) return key.func;
+  }
+  return 0;
+}
+
+template <int G, int RL, int RR>
+__global__ void __launch_bounds__(kRMThreads)
+scan_rowmarch_kernel(const __grid_constant__ RMArgs a) {
+  constexpr int SPAN = kRMThreads * 4 * G;
+  __shared__ __align__(16) float line[2][SPAN + 8];   // +4 guard floats on each side
+  const int tid = threadIdx.x;
+  const int64_t span0 = (int64_t)blockIdx.x * a.own - a.halo_l;  // first processed column
+  const int64_t own0 = (int64_t)blockIdx.x * a.own;
+  const int64_t own1 = min(own0 + a.own, a.nx);
+
+  float cur[G][4];
+  float cb[G][4], cl2[G][4], cl1[G][4], cc[G][4], cr1[G][4], cr2[G][4];
+  (void)cl2; (void)cr2; (void)cl1; (void)cr1;
+
+  // previous row: zero pad for n0 == 0, else the last row of the previous launch
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+    const int64_t c0 = span0 + (int64_t)g * kRMThreads * 4 + tid * 4;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) cur[g][e] = 0.f;
+    if (a.n0 > 0) {
+      const float* prow = a.out + (int64_t)(a.n0 - 1) * a.nx;
+      if (c0 >= 0 && c0 + 3 < a.nx && ((a.nx & 3) == 0)) {
+        const float4 v = *reinterpret_cast<const float4*>(prow + c0);
+        cur[g][0] = v.x; cur[g][1] = v.y; cur[g][2] = v.z; cur[g][3] = v.w;
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (c0 + e >= 0 && c0 + e < a.nx) cur[g][e] = prow[c0 + e];
+      }
+    }
+  }
+  if (tid < 4) {
+    line[0][tid] = line[1][tid] = 0.f;
+    line[0][SPAN + 4 + tid] = line[1][SPAN + 4 + tid] = 0.f;
+  }
+
+  int iv = 0;
+  while (iv + 1 < a.n_breaks && a.row_break[iv + 1] <= a.n0) ++iv;
+  int next_break = a.n0;   // force a coefficient refresh at the first row
+
+  for (int n = a.n0; n < a.n1; ++n) {
+    if (n == next_break) {
+      while (iv + 1 < a.n_breaks && a.row_break[iv + 1] <= n) ++iv;
+      next_break = (iv + 1 < a.n_breaks) ? a.row_break[iv + 1] : 0x7fffffff;
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int64_t c = span0 + (int64_t)g * kRMThreads * 4 + tid * 4 + e;
+          RMFunc f;
+          if (c < 0 || c >= a.nx) {      // pad column: a never-written zero
+            f.bias = 0.f;
+#pragma unroll
+            for (int d = 0; d < 2 * kMaxR + 1; ++d) f.a[d] = 0.f;
+          } else {
+            f = a.func[rm_select(a, n, c)];
+          }
+          cb[g][e] = f.bias;
+          cl2[g][e] = f.a[0]; cl1[g][e] = f.a[1]; cc[g][e] = f.a[2]; cr1[g][e] = f.a[3]; cr2[g][e] = f.a[4];
+        }
+      }
+    }
+    // publish the previous row, then read the neighbours across thread boundaries
+    float* buf = line[n & 1] + 4;
+#pragma unroll
+    for (int g = 0; g < G; ++g)
+      *reinterpret_cast<float4*>(buf + g * kRMThreads * 4 + tid * 4) =
+          make_float4(cur[g][0], cur[g][1], cur[g][2], cur[g][3]);
+    __syncthreads();
+    float nxt[G][4];
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      const int base = g * kRMThreads * 4 + tid * 4;
+      float w[4 + 2 * kMaxR];  // prev[base-2 .. base+5]
+      w[2] = cur[g][0]; w[3] = cur[g][1]; w[4] = cur[g][2]; w[5] = cur[g][3];
+      w[0] = (RL >= 2) ? buf[base - 2] : 0.f;
+      w[1] = (RL >= 1) ? buf[base - 1] : 0.f;
+      w[6] = (RR >= 1) ? buf[base + 4] : 0.f;
+      w[7] = (RR >= 2) ? buf[base + 5] : 0.f;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float v = cb[g][e];
+        if (RL >= 2) v = fmaf(cl2[g][e], w[e + 0], v);
+        if (RL >= 1) v = fmaf(cl1[g][e], w[e + 1], v);
+        v = fmaf(cc[g][e], w[e + 2], v);
+        if (RR >= 1) v = fmaf(cr1[g][e], w[e + 3], v);
+        if (RR >= 2) v = fmaf(cr2[g][e], w[e + 4], v);
+        nxt[g][e] = v;
+      }
+    }
+    float* orow = a.out + (int64_t)n * a.nx;
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      const int64_t c0 = span0 + (int64_t)g * kRMThreads * 4 + tid * 4;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) cur[g][e] = nxt[g][e];
+      if (c0 >= own0 && c0 < own1) {
+        if (c0 + 3 < own1 && ((a.nx & 3) == 0)) {
+          __stcs(reinterpret_cast<float4*>(orow + c0), make_float4(nxt[g][0], nxt[g][1], nxt[g][2], nxt[g][3]));
+        } else {
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            if (c0 + e < own1) orow[c0 + e] = nxt[g][e];
+        }
+      }
+    }
+  }
+}
+
+template <int G>
+int launch_g(const RMArgs& a, int rl, int rr, unsigned blocks, cudaStream_t s) {
+  if (rl <= 1 && rr == 0) scan_rowmarch_kernel<G, 1, 0><<<blocks, kRMThreads, 0, s>>>(a);
+  else if (rl <= 1 && rr <= 1) scan_rowmarch_kernel<G, 1, 1><<<blocks, kRMThreads, 0, s>>>(a);
+  else scan_rowmarch_kernel<G, 2, 2><<<blocks, kRMThreads, 0, s>>>(a);
+  return after_launch("scan_rowmarch_kernel");
+}
+
+bool add_break(int* br, int& n, int64_t v, int nt) {
+  if (v <= 0 || v >= nt) return true;
+  for (int i = 0; i < n; ++i)
+    if (br[i] == (int)v) return true;
+  if (n >= kMaxRowIv) return false;
+  br[n++] = (int)v;
+  return true;
+}
+
+}  // namespace
+
+int try_scan_rowmarch(const KxGeom& g, const KxProgram& p, const void* in, const void* coef_dev, void* out,
+                      int reverse, cudaStream_t s) {
+  (void)in;
+  if (g.ndim != 2 || g.in_dtype != KX_F32 || reverse || coef_dev) return KX_ERR_UNSUPPORTED;
+  const int c0 = (g.ksize[0] - 1) / 2, c1 = (g.ksize[1] - 1) / 2;
+  // every in-bounds cell is a window centre exactly once ('same'-style borders), stride 1
+  for (int d = 0; d < 2; ++d) {
+    const int c = (g.ksize[d] - 1) / 2;
+    if (g.stride[d] != 1 || g.lo[d] != c || g.out_shape[d] != g.in_shape[d]) return KX_ERR_UNSUPPORTED;
+  }
+  if (g.in_shape[0] > 0x7ffffff0 || g.in_shape[0] < 1 || g.in_shape[1] < 1) return KX_ERR_UNSUPPORTED;
+  static thread_local RMArgs a;
+  memset(&a, 0, sizeof(a));
+  int rl = 0, rr = 0;
+  for (int f = 0; f < p.n_funcs; ++f) {
+    const KxFunc& fn = p.func[f];
+    if (fn.kind != KX_AFFINE || fn.post_div != 0.0) return KX_ERR_UNSUPPORTED;
+    a.func[f].bias = (float)fn.bias;
+    for (int t = fn.tap_begin; t < fn.tap_end; ++t) {
+      const int d0 = p.tap_off[t][0] - c0, d1 = p.tap_off[t][1] - c1;
+      if (d0 != -1 || d1 < -kMaxR || d1 > kMaxR) return KX_ERR_UNSUPPORTED;  // must read the row above only
+      a.func[f].a[d1 + kMaxR] += (float)p.coef[t];
+      if (-d1 > rl) rl = -d1;
+      if (d1 > rr) rr = d1;
+    }
+  }
+  const int nt = (int)g.in_shape[0];
+  a.n_breaks = 1;
+  a.row_break[0] = 0;
+  for (int k = 0; k < p.n_keys; ++k) {
+    a.key[k] = p.key[k];
+    if (p.key[k].n_items < 1) continue;
+    const KxKeyItem& it = p.key[k].item[0];
+    bool ok = true;
+    if (it.kind == KX_KEY_EQ) ok = add_break(a.row_break, a.n_breaks, it.a, nt) && add_break(a.row_break, a.n_breaks, it.a + 1, nt);
+    else if (it.kind == KX_KEY_RANGE || (it.kind == KX_KEY_RANGE_STEP && (it.step == 1 || it.step == -1)))
+      ok = add_break(a.row_break, a.n_breaks, it.a, nt) && add_break(a.row_break, a.n_breaks, it.b, nt);
+    else if (it.kind == KX_KEY_RANGE_STEP) return KX_ERR_UNSUPPORTED;  // strided row keys: generic path
+    if (!ok) return KX_ERR_UNSUPPORTED;
+  }
+  for (int i = 1; i < a.n_breaks; ++i)  // insertion sort
+    for (int j = i; j > 0 && a.row_break[j] < a.row_break[j - 1]; --j) {
+      const int t = a.row_break[j];
+      a.row_break[j] = a.row_break[j - 1];
+      a.row_break[j - 1] = t;
+    }
+  a.n_funcs = p.n_funcs;
+  a.n_keys = p.n_keys;
+  a.out = (float*)out;
+  a.nx = g.in_shape[1];
+  a.nt = nt;
+  a.halo_l = ((kT * rl + 3) / 4) * 4;
+  a.halo_r = ((kT * rr + 3) / 4) * 4;
+  // pick G (columns per thread = 4G) so that the grid fills the machine in whole waves
+  const int64_t nx = a.nx;
+  int G = 2;
+  if (nx <= 2048) G = 1;
+  const int span = kRMThreads * 4 * G;
+  int own = span - a.halo_l - a.halo_r;
+  if (own < 256) return KX_ERR_UNSUPPORTED;
+  a.own = own;
+  const int64_t blocks = (nx + own - 1) / own;
+  if (blocks > 0x7fffffff) return KX_ERR_UNSUPPORTED;
+  for (int n0 = 0; n0 < nt; n0 += kT) {
+    a.n0 = n0;
+    a.n1 = n0 + kT < nt ? n0 + kT : nt;
+    int rc = (G == 1) ? launch_g<1>(a, rl, rr, (unsigned)blocks, s) : launch_g<2>(a, rl, rr, (unsigned)blocks, s);
+    if (rc) return rc;
+  }
+  return KX_OK;
+}
+
+}  // namespace kx

@@ -1,10 +1,3 @@
-// Placeholders for fast paths that are not written yet: they decline every request so the
-// generic kernels run.  Each is replaced by a real translation unit as it lands.
+// Intentionally empty: every fast path declared in kx_internal.cuh now has a real
+// translation unit (kx_stencil2d.cu, kx_stencil3d.cu, kx_patch.cu, kx_scan_rowmarch.cu).
 #include "kx_internal.cuh"
-namespace kx {
-#ifndef KX_HAVE_ROWMARCH
-int try_scan_rowmarch(const KxGeom&, const KxProgram&, const void*, const void*, void*, int, cudaStream_t) {
-  return KX_ERR_UNSUPPORTED;
-}
-#endif
-}  // namespace kx
