@@ -134,6 +134,7 @@ stencil3d_kernel(const __grid_constant__ S3Args<T> a) {
   for (int kz = 0; kz < KZ - 1; ++kz) load_plane(z0 - a.lz + kz, q[kz]);
 
   for (int z = z0; z < z1; ++z) {
+    // (a one-plane register prefetch was tried: 124 registers, 2 blocks/SM, 8 % slower)
     load_plane(z - a.lz + KZ - 1, q[KZ - 1]);
 #pragma unroll
     for (int ry = 0; ry < RY; ++ry) {
@@ -180,10 +181,15 @@ int launch_kkk(S3Args<T>& a, int batch, bool vec, cudaStream_t s) {
   const int tiles_y = (a.hout + kTYB * RY - 1) / (kTYB * RY);
   // enough blocks for a few waves (2 resident blocks / SM), but long z marches for reuse
   const int64_t cols = (int64_t)tiles_x * tiles_y * batch;
-  const int64_t want = (int64_t)sm_count() * 2 * 4;
+  // >= ~16 waves of 2 resident blocks per SM keeps the last partial wave under a few percent
+  const int64_t want = (int64_t)sm_count() * 2 * 16;
   int nzc = (int)((want + cols - 1) / cols);
   if (nzc < 1) nzc = 1;
   int zc = (a.dout + nzc - 1) / nzc;
+  // short z chunks keep concurrently resident blocks on a compact slab so tile halos hit L2
+  // (benchmarks/exp3d.cu: 32-64 planes beat full-depth marches by 40 %)
+  static const int zc_cap = getenv("KX_S3_ZC") ? atoi(getenv("KX_S3_ZC")) : 64;
+  if (zc > zc_cap && zc_cap > 0) zc = zc_cap;
   if (zc < 16) zc = a.dout < 16 ? a.dout : 16;
   nzc = (a.dout + zc - 1) / zc;
   a.zc = zc;
@@ -270,6 +276,11 @@ int try_stencil3d(const MapArgs& m, const KxProgram& p, cudaStream_t s) {
   if (g.ksize[g.ndim - 3] == 1) return KX_ERR_UNSUPPORTED;  // a 2-D problem: stencil2d folds it
   const int64_t batch = m.batch * lead;
   if (m.coef_dev && batch > 1 && m.coef_batch_stride != 0) return KX_ERR_UNSUPPORTED;
+  if (batch <= 65535) {
+    // 7-point-style stars take the cp.async shared-memory ring (kx_stencil3d_star.cu)
+    const int rc = try_stencil3d_star(m, p, batch, s);
+    if (rc != KX_ERR_UNSUPPORTED) return rc;
+  }
   if (g.in_dtype == KX_F32) return run3<float>(m, p, batch, s);
   if (g.in_dtype == KX_I32 && p.func[0].coef_is_int) return run3<int32_t>(m, p, batch, s);
   return KX_ERR_UNSUPPORTED;

@@ -164,7 +164,7 @@ def test_stencil3d_random_geometry(kex, seed):
         return acc
 
     got = kex.kernel_map({fn: ()}, (d, h, w), ks, (1, 1, 1), border, False)(x)
-    assert _last_kernel() == "stencil3d_kernel"
+    assert _last_kernel() in ("stencil3d_kernel", "stencil3d_star_kernel")
     _check_affine(got, x, ks, (1, 1, 1), border, taps, coefs, bias)
 
 
