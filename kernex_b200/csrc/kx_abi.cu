@@ -72,6 +72,53 @@ void fill_map_args(MapArgs& a, const KxGeom& g, const KxProgram& p, const void* 
   a.out_base = 0;
 }
 
+// fast templates first, the generic kernel as the universal backstop
+int dispatch_map(const MapArgs& a, const KxProgram& prog, cudaStream_t s) {
+  int rc = try_stencil2d(a, prog, s);
+  if (rc != KX_ERR_UNSUPPORTED) return rc;
+  rc = try_conv2d(a, prog, s);
+  if (rc != KX_ERR_UNSUPPORTED) return rc;
+  rc = try_stencil3d(a, prog, s);
+  if (rc != KX_ERR_UNSUPPORTED) return rc;
+  rc = try_patch2d(a, prog, s);
+  if (rc != KX_ERR_UNSUPPORTED) return rc;
+  rc = try_patch(a, prog, s);
+  if (rc != KX_ERR_UNSUPPORTED) return rc;
+  return launch_generic_map(a, prog, s);
+}
+
+// The input-VJP of a stride-1 AFFINE stencil is itself an AFFINE stencil of the cotangent:
+//   dx[i] = sum_t c_t * g[i + lo - tap_t]  =  stencil(g) with taps (k-1-tap_t), borders (k-1-lo, k-1-hi)
+// so it runs on the same roofline-tuned kernels as the forward pass.
+bool transpose_program(const KxGeom& g, const KxProgram& p, KxGeom& gt, KxProgram& pt) {
+  for (int d = 0; d < g.ndim; ++d)
+    if (g.stride[d] != 1) return false;
+  memset(&gt, 0, sizeof(gt));
+  gt.ndim = g.ndim;
+  gt.in_dtype = gt.out_dtype = KX_F32;
+  for (int d = 0; d < g.ndim; ++d) {
+    gt.in_shape[d] = g.out_shape[d];
+    gt.out_shape[d] = g.in_shape[d];
+    gt.ksize[d] = g.ksize[d];
+    gt.stride[d] = 1;
+    gt.lo[d] = g.ksize[d] - 1 - g.lo[d];
+    gt.hi[d] = g.ksize[d] - 1 - g.hi[d];
+  }
+  memset(&pt, 0, sizeof(pt));
+  pt.n_funcs = 1;
+  pt.n_taps = p.func[0].tap_end - p.func[0].tap_begin;
+  pt.func[0] = p.func[0];
+  pt.func[0].tap_begin = 0;
+  pt.func[0].tap_end = pt.n_taps;
+  pt.func[0].bias = 0.0;
+  for (int t = 0; t < pt.n_taps; ++t) {
+    const int src = p.func[0].tap_begin + t;
+    for (int d = 0; d < g.ndim; ++d) pt.tap_off[t][d] = (int16_t)(g.ksize[d] - 1 - p.tap_off[src][d]);
+    pt.coef[t] = p.coef[src];
+  }
+  return true;
+}
+
 }  // namespace
 
 extern "C" {
@@ -90,14 +137,7 @@ int kx_map(const KxGeom* geom, const KxProgram* prog, const void* in, const void
   MapArgs a;
   fill_map_args(a, *geom, *prog, in, coef_dev, coef_batch_stride, out, batch);
   if (a.n_win == 0) return KX_OK;
-  cudaStream_t s = (cudaStream_t)stream;
-  rc = try_stencil2d(a, *prog, s);
-  if (rc != KX_ERR_UNSUPPORTED) return rc;
-  rc = try_stencil3d(a, *prog, s);
-  if (rc != KX_ERR_UNSUPPORTED) return rc;
-  rc = try_patch(a, *prog, s);
-  if (rc != KX_ERR_UNSUPPORTED) return rc;
-  return launch_generic_map(a, *prog, s);
+  return dispatch_map(a, *prog, (cudaStream_t)stream);
 }
 
 int kx_map_offset(const KxGeom* geom, const KxProgram* prog, const void* in, const void* coef_dev,
@@ -134,12 +174,22 @@ int kx_map_vjp_input(const KxGeom* geom, const KxProgram* prog, const void* g, c
   if (prog->n_funcs != 1 || prog->func[0].kind != KX_AFFINE || geom->in_dtype != KX_F32 || geom->out_dtype != KX_F32)
     return fail(KX_ERR_UNSUPPORTED, "VJP is implemented for single-function float32 AFFINE programs");
   if (!g || !dx) return fail(KX_ERR_INVALID, "null device pointer");
+  static thread_local KxGeom gt;
+  static thread_local KxProgram pt;
+  const int first = prog->func[0].tap_begin;
+  if (transpose_program(*geom, *prog, gt, pt) && prod(gt.out_shape, gt.ndim) > 0 && prod(gt.in_shape, gt.ndim) > 0) {
+    MapArgs a;
+    const void* cd = coef_dev ? (const void*)((const float*)coef_dev + first) : nullptr;
+    fill_map_args(a, gt, pt, g, cd, 0, dx, 1);
+    return dispatch_map(a, pt, (cudaStream_t)stream);
+  }
   return launch_generic_vjp_input(*geom, *prog, g, coef_dev, dx, (cudaStream_t)stream);
 }
 
 int64_t kx_vjp_coef_scratch_bytes(const KxGeom* geom, const KxProgram* prog) {
   if (!geom || !prog) return 0;
-  return generic_vjp_coef_scratch_bytes(*geom, *prog);
+  const int64_t a = generic_vjp_coef_scratch_bytes(*geom, *prog), b = conv_wgrad_scratch_bytes(*geom, *prog);
+  return a > b ? a : b;
 }
 
 int kx_map_vjp_coef(const KxGeom* geom, const KxProgram* prog, const void* x, const void* g, void* scratch,
@@ -149,6 +199,8 @@ int kx_map_vjp_coef(const KxGeom* geom, const KxProgram* prog, const void* x, co
   if (prog->n_funcs != 1 || prog->func[0].kind != KX_AFFINE || geom->in_dtype != KX_F32 || geom->out_dtype != KX_F32)
     return fail(KX_ERR_UNSUPPORTED, "VJP is implemented for single-function float32 AFFINE programs");
   if (!x || !g || !scratch || !dcoef) return fail(KX_ERR_INVALID, "null device pointer");
+  rc = try_conv_wgrad(*geom, *prog, x, g, scratch, dcoef, (cudaStream_t)stream);
+  if (rc != KX_ERR_UNSUPPORTED) return rc;
   return launch_generic_vjp_coef(*geom, *prog, x, g, scratch, dcoef, (cudaStream_t)stream);
 }
 

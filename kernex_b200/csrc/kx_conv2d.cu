@@ -1,0 +1,426 @@
+// Fast paths for conv-as-kmap (README.md:96-111, tests/test_interface.py:315-348, BASELINE
+// config 3a): a (C, KY, KX) window over a channel-first (C, H, W) image with padding
+// ('valid', *, *), i.e. out[0, y, x] = sum_c sum_ky sum_kx w[c,ky,kx] * in[c, y+ky-ly, x+kx-lx],
+// and the fused weight-gradient reduction of the same geometry.
+//
+// Both kernels use the row-marching skeleton of kx_stencil2d.cu with one register queue per
+// channel: a thread owns 4 output columns, walks down a band of rows and keeps the last KY
+// rows of each of the C input planes in registers, so every input row is fetched once per
+// thread column (16 B per lattice update for C = 3: three planes read, one written) and the
+// 27 taps are pure register FMAs.  Marching along axis 0 (kx_stencil3d.cu) has nothing to
+// reuse here because the output is a single plane.
+//
+//   conv_fwd_kernel    : forward; weights from kernel parameters or a device table
+//   conv_wgrad_kernel  : dW[c,ky,kx] = sum_{y,x} g[y,x] * in[c, y+ky-ly, x+kx-lx]; each thread
+//                        accumulates C*KY*KX partial sums in registers, blocks reduce through
+//                        shuffles + shared memory into partial[block][tap]; a second kernel sums
+//                        the partials in a fixed order (deterministic, no atomics).
+#include "kx_internal.cuh"
+
+namespace kx {
+
+namespace {
+
+constexpr int kTX = 128;
+constexpr int kCols = 4;
+constexpr int kMaxC = 4;
+
+template <typename T>
+struct ConvArgs {
+  const T* in;
+  const T* g;                  // wgrad: cotangent [hout, wout]
+  T* out;                      // fwd: [hout, wout]; wgrad: partial[blocks][C*KY*KX]
+  const T* coef_dev;
+  int64_t in_batch, out_batch, plane;
+  int hin, win, hout, wout;
+  int ly, lx, th;
+  int coef_rev;                // device table is in reversed tap order (transposed program)
+  T bias;
+  T coef[kMaxC * 9];
+};
+
+template <typename T>
+__device__ __forceinline__ void ldv4(const T* p, T (&d)[4]) {
+  const int4 raw = __ldg(reinterpret_cast<const int4*>(p));
+  d[0] = reinterpret_cast<const T&>(raw.x);
+  d[1] = reinterpret_cast<const T&>(raw.y);
+  d[2] = reinterpret_cast<const T&>(raw.z);
+  d[3] = reinterpret_cast<const T&>(raw.w);
+}
+
+template <typename T, int KX, int SHIFT, bool VEC, int NE>
+__device__ __forceinline__ void load_row(const T* __restrict__ plane, int iy, int xa, int hin, int win, T (&dst)[NE]) {
+  const bool row_ok = (iy >= 0) && (iy < hin);
+  const T* rp = plane + (int64_t)iy * win;
+  if (VEC) {
+#pragma unroll
+    for (int v = 0; v < NE / 4; ++v) {
+      const int c = xa + 4 * v;
+      T t4[4] = {T(0), T(0), T(0), T(0)};
+      if (row_ok && c >= 0 && c + 3 < win) ldv4(rp + c, t4);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) dst[4 * v + e] = t4[e];
+    }
+  } else {
+#pragma unroll
+    for (int e = 0; e < KX + kCols - 1; ++e) {
+      const int c = xa + e;
+      dst[e] = (row_ok && c >= 0 && c < win) ? __ldg(rp + c) : T(0);
+    }
+  }
+}
+
+template <typename T, int C, int KY, int KX, int SHIFT, bool VEC>
+__global__ void __launch_bounds__(kTX)
+conv_fwd_kernel(const __grid_constant__ ConvArgs<T> a) {
+  constexpr int NV = (SHIFT + KX + kCols - 1 + 3) / 4;
+  constexpr int NE = NV * 4;
+  constexpr int NT = C * KY * KX;
+  const int j0 = (blockIdx.x * kTX + threadIdx.x) * kCols;
+  if (j0 >= a.wout) return;
+  const int r0 = blockIdx.y * a.th, r1 = min(r0 + a.th, a.hout);
+  const T* __restrict__ in = a.in + (int64_t)blockIdx.z * a.in_batch;
+  T* __restrict__ out = a.out + (int64_t)blockIdx.z * a.out_batch;
+  const int xa = j0 - a.lx - SHIFT;
+  const int n_valid = min(kCols, a.wout - j0);
+
+  T w[NT];
+  if (a.coef_dev) {
+#pragma unroll
+    for (int i = 0; i < NT; ++i) w[i] = a.coef_dev[a.coef_rev ? NT - 1 - i : i];
+  } else {
+#pragma unroll
+    for (int i = 0; i < NT; ++i) w[i] = a.coef[i];
+  }
+
+  T q[C][KY][NE];
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+#pragma unroll
+    for (int ky = 0; ky < KY - 1; ++ky)
+      load_row<T, KX, SHIFT, VEC, NE>(in + c * a.plane, r0 - a.ly + ky, xa, a.hin, a.win, q[c][ky]);
+  }
+  for (int r = r0; r < r1; ++r) {
+#pragma unroll
+    for (int c = 0; c < C; ++c)
+      load_row<T, KX, SHIFT, VEC, NE>(in + c * a.plane, r - a.ly + KY - 1, xa, a.hin, a.win, q[c][KY - 1]);
+    T acc[kCols];
+#pragma unroll
+    for (int i = 0; i < kCols; ++i) acc[i] = a.bias;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+#pragma unroll
+      for (int ky = 0; ky < KY; ++ky) {
+#pragma unroll
+        for (int kx = 0; kx < KX; ++kx) {
+#pragma unroll
+          for (int i = 0; i < kCols; ++i)
+            acc[i] = mad_wrap(w[(c * KY + ky) * KX + kx], q[c][ky][SHIFT + kx + i], acc[i]);
+        }
+      }
+    }
+    T* o = out + (int64_t)r * a.wout + j0;
+    const uintptr_t addr = reinterpret_cast<uintptr_t>(o);
+    if (n_valid == 4 && (addr & 15) == 0) {
+      int4 raw;
+      raw.x = reinterpret_cast<const int&>(acc[0]);
+      raw.y = reinterpret_cast<const int&>(acc[1]);
+      raw.z = reinterpret_cast<const int&>(acc[2]);
+      raw.w = reinterpret_cast<const int&>(acc[3]);
+      __stcs(reinterpret_cast<int4*>(o), raw);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (i < n_valid) o[i] = acc[i];
+    }
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+#pragma unroll
+      for (int ky = 0; ky < KY - 1; ++ky) {
+#pragma unroll
+        for (int e = 0; e < NE; ++e) q[c][ky][e] = q[c][ky + 1][e];
+      }
+    }
+  }
+}
+
+template <int C, int KY, int KX, int SHIFT, bool VEC>
+__global__ void __launch_bounds__(kTX)
+conv_wgrad_kernel(const __grid_constant__ ConvArgs<float> a) {
+  constexpr int NV = (SHIFT + KX + kCols - 1 + 3) / 4;
+  constexpr int NE = NV * 4;
+  constexpr int NT = C * KY * KX;
+  __shared__ float red[kTX / 32][NT];
+  const int j0 = (blockIdx.x * kTX + threadIdx.x) * kCols;
+  const int r0 = blockIdx.y * a.th, r1 = min(r0 + a.th, a.hout);
+  const float* __restrict__ in = a.in;
+  const int xa = j0 - a.lx - SHIFT;
+  float acc[NT];
+#pragma unroll
+  for (int t = 0; t < NT; ++t) acc[t] = 0.f;
+
+  if (j0 < a.wout) {
+    float q[C][KY][NE];
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+#pragma unroll
+      for (int ky = 0; ky < KY - 1; ++ky)
+        load_row<float, KX, SHIFT, VEC, NE>(in + c * a.plane, r0 - a.ly + ky, xa, a.hin, a.win, q[c][ky]);
+    }
+    for (int r = r0; r < r1; ++r) {
+#pragma unroll
+      for (int c = 0; c < C; ++c)
+        load_row<float, KX, SHIFT, VEC, NE>(in + c * a.plane, r - a.ly + KY - 1, xa, a.hin, a.win, q[c][KY - 1]);
+      float gv[kCols];
+      const float* gp = a.g + (int64_t)r * a.wout + j0;
+      if (j0 + 3 < a.wout && ((reinterpret_cast<uintptr_t>(gp) & 15) == 0)) {
+        ldv4(gp, gv);
+      } else {
+#pragma unroll
+        for (int i = 0; i < kCols; ++i) gv[i] = (j0 + i < a.wout) ? __ldg(gp + i) : 0.f;
+      }
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+#pragma unroll
+        for (int ky = 0; ky < KY; ++ky) {
+#pragma unroll
+          for (int kx = 0; kx < KX; ++kx) {
+#pragma unroll
+            for (int i = 0; i < kCols; ++i)
+              acc[(c * KY + ky) * KX + kx] = fmaf(gv[i], q[c][ky][SHIFT + kx + i], acc[(c * KY + ky) * KX + kx]);
+          }
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+#pragma unroll
+        for (int ky = 0; ky < KY - 1; ++ky) {
+#pragma unroll
+          for (int e = 0; e < NE; ++e) q[c][ky][e] = q[c][ky + 1][e];
+        }
+      }
+    }
+  }
+  // block reduction: shuffles inside a warp, shared memory across the 4 warps
+#pragma unroll
+  for (int t = 0; t < NT; ++t) {
+    float v = acc[t];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][t] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < NT) {
+    float v = 0.f;
+#pragma unroll
+    for (int wv = 0; wv < kTX / 32; ++wv) v += red[wv][threadIdx.x];
+    const int64_t blk = (int64_t)blockIdx.y * gridDim.x + blockIdx.x;
+    a.out[blk * NT + threadIdx.x] = v;
+  }
+}
+
+// fixed-order sum of the per-block partials; slot order -> program tap order through `perm`
+struct PermArgs {
+  int n_taps;
+  int perm[kMaxC * 9];   // dcoef[t] = sum over blocks of partial[block][perm[t]]
+};
+__global__ void conv_wgrad_finish(const float* __restrict__ partial, float* __restrict__ dcoef, int64_t nblocks,
+                                  int nslots, const __grid_constant__ PermArgs pa) {
+  const int t = blockIdx.x;
+  const int slot = pa.perm[t];
+  float acc = 0.f;
+  for (int64_t i = threadIdx.x; i < nblocks; i += blockDim.x) acc += partial[i * nslots + slot];
+  __shared__ float red[8];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) s += red[i];
+    dcoef[t] = s;
+  }
+}
+
+struct ConvGeom {
+  int C, KY, KX, ac, ay, ax;
+  int64_t batch;
+};
+
+// (C, KY, KX) window over (C, H, W) with the channel axis fully consumed; leading axes batch
+bool conv_geometry(const KxGeom& g, ConvGeom& cg) {
+  const int nd = g.ndim;
+  if (nd < 3) return false;
+  cg.ac = nd - 3;
+  cg.ay = nd - 2;
+  cg.ax = nd - 1;
+  cg.C = g.ksize[cg.ac];
+  cg.KY = g.ksize[cg.ay];
+  cg.KX = g.ksize[cg.ax];
+  if (cg.C < 1 || cg.C > kMaxC || cg.KY != 3 || cg.KX != 3) return false;
+  if (g.in_shape[cg.ac] != cg.C || g.lo[cg.ac] != 0 || g.hi[cg.ac] != 0 || g.out_shape[cg.ac] != 1) return false;
+  cg.batch = 1;
+  for (int d = 0; d < nd - 3; ++d) {
+    if (g.ksize[d] != 1 || g.stride[d] != 1 || g.lo[d] != 0 || g.hi[d] != 0) return false;
+    cg.batch *= g.in_shape[d];
+  }
+  for (int d = nd - 3; d < nd; ++d) {
+    if (g.stride[d] != 1 || g.in_shape[d] > 0x3fffffff || g.out_shape[d] > 0x3fffffff) return false;
+  }
+  return true;
+}
+
+template <typename T>
+void fill_common(ConvArgs<T>& a, const KxGeom& g, const ConvGeom& cg) {
+  memset(&a, 0, sizeof(a));
+  a.hin = (int)g.in_shape[cg.ay];
+  a.win = (int)g.in_shape[cg.ax];
+  a.hout = (int)g.out_shape[cg.ay];
+  a.wout = (int)g.out_shape[cg.ax];
+  a.ly = g.lo[cg.ay];
+  a.lx = g.lo[cg.ax];
+  a.plane = (int64_t)a.hin * a.win;
+  a.in_batch = a.plane * cg.C;
+  a.out_batch = (int64_t)a.hout * a.wout;
+  a.th = a.hout >= 512 ? 32 : (a.hout >= 64 ? 16 : 8);
+  while ((a.hout + a.th - 1) / a.th > 65535) a.th *= 2;
+}
+
+template <typename T, int C>
+int launch_fwd(const ConvArgs<T>& a, dim3 grid, bool vec, cudaStream_t s) {
+  const int shift = vec ? (((-a.lx) % 4) + 4) % 4 : 0;
+  if (!vec) conv_fwd_kernel<T, C, 3, 3, 0, false><<<grid, kTX, 0, s>>>(a);
+  else if (shift == 0) conv_fwd_kernel<T, C, 3, 3, 0, true><<<grid, kTX, 0, s>>>(a);
+  else if (shift == 1) conv_fwd_kernel<T, C, 3, 3, 1, true><<<grid, kTX, 0, s>>>(a);
+  else if (shift == 2) conv_fwd_kernel<T, C, 3, 3, 2, true><<<grid, kTX, 0, s>>>(a);
+  else conv_fwd_kernel<T, C, 3, 3, 3, true><<<grid, kTX, 0, s>>>(a);
+  return after_launch("conv_fwd_kernel");
+}
+
+template <int C>
+int launch_wgrad(const ConvArgs<float>& a, dim3 grid, bool vec, cudaStream_t s) {
+  const int shift = vec ? (((-a.lx) % 4) + 4) % 4 : 0;
+  if (!vec) conv_wgrad_kernel<C, 3, 3, 0, false><<<grid, kTX, 0, s>>>(a);
+  else if (shift == 0) conv_wgrad_kernel<C, 3, 3, 0, true><<<grid, kTX, 0, s>>>(a);
+  else if (shift == 1) conv_wgrad_kernel<C, 3, 3, 1, true><<<grid, kTX, 0, s>>>(a);
+  else if (shift == 2) conv_wgrad_kernel<C, 3, 3, 2, true><<<grid, kTX, 0, s>>>(a);
+  else conv_wgrad_kernel<C, 3, 3, 3, true><<<grid, kTX, 0, s>>>(a);
+  return after_launch("conv_wgrad_kernel");
+}
+
+template <typename T>
+int run_fwd(const MapArgs& m, const KxProgram& p, const ConvGeom& cg, cudaStream_t s) {
+  const KxGeom& g = m.g;
+  const KxFunc& f = p.func[0];
+  const int NT = cg.C * 9;
+  if (f.tap_end - f.tap_begin != NT) return KX_ERR_UNSUPPORTED;  // dense windows only (no tap mask here)
+  ConvArgs<T> a;
+  fill_common(a, g, cg);
+  uint64_t seen = 0;
+  bool fwd_order = true, rev_order = true;
+  for (int t = f.tap_begin; t < f.tap_end; ++t) {
+    const int slot = (p.tap_off[t][cg.ac] * 3 + p.tap_off[t][cg.ay]) * 3 + p.tap_off[t][cg.ax];
+    if (seen & (1ull << slot)) return KX_ERR_UNSUPPORTED;
+    seen |= 1ull << slot;
+    a.coef[slot] = (T)p.coef[t];
+    if (slot != t - f.tap_begin) fwd_order = false;
+    if (slot != NT - 1 - (t - f.tap_begin)) rev_order = false;
+  }
+  if (m.coef_dev) {
+    if (!(fwd_order || rev_order) || (m.coef_batch_stride != 0 && m.batch * cg.batch > 1)) return KX_ERR_UNSUPPORTED;
+    a.coef_dev = (const T*)m.coef_dev;
+    a.coef_rev = fwd_order ? 0 : 1;
+  }
+  a.in = (const T*)m.in;
+  a.out = (T*)m.out;
+  a.bias = (T)f.bias;
+  const int64_t batch = m.batch * cg.batch;
+  if (batch > 65535) return KX_ERR_UNSUPPORTED;
+  const bool vec = (a.win % 4 == 0) && ((reinterpret_cast<uintptr_t>(m.in) & 15) == 0);
+  dim3 grid((a.wout + kTX * kCols - 1) / (kTX * kCols), (a.hout + a.th - 1) / a.th, (unsigned)batch);
+  switch (cg.C) {
+    case 1: return launch_fwd<T, 1>(a, grid, vec, s);
+    case 2: return launch_fwd<T, 2>(a, grid, vec, s);
+    case 3: return launch_fwd<T, 3>(a, grid, vec, s);
+    case 4: return launch_fwd<T, 4>(a, grid, vec, s);
+  }
+  return KX_ERR_UNSUPPORTED;
+}
+
+}  // namespace
+
+int try_conv2d(const MapArgs& m, const KxProgram& p, cudaStream_t s) {
+  const KxGeom& g = m.g;
+  if (p.n_funcs != 1 || p.func[0].kind != KX_AFFINE || p.func[0].post_div != 0.0) return KX_ERR_UNSUPPORTED;
+  if (g.in_dtype != g.out_dtype || m.fn_elems != 1) return KX_ERR_UNSUPPORTED;
+  ConvGeom cg;
+  if (!conv_geometry(g, cg) || cg.C < 2) return KX_ERR_UNSUPPORTED;  // C == 1 is stencil2d's job
+  if (g.in_dtype == KX_F32) return run_fwd<float>(m, p, cg, s);
+  if (g.in_dtype == KX_I32 && p.func[0].coef_is_int) return run_fwd<int32_t>(m, p, cg, s);
+  return KX_ERR_UNSUPPORTED;
+}
+
+// ---- weight gradient -------------------------------------------------------------------
+// geometry accepted: the conv geometry above (C in 1..4, 3x3), or a plain 2-D 3x3 stencil (C = 1)
+static bool wgrad_geometry(const KxGeom& g, ConvGeom& cg) {
+  if (conv_geometry(g, cg)) return cg.batch == 1;
+  if (g.ndim == 2 && g.ksize[0] == 3 && g.ksize[1] == 3 && g.stride[0] == 1 && g.stride[1] == 1 &&
+      g.in_shape[0] <= 0x3fffffff && g.in_shape[1] <= 0x3fffffff) {
+    cg.C = 1;
+    cg.KY = cg.KX = 3;
+    cg.ac = -1;
+    cg.ay = 0;
+    cg.ax = 1;
+    cg.batch = 1;
+    return true;
+  }
+  return false;
+}
+
+static dim3 wgrad_grid(const ConvArgs<float>& a) {
+  return dim3((a.wout + kTX * kCols - 1) / (kTX * kCols), (a.hout + a.th - 1) / a.th, 1);
+}
+
+int64_t conv_wgrad_scratch_bytes(const KxGeom& g, const KxProgram& p) {
+  ConvGeom cg;
+  if (p.n_funcs != 1 || !wgrad_geometry(g, cg)) return 0;
+  ConvArgs<float> a;
+  fill_common(a, g, cg);
+  const dim3 grid = wgrad_grid(a);
+  return (int64_t)grid.x * grid.y * cg.C * 9 * (int64_t)sizeof(float);
+}
+
+int try_conv_wgrad(const KxGeom& g, const KxProgram& p, const void* x, const void* gout, void* scratch, void* dcoef,
+                   cudaStream_t s) {
+  ConvGeom cg;
+  if (p.n_funcs != 1 || p.func[0].kind != KX_AFFINE || p.func[0].post_div != 0.0) return KX_ERR_UNSUPPORTED;
+  if (g.in_dtype != KX_F32 || g.out_dtype != KX_F32 || !wgrad_geometry(g, cg)) return KX_ERR_UNSUPPORTED;
+  const KxFunc& f = p.func[0];
+  const int NT = cg.C * 9, ntaps = f.tap_end - f.tap_begin;
+  if (ntaps < 1 || ntaps > NT) return KX_ERR_UNSUPPORTED;
+  ConvArgs<float> a;
+  fill_common(a, g, cg);
+  PermArgs pa;
+  pa.n_taps = ntaps;
+  for (int t = 0; t < ntaps; ++t) {
+    const int oc = cg.ac >= 0 ? p.tap_off[f.tap_begin + t][cg.ac] : 0;
+    pa.perm[t] = (oc * 3 + p.tap_off[f.tap_begin + t][cg.ay]) * 3 + p.tap_off[f.tap_begin + t][cg.ax];
+  }
+  a.in = (const float*)x;
+  a.g = (const float*)gout;
+  a.out = (float*)scratch;
+  const bool vec = (a.win % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+  const dim3 grid = wgrad_grid(a);
+  int rc = KX_ERR_UNSUPPORTED;
+  switch (cg.C) {
+    case 1: rc = launch_wgrad<1>(a, grid, vec, s); break;
+    case 2: rc = launch_wgrad<2>(a, grid, vec, s); break;
+    case 3: rc = launch_wgrad<3>(a, grid, vec, s); break;
+    case 4: rc = launch_wgrad<4>(a, grid, vec, s); break;
+  }
+  if (rc) return rc;
+  conv_wgrad_finish<<<ntaps, 256, 0, s>>>((const float*)scratch, (float*)dcoef, (int64_t)grid.x * grid.y, NT, pa);
+  return after_launch("conv_wgrad_finish");
+}
+
+}  // namespace kx

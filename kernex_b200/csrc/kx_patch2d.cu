@@ -1,0 +1,168 @@
+// Fast path: dense patch extraction over the last two axes (1-D arrays as one row), stride 1
+// -- kmap(lambda x: x), README.md:157-186, tests_and_benchmarks/test_benchmark_patch.py,
+// BASELINE config 3b (3x3 'same' patches of an 8192^2 image: 4 B read + 36 B written per
+// window, i.e. a WRITE-bound kernel).
+//
+// A block of 128 threads owns 512 consecutive windows of one output row and marches down a
+// band of rows:
+//   * the KY input row segments a window row needs live in a shared-memory ring; each new
+//     output row fetches ONE new input row segment (coalesced), so the input is read once;
+//   * every thread builds its 4 windows x (KY*KX) outputs from (KY rows) x (KX+3 columns)
+//     it reads with 128/64-bit shared loads -- the patch layout (row-major, or rolled for
+//     relative=True, kernex/_src/utils.py:163-181) is a compile-time register permutation;
+//   * the 4*KY*KX values are staged in shared memory with conflict-free 128-bit stores and
+//     the block then writes the (512*KY*KX)-float output segment with fully coalesced
+//     128-bit streaming stores (a thread's own 36 floats are 144 B apart from its
+//     neighbour's, which would otherwise cost 32 transactions per store instruction).
+// Values are moved as 32-bit words, so one kernel serves float32 and int32 bit-exactly.
+#include "kx_internal.cuh"
+
+namespace kx {
+
+namespace {
+
+constexpr int kPT = 128;            // threads per block
+constexpr int kWPT = 4;             // windows per thread
+constexpr int kTW = kPT * kWPT;     // windows per block row
+
+struct P2Args {
+  const uint32_t* in;
+  uint32_t* out;
+  int64_t in_batch, out_batch;
+  int hin, win, hout, wout;
+  int ly, lx, th;
+};
+
+template <int KY, int KX, bool ROLLED>
+__global__ void __launch_bounds__(kPT)
+patch2d_kernel(const __grid_constant__ P2Args a) {
+  constexpr int NT = KY * KX;
+  constexpr int PW = kTW + 8;                     // input row pitch in shared memory (>= kTW + KX - 1, multiple of 4)
+  constexpr int NC = KX + kWPT - 1;               // input columns a thread touches per row
+  __shared__ __align__(16) uint32_t rows[KY][PW];
+  __shared__ __align__(16) uint32_t stage[kTW * NT];
+  const int tid = threadIdx.x;
+  const int x0 = blockIdx.x * kTW;
+  const int r0 = blockIdx.y * a.th, r1 = min(r0 + a.th, a.hout);
+  const uint32_t* __restrict__ in = a.in + (int64_t)blockIdx.z * a.in_batch;
+  uint32_t* __restrict__ out = a.out + (int64_t)blockIdx.z * a.out_batch;
+  const int nwin = min(kTW, a.wout - x0);          // windows of this block row that exist
+  const int count = nwin * NT;                     // output words per row segment
+
+  auto load_row = [&](int iy, int slot) {          // input row iy -> ring slot
+    const bool row_ok = (iy >= 0) && (iy < a.hin);
+    const uint32_t* rp = in + (int64_t)iy * a.win;
+    for (int c = tid; c < kTW + KX - 1; c += kPT) {
+      const int gx = x0 - a.lx + c;
+      rows[slot][c] = (row_ok && gx >= 0 && gx < a.win) ? __ldg(rp + gx) : 0u;
+    }
+  };
+
+#pragma unroll
+  for (int ky = 0; ky < KY - 1; ++ky) load_row(r0 - a.ly + ky, (r0 + ky) % KY);
+
+  for (int r = r0; r < r1; ++r) {
+    load_row(r - a.ly + KY - 1, (r + KY - 1) % KY);
+    __syncthreads();                               // ring complete; previous row's staging drained
+    // ---- build this thread's 4 windows --------------------------------------------------
+    uint32_t v[KY][NC];
+#pragma unroll
+    for (int ky = 0; ky < KY; ++ky) {
+      const uint32_t* rp = rows[(r + ky) % KY] + kWPT * tid;
+      const uint4 q = *reinterpret_cast<const uint4*>(rp);
+      v[ky][0] = q.x; v[ky][1] = q.y; v[ky][2] = q.z; v[ky][3] = q.w;
+#pragma unroll
+      for (int e = 4; e < NC; ++e) v[ky][e] = rp[e];
+    }
+    uint32_t o[kWPT * NT];
+#pragma unroll
+    for (int w = 0; w < kWPT; ++w) {
+#pragma unroll
+      for (int ty = 0; ty < KY; ++ty) {
+#pragma unroll
+        for (int tx = 0; tx < KX; ++tx) {
+          // rolled layout: patch index (ty,tx) holds window element ((ty+cy)%KY, (tx+cx)%KX)
+          const int sy = ROLLED ? (ty + (KY - 1) / 2) % KY : ty;
+          const int sx = ROLLED ? (tx + (KX - 1) / 2) % KX : tx;
+          o[w * NT + ty * KX + tx] = v[sy][w + sx];
+        }
+      }
+    }
+    static_assert((kWPT * NT) % 4 == 0, "a thread's outputs must be whole 128-bit words");
+    uint32_t* sp = stage + tid * (kWPT * NT);
+#pragma unroll
+    for (int q = 0; q < kWPT * NT / 4; ++q)
+      *reinterpret_cast<uint4*>(sp + 4 * q) = make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+    __syncthreads();
+    // ---- coalesced write-out of the row segment ------------------------------------------
+    uint32_t* dst = out + ((int64_t)r * a.wout + x0) * NT;
+    if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+      for (int i = tid; 4 * i + 3 < count; i += kPT)
+        __stcs(reinterpret_cast<uint4*>(dst) + i, *reinterpret_cast<const uint4*>(stage + 4 * i));
+      for (int i = (count & ~3) + tid; i < count; i += kPT) dst[i] = stage[i];
+    } else {
+      for (int i = tid; i < count; i += kPT) dst[i] = stage[i];
+    }
+  }
+}
+
+template <int KY, int KX>
+int launch_p2(const P2Args& a, bool rolled, int64_t batch, cudaStream_t s) {
+  dim3 grid((a.wout + kTW - 1) / kTW, (a.hout + a.th - 1) / a.th, (unsigned)batch);
+  if (rolled) patch2d_kernel<KY, KX, true><<<grid, kPT, 0, s>>>(a);
+  else patch2d_kernel<KY, KX, false><<<grid, kPT, 0, s>>>(a);
+  return after_launch("patch2d_kernel");
+}
+
+}  // namespace
+
+int try_patch2d(const MapArgs& m, const KxProgram& p, cudaStream_t s) {
+  const KxGeom& g = m.g;
+  if (p.n_funcs != 1 || p.func[0].kind != KX_GATHER || g.in_dtype != g.out_dtype) return KX_ERR_UNSUPPORTED;
+  const int nd = g.ndim, ax = nd - 1, ay = nd - 2;
+  int64_t lead = 1;
+  for (int d = 0; d < nd - 2; ++d) {
+    if (g.ksize[d] != 1 || g.stride[d] != 1 || g.lo[d] != 0 || g.hi[d] != 0) return KX_ERR_UNSUPPORTED;
+    lead *= g.in_shape[d];
+  }
+  if (g.stride[ax] != 1 || (ay >= 0 && g.stride[ay] != 1)) return KX_ERR_UNSUPPORTED;
+  const int KY = ay >= 0 ? g.ksize[ay] : 1, KX = g.ksize[ax];
+  const KxFunc& f = p.func[0];
+  if (f.tap_end - f.tap_begin != KY * KX) return KX_ERR_UNSUPPORTED;
+  // tap order must be the plain row-major window or its roll_view rotation
+  bool plain = true, rolled = true;
+  for (int t = 0; t < KY * KX; ++t) {
+    const int ty = t / KX, tx = t % KX;
+    const int oy = ay >= 0 ? p.tap_off[f.tap_begin + t][ay] : 0, ox = p.tap_off[f.tap_begin + t][ax];
+    if (oy != ty || ox != tx) plain = false;
+    if (oy != (ty + (KY - 1) / 2) % KY || ox != (tx + (KX - 1) / 2) % KX) rolled = false;
+    for (int d = 0; d < nd - 2; ++d)
+      if (p.tap_off[f.tap_begin + t][d] != 0) return KX_ERR_UNSUPPORTED;
+  }
+  if (!plain && !rolled) return KX_ERR_UNSUPPORTED;
+  const int64_t batch = m.batch * lead;
+  if (batch > 65535) return KX_ERR_UNSUPPORTED;
+  P2Args a;
+  memset(&a, 0, sizeof(a));
+  a.in = (const uint32_t*)m.in;
+  a.out = (uint32_t*)m.out;
+  a.hin = ay >= 0 ? (int)g.in_shape[ay] : 1;
+  a.win = (int)g.in_shape[ax];
+  a.hout = ay >= 0 ? (int)g.out_shape[ay] : 1;
+  a.wout = (int)g.out_shape[ax];
+  if (g.in_shape[ax] > 0x3fffffff || (ay >= 0 && g.in_shape[ay] > 0x3fffffff)) return KX_ERR_UNSUPPORTED;
+  a.ly = ay >= 0 ? g.lo[ay] : 0;
+  a.lx = g.lo[ax];
+  a.in_batch = (int64_t)a.hin * a.win;
+  a.out_batch = (int64_t)a.hout * a.wout * KY * KX;
+  a.th = a.hout >= 512 ? 16 : (a.hout >= 64 ? 8 : 4);
+  while ((a.hout + a.th - 1) / a.th > 65535) a.th *= 2;
+  const bool roll = !plain;
+  if (KY == 3 && KX == 3) return launch_p2<3, 3>(a, roll, batch, s);
+  if (KY == 1 && KX == 3) return launch_p2<1, 3>(a, roll, batch, s);
+  if (KY == 2 && KX == 2) return launch_p2<2, 2>(a, roll, batch, s);
+  if (KY == 1 && KX == 5) return launch_p2<1, 5>(a, roll, batch, s);
+  return KX_ERR_UNSUPPORTED;
+}
+
+}  // namespace kx

@@ -208,23 +208,47 @@ class _Program:
 
     def coef_tensor(self, device_args, dtype, device):
         """Device coefficient table ``const + sum scale * W.flatten()[idx]`` built with
-        torch ops so that autograd reaches the weights."""
+        torch ops so that autograd reaches the weights.  The index / scale tensors are
+        uploaded once per (program, device); when the table is exactly ``W.flatten()`` (the
+        usual ``sum(x*w)``) the weight tensor itself is the table: zero extra launches."""
         if not self.device_refs:
             return None
         n = self.c.n_taps
-        coef = torch.tensor([self.c.coef[i] for i in range(n)], dtype=dtype, device=device)
-        by_arg: dict[Any, list] = {}
-        for slot, c in self.device_refs:
-            for (arg, flat), scale in c.w.items():
-                by_arg.setdefault(arg, []).append((slot, flat, scale))
-        for arg, refs in by_arg.items():
+        cache = self.__dict__.setdefault("_coef_cache", {})
+        ck = (str(device), dtype)
+        if ck not in cache:
+            by_arg: dict[Any, list] = {}
+            for slot, c in self.device_refs:
+                for (arg, flat), scale in c.w.items():
+                    by_arg.setdefault(arg, []).append((slot, flat, scale))
+            base = [self.c.coef[i] for i in range(n)]
+            identity = None
+            if len(by_arg) == 1 and all(v == 0.0 for v in base):
+                (arg, refs), = by_arg.items()
+                if [r[0] for r in refs] == list(range(n)) and [r[1] for r in refs] == list(range(n)) \
+                        and all(r[2] == 1 for r in refs):
+                    identity = arg
+            plan = []
+            if identity is None:
+                for arg, refs in by_arg.items():
+                    plan.append((arg,
+                                 torch.tensor([r[0] for r in refs], dtype=torch.long, device=device),
+                                 torch.tensor([r[1] for r in refs], dtype=torch.long, device=device),
+                                 torch.tensor([r[2] for r in refs], dtype=dtype, device=device)))
+            cache[ck] = (identity, torch.tensor(base, dtype=dtype, device=device), plan)
+        identity, base, plan = cache[ck]
+        if identity is not None:
+            w = device_args[identity]
+            if w.numel() == n:
+                return w.to(device=device, dtype=dtype).reshape(-1).contiguous()
+        coef = base
+        for arg, slots, flats, scales in plan if identity is None else []:
             w = device_args[arg]
-            if not w.is_cuda:
-                w = w.to(device)
-            slots = torch.tensor([r[0] for r in refs], dtype=torch.long, device=device)
-            flats = torch.tensor([r[1] for r in refs], dtype=torch.long, device=device)
-            scales = torch.tensor([r[2] for r in refs], dtype=dtype, device=device)
-            coef = coef.index_add(0, slots, w.reshape(-1).to(dtype)[flats] * scales)
+            coef = coef.index_add(0, slots, w.to(device=device, dtype=dtype).reshape(-1)[flats] * scales)
+        if identity is not None:  # numel mismatch (broadcast weights): rebuild the general way
+            w = device_args[identity]
+            idx = torch.arange(n, device=device)
+            coef = base.index_add(0, idx, w.to(device=device, dtype=dtype).reshape(-1)[idx])
         return coef.contiguous()
 
 
@@ -318,21 +342,44 @@ _PLAN_CACHE: "dict[tuple, tuple]" = {}
 _PLAN_CACHE_MAX = 128
 
 
-def _plan_key(tag, func_map, shape, kernel_size, strides, border, relative, in_kx):
+def _arg_signature(v):
+    """Hashable description of an extra argument as far as tracing is concerned: device
+    tensors are symbolic (only shape / dtype matter), host values are baked into the taps."""
+    if isinstance(v, torch.Tensor):
+        if v.is_cuda or v.requires_grad:
+            return ("dev", tuple(v.shape), str(v.dtype), bool(v.requires_grad))
+        v = v.detach().numpy()
+    if isinstance(v, np.ndarray):
+        if v.nbytes > 8192:
+            raise TypeError("large host array: not cached")
+        return ("arr", v.shape, str(v.dtype), v.tobytes())
+    if isinstance(v, (bool, int, float, str, type(None), np.generic)):
+        return ("val", type(v).__name__, v)
+    raise TypeError("unhashable argument kind")
+
+
+def _plan_key(tag, func_map, shape, kernel_size, strides, border, relative, in_kx, a=(), k=None):
     try:
         keys = repr([v for v in func_map.values()])
+        sig = tuple(_arg_signature(v) for v in a) + tuple((n, _arg_signature(v)) for n, v in sorted((k or {}).items()))
     except Exception:
         return None
-    return (tag, tuple(id(f) for f in func_map), keys, shape, kernel_size, strides, border, bool(relative), in_kx)
+    return (tag, tuple(id(f) for f in func_map), keys, shape, kernel_size, strides, border, bool(relative), in_kx,
+            sig)
 
 
 def _map_plan(func_map, shape, kernel_size, strides, border, relative, in_kx, a, k):
     """Trace + classify + build the KxGeom / KxProgram.  Plans of argument-free window
     functions are cached on the function objects' identity (the reference re-traces under
     ``jit`` at most once per shape too), so steady-state calls cost one ctypes launch."""
-    key = _plan_key("map", func_map, shape, kernel_size, strides, border, relative, in_kx) if not a and not k else None
+    key = _plan_key("map", func_map, shape, kernel_size, strides, border, relative, in_kx, a, k)
     if key is not None and key in _PLAN_CACHE:
-        return _PLAN_CACHE[key][1]
+        specs, _stale_args, out_kx, prog, geom, full_shape = _PLAN_CACHE[key][1]
+        # device tensors are looked up afresh: the cached plan only remembers their positions
+        fresh = {i: v for i, v in enumerate(a) if isinstance(v, torch.Tensor) and (v.is_cuda or v.requires_grad)}
+        fresh.update({("kw", n): v for n, v in (k or {}).items()
+                      if isinstance(v, torch.Tensor) and (v.is_cuda or v.requires_grad)})
+        return specs, fresh, out_kx, prog, geom, full_shape
     specs, device_args = _trace_all(func_map, kernel_size, relative, a, k)
     groups = [tuple(v) for v in func_map.values()]
     out_shape = calculate_output_shape(shape, kernel_size, strides, border)
