@@ -173,6 +173,17 @@ int64_t kx_scan_state_bytes(const KxGeom* geom);
 int kx_scan(const KxGeom* geom, const KxProgram* prog, const void* in, const void* coef_dev,
             void* state, void* out, int32_t reverse, void* stream);
 
+/* Axis-1 shard of a row-marching kscan (time-marching stencils, README.md:231-266): produces
+ * columns [col_base, col_base + geom.in_shape[1]) of the scan kernel_scan would run on a
+ * (geom.in_shape[0], global_nx) array; region keys and the zero pad are in GLOBAL columns.
+ * Axis 0 is the sequential axis, so a multi-GPU kscan shards columns; a shard that does not
+ * touch the global edge must be over-allocated by nt*R columns on that side (R = the largest
+ * column offset the functions read) and the caller drops them: inside that cone the values
+ * are computed from cells the shard does not hold.  Returns KX_ERR_UNSUPPORTED unless the
+ * dependency analysis of kx_scan's fast path applies (every tap reads the row above). */
+int kx_scan_rowmarch_shard(const KxGeom* geom, const KxProgram* prog, int64_t col_base, int64_t global_nx,
+                           void* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -224,4 +224,20 @@ int kx_scan(const KxGeom* geom, const KxProgram* prog, const void* in, const voi
   return launch_generic_scan(*geom, *prog, in, coef_dev, state, out, reverse, s);
 }
 
+int kx_scan_rowmarch_shard(const KxGeom* geom, const KxProgram* prog, int64_t col_base, int64_t global_nx, void* out,
+                           void* stream) {
+  int rc = validate(geom, prog);
+  if (rc) return rc;
+  if (!out) return fail(KX_ERR_INVALID, "null device pointer");
+  if (geom->ndim != 2 || col_base + geom->in_shape[1] > global_nx + (int64_t)geom->in_shape[0] * 4 || global_nx < 1)
+    return fail(KX_ERR_INVALID, "shard [%lld, %lld) does not belong to a scan of width %lld", (long long)col_base,
+                (long long)(col_base + (geom->ndim == 2 ? geom->in_shape[1] : 0)), (long long)global_nx);
+  rc = scan_rowmarch_shard(*geom, *prog, nullptr, out, 0, col_base, global_nx, (cudaStream_t)stream);
+  if (rc == KX_ERR_UNSUPPORTED)
+    return fail(KX_ERR_UNSUPPORTED,
+                "row-march sharding needs a 2-D float32 kscan with 'same'-style borders whose functions read only "
+                "the row above");
+  return rc;
+}
+
 }  // extern "C"

@@ -78,5 +78,7 @@ int try_conv_wgrad(const KxGeom& g, const KxProgram& prog, const void* x, const 
                    void* dcoef, cudaStream_t s);
 int try_scan_rowmarch(const KxGeom& g, const KxProgram& prog, const void* in, const void* coef_dev,
                       void* out, int reverse, cudaStream_t s);
+int scan_rowmarch_shard(const KxGeom& g, const KxProgram& prog, const void* coef_dev, void* out, int reverse,
+                        int64_t col_base, int64_t gnx, cudaStream_t s);
 
 }  // namespace kx

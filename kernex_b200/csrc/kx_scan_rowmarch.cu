@@ -38,7 +38,8 @@ struct RMFunc {
 
 struct RMArgs {
   float* out;
-  int64_t nx;
+  int64_t nx;                   // local width (columns held by this call)
+  int64_t col_base, gnx;        // global column of local column 0, global width (axis-1 sharding)
   int nt;
   int n0, n1;                   // rows advanced by this launch
   int own;                      // owned columns per block (multiple of 4)
@@ -120,12 +121,13 @@ scan_rowmarch_kernel(const __grid_constant__ RMArgs a) {
         for (int e = 0; e < 4; ++e) {
           const int64_t c = span0 + (int64_t)g * kRMThreads * 4 + tid * 4 + e;
           RMFunc f;
-          if (c < 0 || c >= a.nx) {      // pad column: a never-written zero
+          const int64_t gc = a.col_base + c;
+          if (c < 0 || c >= a.nx || gc < 0 || gc >= a.gnx) {   // pad (or not-held) column: reads as zero
             f.bias = 0.f;
 #pragma unroll
             for (int d = 0; d < 2 * kMaxR + 1; ++d) f.a[d] = 0.f;
           } else {
-            f = a.func[rm_select(a, n, c)];
+            f = a.func[rm_select(a, n, gc)];
           }
           cb[g][e] = f.bias;
           cl2[g][e] = f.a[0]; cl1[g][e] = f.a[1]; cc[g][e] = f.a[2]; cr1[g][e] = f.a[3]; cr2[g][e] = f.a[4];
@@ -198,9 +200,12 @@ bool add_break(int* br, int& n, int64_t v, int nt) {
 
 }  // namespace
 
-int try_scan_rowmarch(const KxGeom& g, const KxProgram& p, const void* in, const void* coef_dev, void* out,
-                      int reverse, cudaStream_t s) {
-  (void)in;
+// `col_base` / `gnx`: the call produces columns [col_base, col_base + g.in_shape[1]) of a scan whose
+// global width is gnx (region keys and the zero pad are in GLOBAL coordinates).  Columns the call
+// does not hold read as zero, so the first nt*RL (last nt*RR) local columns of a shard that does not
+// start (end) at the global edge are only valid if the caller overlaps shards by that much.
+int scan_rowmarch_shard(const KxGeom& g, const KxProgram& p, const void* coef_dev, void* out, int reverse,
+                        int64_t col_base, int64_t gnx, cudaStream_t s) {
   if (g.ndim != 2 || g.in_dtype != KX_F32 || reverse || coef_dev) return KX_ERR_UNSUPPORTED;
   const int c0 = (g.ksize[0] - 1) / 2, c1 = (g.ksize[1] - 1) / 2;
   // every in-bounds cell is a window centre exactly once ('same'-style borders), stride 1
@@ -248,6 +253,8 @@ int try_scan_rowmarch(const KxGeom& g, const KxProgram& p, const void* in, const
   a.n_keys = p.n_keys;
   a.out = (float*)out;
   a.nx = g.in_shape[1];
+  a.col_base = col_base;
+  a.gnx = gnx;
   a.nt = nt;
   a.halo_l = ((kT * rl + 3) / 4) * 4;
   a.halo_r = ((kT * rr + 3) / 4) * 4;
@@ -268,6 +275,12 @@ int try_scan_rowmarch(const KxGeom& g, const KxProgram& p, const void* in, const
     if (rc) return rc;
   }
   return KX_OK;
+}
+
+int try_scan_rowmarch(const KxGeom& g, const KxProgram& p, const void* in, const void* coef_dev, void* out,
+                      int reverse, cudaStream_t s) {
+  (void)in;
+  return scan_rowmarch_shard(g, p, coef_dev, out, reverse, 0, g.ndim == 2 ? g.in_shape[1] : 0, s);
 }
 
 }  // namespace kx

@@ -165,3 +165,79 @@ class SlabStencil:
         if self.world > 1:
             main.wait_stream(self.side)
         return self.out
+
+
+# --------------------------------------------------------------------------- #
+# kscan: column (axis-1) sharding of time-marching meshes                       #
+# --------------------------------------------------------------------------- #
+
+
+def column_shard_plan(nx_global: int, world: int, rank: int, nt: int, rl: int, rr: int):
+    """Columns a rank must HOLD to produce its own share of a row-marching kscan without
+    talking to its neighbours.
+
+    Axis 0 of a kscan is sequential (time), so the grid shards along axis 1.  A cell at
+    row ``n`` depends on columns ``[i - n*rl, i + n*rr]`` of the initial row (``rl`` / ``rr`` =
+    largest column offset any function reads to the left / right), so a shard that is
+    over-allocated by ``nt*rl`` columns on the left and ``nt*rr`` on the right computes its
+    own columns exactly; the overlap is recomputed redundantly (4096 / 2^21 = 0.2 % at
+    BASELINE config 4) instead of exchanged.  Returns ``(col_base, width, keep_lo, keep_hi)``:
+    hold global columns ``[col_base, col_base+width)``, keep local ``[keep_lo, keep_hi)``.
+    """
+    per = -(-nx_global // world)
+    c0, c1 = min(rank * per, nx_global), min((rank + 1) * per, nx_global)
+    lo = max(0, c0 - nt * rl)
+    lo -= lo % 4                       # keep rows 16-byte aligned for 128-bit stores
+    hi = min(nx_global, c1 + nt * rr)
+    return lo, hi - lo, c0 - lo, c1 - lo
+
+
+class ColumnShardedScan:
+    """A ``kscan`` mesh (``F[slice] = fn`` region assignments on a ``kernex_b200.kscan`` object)
+    over a global ``(nt, nx_global)`` grid, with the columns sharded over the ranks.  Only
+    time-marching meshes qualify (every function reads the row above): the same dependency
+    analysis as the single-GPU fast path, enforced by ``kx_scan_rowmarch_shard``."""
+
+    def __init__(self, mesh, nt: int, nx_global: int, rank=None, world=None, device=None):
+        import ctypes as C
+
+        from . import _lib
+        from .engine import _geom, _Program, _trace_all
+        from .resolve import normalize_slices
+
+        if rank is None:
+            rank = dist.get_rank() if dist.is_initialized() else 0
+        if world is None:
+            world = dist.get_world_size() if dist.is_initialized() else 1
+        self.rank, self.world, self.nt, self.nx_global = rank, world, nt, nx_global
+        self.device = device or torch.device("cuda", torch.cuda.current_device())
+        shape = (nt, nx_global)
+        ksize, strides, border = mesh._resolved(shape)
+        if mesh.use_offset or not mesh.inplace:
+            raise ValueError("ColumnShardedScan needs a kscan mesh")
+        normalized = normalize_slices(mesh.container, shape)
+        func_map = {mesh._named(f, ksize): keys for f, keys in normalized.items()}
+        specs, device_args = _trace_all(func_map, ksize, mesh.relative, (), {})
+        if device_args:
+            raise ValueError("device-resident arguments are not supported in a sharded kscan")
+        c1 = (ksize[1] - 1) // 2
+        offs = [t[1] - c1 for s in specs for t in s.taps]
+        self.rl, self.rr = max([0] + [-o for o in offs]), max([0] + offs)
+        self.col_base, self.width, self.keep_lo, self.keep_hi = column_shard_plan(
+            nx_global, world, rank, nt, self.rl, self.rr)
+        self._prog = _Program(specs, [tuple(v) for v in func_map.values()], 2)
+        local = (nt, self.width)
+        self._geom = _geom(local, local, ksize, strides, border, _lib.KX_F32, _lib.KX_F32)
+        self._lib, self._C = _lib, C
+        self.out = torch.empty(local, dtype=torch.float32, device=self.device)
+        self.local_windows = nt * (self.keep_hi - self.keep_lo)
+
+    def run(self):
+        """Launch the scan; returns this rank's columns ``(nt, nx_local)`` as a view of the
+        over-allocated buffer (row pitch = held width)."""
+        C, L = self._C, self._lib
+        lib = L.load()
+        stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        L.check(lib.kx_scan_rowmarch_shard(C.byref(self._geom), C.byref(self._prog.c), C.c_int64(self.col_base),
+                                           C.c_int64(self.nx_global), C.c_void_p(self.out.data_ptr()), stream))
+        return self.out[:, self.keep_lo:self.keep_hi]

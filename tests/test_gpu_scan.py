@@ -150,3 +150,25 @@ def test_rowmarch_config4_prefix_strip_full_depth(kex):
     assert torch.all(out[0, q1:q2] == 2) and torch.all(out[0, :q1] == 1) and torch.all(out[0, q2:] == 1)
     # the square wave is transported, never amplified (convex combination of the row above)
     assert float(out.max()) <= 2.0 and float(out.min()) >= 1.0
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_column_sharded_scan_is_bit_identical_to_unsharded(kex, world):
+    """kscan shards on axis 1 (axis 0 is time): every emulated rank recomputes its nt*R-column
+    dependency cone instead of exchanging it; the stitched result must equal the single-launch
+    result bit for bit (no communication is involved, so the ranks can run one after another
+    on one GPU)."""
+    from kernex_b200.dist import ColumnShardedScan
+    nt, nx, kappa = 96, 6000, 0.5
+    F, _ = _convection_mesh(kex.kscan, nt, nx, kappa)
+    whole = F(torch.ones((nt, nx), device="cuda"))
+    parts = []
+    for rank in range(world):
+        Fr, _ = _convection_mesh(kex.kscan, nt, nx, kappa)
+        sh = ColumnShardedScan(Fr, nt, nx, rank=rank, world=world)
+        assert sh.rl == 1 and sh.rr == 0
+        parts.append(sh.run().clone())
+        assert _last_kernel() == "scan_rowmarch_kernel"
+    stitched = torch.cat(parts, dim=1)
+    assert stitched.shape == whole.shape
+    assert torch.equal(stitched, whole)
