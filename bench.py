@@ -54,52 +54,85 @@ def measured_peak():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    """SM clock and throttle reasons DURING the timed region (B200_PROFILING.md): an NVML
+    polling thread (5 ms period; `nvidia-smi -lms` is the fallback), samples are time-stamped
+    and only those inside [mark_start, mark_end] are summarised."""
 
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    REASONS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
     def __init__(self, index):
-        self.rows, self.proc, self.index = [], None, index
+        self.index, self.rows, self.stop, self.t0, self.t1 = index, [], False, None, None
+        self.thread = None
+
+    def _poll_nvml(self):
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+        mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+        while not self.stop:
+            sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+            try:
+                bits = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
+            except Exception:
+                bits = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+            self.rows.append((time.perf_counter(), float(sm), float(mx), int(bits)))
+            time.sleep(0.005)
+
+    def _poll_smi(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "20",
+                                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        try:
+            for line in proc.stdout:
+                c = [v.strip() for v in line.split(",")]
+                bits = 0
+                for nm, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[2:6]):
+                    if v.lower().startswith("active"):
+                        bits |= self.REASONS[nm]
+                try:
+                    self.rows.append((time.perf_counter(), float(c[0]), float(c[1]), bits))
+                except ValueError:
+                    pass
+                if self.stop:
+                    break
+        finally:
+            proc.terminate()
+
+    def _run(self):
+        try:
+            self._poll_nvml()
+        except Exception:
+            try:
+                self._poll_smi()
+            except Exception:
+                pass
 
     def __enter__(self):
-        try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20", "-i",
-                 str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
-            self.thread.start()
-        except Exception:
-            self.proc = None
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
         return self
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+    def mark_start(self):
+        self.t0 = time.perf_counter()
+
+    def mark_end(self):
+        self.t1 = time.perf_counter()
 
     def __exit__(self, *exc):
-        if self.proc is not None:
-            time.sleep(0.06)
-            self.proc.terminate()
-            try:
-                self.proc.wait(timeout=2)
-            except Exception:
-                self.proc.kill()
+        self.stop = True
+        if self.thread is not None:
+            self.thread.join(timeout=2)
 
     def summary(self):
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            try:
-                sm.append(float(r[0]))
-                mx.append(float(r[1]))
-                for nm, v in zip(names, r[2:6]):
-                    if v.lower().startswith("active"):
-                        reasons.add(nm)
-            except Exception:
-                continue
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        rows = [r for r in self.rows if self.t0 is not None and self.t0 <= r[0] <= (self.t1 or 1e30)]
+        window = "timed region"
+        if not rows:
+            rows, window = list(self.rows), "warm-up + timed region (no sample fell inside the timed region)"
+        sm = [r[1] for r in rows]
+        reasons = sorted(nm for nm, bit in self.REASONS.items() if any(r[3] & bit for r in rows))
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max((r[2] for r in rows), default=None),
+                "reasons": reasons, "samples": len(sm), "window": window}
 
 
 def host_threads():
@@ -200,18 +233,19 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
-        step()
-    barrier()
-    launches0 = _lib.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local) as clocks:
+    with ClockSampler(local) as clocks:   # started before the warm-up so it is polling by the timed region
+        for _ in range(max(args.warmup, 3)):
+            step()
         barrier()
+        launches0 = _lib.launch_count()
+        clocks.mark_start()
         ev0.record()
         for _ in range(args.steps):
             step()
         ev1.record()
         barrier()
+        clocks.mark_end()
     ms = ev0.elapsed_time(ev1)
     launches = _lib.launch_count() - launches0
     kernel_name = _lib.last_kernel()
@@ -301,7 +335,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=300)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     args = ap.parse_args()

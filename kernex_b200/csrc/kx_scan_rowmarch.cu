@@ -43,6 +43,7 @@ struct RMArgs {
   int nt;
   int n0, n1;                   // rows advanced by this launch
   int own;                      // owned columns per block (multiple of 4)
+  int ntiles;                   // fat kernel: column tiles (a block loops over tile, tile+grid, ...)
   int halo_l, halo_r;           // redundant columns per side (multiples of 4)
   int n_funcs, n_keys;
   int n_breaks;
@@ -73,8 +74,8 @@ __device__ __forceinline__ int rm_select(const RMArgs& a, int64_t row, int64_t c
 template <int G, int RL, int RR>
 __global__ void __launch_bounds__(kRMThreads)
 scan_rowmarch_kernel(const __grid_constant__ RMArgs a) {
-  constexpr int SPAN = kRMThreads * 4 * G;
-  __shared__ __align__(16) float line[2][SPAN + 8];   // +4 guard floats on each side
+  constexpr int kEdge = 2 * (G * (kRMThreads / 32) + 2);   // 2 floats per warp slot (+ a zero slot per side)
+  __shared__ float edge[2][2 * kEdge];                     // [parity][right edges | left edges]
   const int tid = threadIdx.x;
   const int64_t span0 = (int64_t)blockIdx.x * a.own - a.halo_l;  // first processed column
   const int64_t own0 = (int64_t)blockIdx.x * a.own;
@@ -102,10 +103,8 @@ scan_rowmarch_kernel(const __grid_constant__ RMArgs a) {
       }
     }
   }
-  if (tid < 4) {
-    line[0][tid] = line[1][tid] = 0.f;
-    line[0][SPAN + 4 + tid] = line[1][SPAN + 4 + tid] = 0.f;
-  }
+  for (int i = tid; i < 4 * kEdge; i += kRMThreads) (&edge[0][0])[i] = 0.f;   // incl. the zero slots
+  __syncthreads();
 
   int iv = 0;
   while (iv + 1 < a.n_breaks && a.row_break[iv + 1] <= a.n0) ++iv;
@@ -134,23 +133,46 @@ scan_rowmarch_kernel(const __grid_constant__ RMArgs a) {
         }
       }
     }
-    // publish the previous row, then read the neighbours across thread boundaries
-    float* buf = line[n & 1] + 4;
+    // neighbours across thread boundaries: warp shuffles inside a warp; only the two edge
+    // lanes of every warp go through shared memory (one barrier per row, double buffered)
+    float* eb = edge[n & 1];
+    const int lane = tid & 31, wrp = tid >> 5;
 #pragma unroll
-    for (int g = 0; g < G; ++g)
-      *reinterpret_cast<float4*>(buf + g * kRMThreads * 4 + tid * 4) =
-          make_float4(cur[g][0], cur[g][1], cur[g][2], cur[g][3]);
+    for (int g = 0; g < G; ++g) {
+      const int slot = 1 + g * (kRMThreads / 32) + wrp;      // slot 0 and the last slot stay zero
+      if (RL >= 1 && lane == 31) {
+        eb[2 * slot] = cur[g][3];
+        if (RL >= 2) eb[2 * slot + 1] = cur[g][2];
+      }
+      if (RR >= 1 && lane == 0) {
+        eb[kEdge + 2 * slot] = cur[g][0];
+        if (RR >= 2) eb[kEdge + 2 * slot + 1] = cur[g][1];
+      }
+    }
     __syncthreads();
     float nxt[G][4];
 #pragma unroll
     for (int g = 0; g < G; ++g) {
-      const int base = g * kRMThreads * 4 + tid * 4;
+      const int slot = 1 + g * (kRMThreads / 32) + wrp;
       float w[4 + 2 * kMaxR];  // prev[base-2 .. base+5]
       w[2] = cur[g][0]; w[3] = cur[g][1]; w[4] = cur[g][2]; w[5] = cur[g][3];
-      w[0] = (RL >= 2) ? buf[base - 2] : 0.f;
-      w[1] = (RL >= 1) ? buf[base - 1] : 0.f;
-      w[6] = (RR >= 1) ? buf[base + 4] : 0.f;
-      w[7] = (RR >= 2) ? buf[base + 5] : 0.f;
+      w[0] = w[1] = w[6] = w[7] = 0.f;
+      if (RL >= 1) {
+        w[1] = __shfl_up_sync(0xffffffffu, cur[g][3], 1);
+        if (lane == 0) w[1] = eb[2 * (slot - 1)];
+      }
+      if (RL >= 2) {
+        w[0] = __shfl_up_sync(0xffffffffu, cur[g][2], 1);
+        if (lane == 0) w[0] = eb[2 * (slot - 1) + 1];
+      }
+      if (RR >= 1) {
+        w[6] = __shfl_down_sync(0xffffffffu, cur[g][0], 1);
+        if (lane == 31) w[6] = eb[kEdge + 2 * (slot + 1)];
+      }
+      if (RR >= 2) {
+        w[7] = __shfl_down_sync(0xffffffffu, cur[g][1], 1);
+        if (lane == 31) w[7] = eb[kEdge + 2 * (slot + 1) + 1];
+      }
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         float v = cb[g][e];
@@ -186,6 +208,188 @@ int launch_g(const RMArgs& a, int rl, int rr, unsigned blocks, cudaStream_t s) {
   if (rl <= 1 && rr == 0) scan_rowmarch_kernel<G, 1, 0><<<blocks, kRMThreads, 0, s>>>(a);
   else if (rl <= 1 && rr <= 1) scan_rowmarch_kernel<G, 1, 1><<<blocks, kRMThreads, 0, s>>>(a);
   else scan_rowmarch_kernel<G, 2, 2><<<blocks, kRMThreads, 0, s>>>(a);
+  return after_launch("scan_rowmarch_kernel");
+}
+
+// ---- "fat" variant: one 512-thread block per SM owning ~16K columns -----------------------
+// benchmarks/expwrite.cu: the same 2-D write pattern runs at 6.0 TB/s with 1024 blocks of 2048
+// columns but at 7.1 TB/s with <= 128 blocks of 16384 columns (one long write stream per SM, 16
+// blocks per GPC), so wide grids use this kernel.  32 columns per thread would need 3 coefficient
+// registers per column; instead a group of 4 columns shares ONE coefficient set (regions are
+// rectangles, so almost every group is uniform) and the few groups a region boundary cuts
+// through fetch per-column sets from a small shared-memory exception table.
+constexpr int kFatThreads = 512, kFatG = 8, kFatSpan = kFatThreads * 4 * kFatG;   // 16384 columns
+constexpr int kMaxExc = 96;
+
+template <int RL, int RR>
+__global__ void __launch_bounds__(kFatThreads, 1)
+scan_rowmarch_fat_kernel(const __grid_constant__ RMArgs a) {
+  constexpr int G = kFatG, NW = kFatThreads / 32;
+  constexpr int kEdge = 2 * (G * NW + 2);
+  __shared__ float edge[2][2 * kEdge];
+  __shared__ float exc[kMaxExc][4][6];      // [slot][column][bias, a(-2..2)]
+  __shared__ int exc_count;
+  const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
+  for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+  const int64_t span0 = (int64_t)tile * a.own - a.halo_l;
+  const int64_t own0 = (int64_t)tile * a.own;
+  const int64_t own1 = min(own0 + a.own, a.nx);
+
+  float cur[G][4];
+  float ub[G], ul2[G], ul1[G], uc[G], ur1[G], ur2[G];
+  int xs[G];
+  (void)ul2; (void)ur2; (void)ul1; (void)ur1;
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+    const int64_t c0 = span0 + (int64_t)g * kFatThreads * 4 + tid * 4;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) cur[g][e] = 0.f;
+    xs[g] = -1;
+    if (a.n0 > 0) {
+      const float* prow = a.out + (int64_t)(a.n0 - 1) * a.nx;
+      if (c0 >= 0 && c0 + 3 < a.nx && ((a.nx & 3) == 0)) {
+        const float4 v = *reinterpret_cast<const float4*>(prow + c0);
+        cur[g][0] = v.x; cur[g][1] = v.y; cur[g][2] = v.z; cur[g][3] = v.w;
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (c0 + e >= 0 && c0 + e < a.nx) cur[g][e] = prow[c0 + e];
+      }
+    }
+  }
+  for (int i = tid; i < 4 * kEdge; i += kFatThreads) (&edge[0][0])[i] = 0.f;
+  __syncthreads();
+
+  int iv = 0;
+  while (iv + 1 < a.n_breaks && a.row_break[iv + 1] <= a.n0) ++iv;
+  int next_break = a.n0;
+
+  for (int n = a.n0; n < a.n1; ++n) {
+    if (n == next_break) {   // block-uniform: resolve the region functions of this row interval
+      while (iv + 1 < a.n_breaks && a.row_break[iv + 1] <= n) ++iv;
+      next_break = (iv + 1 < a.n_breaks) ? a.row_break[iv + 1] : 0x7fffffff;
+      if (tid == 0) exc_count = 0;
+      __syncthreads();
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        int fi[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int64_t c = span0 + (int64_t)g * kFatThreads * 4 + tid * 4 + e;
+          const int64_t gc = a.col_base + c;
+          fi[e] = (c < 0 || c >= a.nx || gc < 0 || gc >= a.gnx) ? -1 : rm_select(a, n, gc);
+        }
+        const bool uniform = fi[0] == fi[1] && fi[1] == fi[2] && fi[2] == fi[3];
+        RMFunc f;
+        f.bias = 0.f;
+#pragma unroll
+        for (int d = 0; d < 2 * kMaxR + 1; ++d) f.a[d] = 0.f;
+        if (uniform) {
+          if (fi[0] >= 0) f = a.func[fi[0]];
+          xs[g] = -1;
+        } else {
+          const int slot = atomicAdd(&exc_count, 1);
+          xs[g] = slot < kMaxExc ? slot : kMaxExc - 1;   // the host guarantees it fits
+          if (slot < kMaxExc) {
+            for (int e = 0; e < 4; ++e) {
+              RMFunc fe;
+              fe.bias = 0.f;
+              for (int d = 0; d < 2 * kMaxR + 1; ++d) fe.a[d] = 0.f;
+              if (fi[e] >= 0) fe = a.func[fi[e]];
+              exc[slot][e][0] = fe.bias;
+              for (int d = 0; d < 2 * kMaxR + 1; ++d) exc[slot][e][1 + d] = fe.a[d];
+            }
+          }
+        }
+        ub[g] = f.bias;
+        ul2[g] = f.a[0]; ul1[g] = f.a[1]; uc[g] = f.a[2]; ur1[g] = f.a[3]; ur2[g] = f.a[4];
+      }
+      __syncthreads();
+    }
+    float* eb = edge[n & 1];
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      const int slot = 1 + g * NW + wrp;
+      if (RL >= 1 && lane == 31) {
+        eb[2 * slot] = cur[g][3];
+        if (RL >= 2) eb[2 * slot + 1] = cur[g][2];
+      }
+      if (RR >= 1 && lane == 0) {
+        eb[kEdge + 2 * slot] = cur[g][0];
+        if (RR >= 2) eb[kEdge + 2 * slot + 1] = cur[g][1];
+      }
+    }
+    __syncthreads();
+    float* orow = a.out + (int64_t)n * a.nx;
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      const int slot = 1 + g * NW + wrp;
+      float w[4 + 2 * kMaxR];
+      w[2] = cur[g][0]; w[3] = cur[g][1]; w[4] = cur[g][2]; w[5] = cur[g][3];
+      w[0] = w[1] = w[6] = w[7] = 0.f;
+      if (RL >= 1) {
+        w[1] = __shfl_up_sync(0xffffffffu, cur[g][3], 1);
+        if (lane == 0) w[1] = eb[2 * (slot - 1)];
+      }
+      if (RL >= 2) {
+        w[0] = __shfl_up_sync(0xffffffffu, cur[g][2], 1);
+        if (lane == 0) w[0] = eb[2 * (slot - 1) + 1];
+      }
+      if (RR >= 1) {
+        w[6] = __shfl_down_sync(0xffffffffu, cur[g][0], 1);
+        if (lane == 31) w[6] = eb[kEdge + 2 * (slot + 1)];
+      }
+      if (RR >= 2) {
+        w[7] = __shfl_down_sync(0xffffffffu, cur[g][1], 1);
+        if (lane == 31) w[7] = eb[kEdge + 2 * (slot + 1) + 1];
+      }
+      float v[4];
+      if (xs[g] < 0) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          float t = ub[g];
+          if (RL >= 2) t = fmaf(ul2[g], w[e + 0], t);
+          if (RL >= 1) t = fmaf(ul1[g], w[e + 1], t);
+          t = fmaf(uc[g], w[e + 2], t);
+          if (RR >= 1) t = fmaf(ur1[g], w[e + 3], t);
+          if (RR >= 2) t = fmaf(ur2[g], w[e + 4], t);
+          v[e] = t;
+        }
+      } else {
+        const float(*x)[6] = exc[xs[g]];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          float t = x[e][0];
+          if (RL >= 2) t = fmaf(x[e][1], w[e + 0], t);
+          if (RL >= 1) t = fmaf(x[e][2], w[e + 1], t);
+          t = fmaf(x[e][3], w[e + 2], t);
+          if (RR >= 1) t = fmaf(x[e][4], w[e + 3], t);
+          if (RR >= 2) t = fmaf(x[e][5], w[e + 4], t);
+          v[e] = t;
+        }
+      }
+      const int64_t c0 = span0 + (int64_t)g * kFatThreads * 4 + tid * 4;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) cur[g][e] = v[e];
+      if (c0 >= own0 && c0 < own1) {
+        if (c0 + 3 < own1 && ((a.nx & 3) == 0)) {
+          __stcs(reinterpret_cast<float4*>(orow + c0), make_float4(v[0], v[1], v[2], v[3]));
+        } else {
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            if (c0 + e < own1) orow[c0 + e] = v[e];
+        }
+      }
+    }
+  }
+  __syncthreads();   // the shared tables are reused by the next tile
+  }
+}
+
+int launch_fat(const RMArgs& a, int rl, int rr, unsigned blocks, cudaStream_t s) {
+  if (rl <= 1 && rr == 0) scan_rowmarch_fat_kernel<1, 0><<<blocks, kFatThreads, 0, s>>>(a);
+  else if (rl <= 1 && rr <= 1) scan_rowmarch_fat_kernel<1, 1><<<blocks, kFatThreads, 0, s>>>(a);
+  else scan_rowmarch_fat_kernel<2, 2><<<blocks, kFatThreads, 0, s>>>(a);
   return after_launch("scan_rowmarch_kernel");
 }
 
@@ -258,8 +462,33 @@ int scan_rowmarch_shard(const KxGeom& g, const KxProgram& p, const void* coef_de
   a.nt = nt;
   a.halo_l = ((kT * rl + 3) / 4) * 4;
   a.halo_r = ((kT * rr + 3) / 4) * 4;
-  // pick G (columns per thread = 4G) so that the grid fills the machine in whole waves
   const int64_t nx = a.nx;
+  // wide grids: one fat block per SM (see scan_rowmarch_fat_kernel); needs rectangular column keys
+  {
+    bool col_steps = false;
+    for (int k = 0; k < p.n_keys; ++k)
+      if (p.key[k].n_items >= 2 && p.key[k].item[1].kind == KX_KEY_RANGE_STEP && p.key[k].item[1].step != 1 &&
+          p.key[k].item[1].step != -1)
+        col_steps = true;
+    const int fat_own = kFatSpan - a.halo_l - a.halo_r;
+    const int64_t ntiles = (nx + fat_own - 1) / fat_own;
+    // measured on B200 (C4, nx = 2^21): thin 6.65 ms, fat 7.96 ms -- with one 16-warp block per SM the
+    // fat kernel is issue/latency-bound, so it stays opt-in (KX_RM_FAT=1) until it is tuned further
+    const bool fat_on = getenv("KX_RM_FAT") != nullptr;
+    if (!col_steps && fat_on && ntiles >= 96 && ntiles < 0x7fffffff && 4 * p.n_keys + 8 <= kMaxExc) {
+      a.own = fat_own;
+      a.ntiles = (int)ntiles;
+      const unsigned grid = ntiles <= 148 ? (unsigned)ntiles : 128u;
+      for (int n0 = 0; n0 < nt; n0 += kT) {
+        a.n0 = n0;
+        a.n1 = n0 + kT < nt ? n0 + kT : nt;
+        int rc = launch_fat(a, rl, rr, grid, s);
+        if (rc) return rc;
+      }
+      return KX_OK;
+    }
+  }
+  // otherwise: pick G (columns per thread = 4G) for the thin kernel
   int G = 2;
   if (nx <= 2048) G = 1;
   const int span = kRMThreads * 4 * G;
