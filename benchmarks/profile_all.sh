@@ -1,0 +1,14 @@
+#!/bin/bash
+# ncu captures of every roofline-tuned kernel on its BASELINE config (run under gpurun, 1 GPU).
+# Each kernel is profiled only after the same command exited 0 without ncu.
+set -u
+mkdir -p gpurun_out
+NCU="ncu --set full --clock-control none --import-source on"
+python benchmarks/run_configs.py --reps 6 > gpurun_out/configs_plain.jsonl 2> gpurun_out/configs_plain.err || exit 1
+$NCU -k regex:stencil2d -s 8 -c 1 -o gpurun_out/p_stencil2d python benchmarks/run_configs.py --only C2 --reps 2 > /dev/null 2>&1
+$NCU -k regex:stencil3d_star -s 3 -c 1 -o gpurun_out/p_stencil3d_star python benchmarks/run_configs.py --only C5 --reps 2 > /dev/null 2>&1
+$NCU -k regex:scan_rowmarch -s 70 -c 1 -o gpurun_out/p_rowmarch python benchmarks/run_configs.py --only C4 --reps 2 > /dev/null 2>&1
+$NCU -k regex:conv_fwd -s 8 -c 1 -o gpurun_out/p_conv_fwd python benchmarks/run_configs.py --only C3a --reps 2 > /dev/null 2>&1
+$NCU -k regex:conv_wgrad_kernel -s 3 -c 1 -o gpurun_out/p_conv_wgrad python benchmarks/run_configs.py --only C3a --reps 2 > /dev/null 2>&1
+$NCU -k regex:patch2d -s 8 -c 1 -o gpurun_out/p_patch2d python benchmarks/run_configs.py --only C3b --reps 2 > /dev/null 2>&1
+ls -la gpurun_out/p_*.ncu-rep

@@ -30,18 +30,29 @@ def peak():
         return 6650.0
 
 
-def timeit(fn, reps, warm=3):
+def timeit(fn, reps, warm=3, inner=None):
+    """Median / min time per call; each sample brackets `inner` back-to-back calls with CUDA
+    events (sustained rate: launch gaps of a single call are not charged to the kernel)."""
     for _ in range(warm):
         fn()
     torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    fn()
+    e1.record()
+    torch.cuda.synchronize()
+    one = max(e0.elapsed_time(e1), 1e-3)
+    if inner is None:
+        inner = max(1, min(20, int(5.0 / one)))   # ~5 ms of work per sample
     times = []
     for _ in range(reps):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        fn()
+        for _ in range(inner):
+            fn()
         e1.record()
         torch.cuda.synchronize()
-        times.append(e0.elapsed_time(e1))
+        times.append(e0.elapsed_time(e1) / inner)
     times.sort()
     return times[len(times) // 2], times[0]
 

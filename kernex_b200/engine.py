@@ -509,7 +509,7 @@ def offset_kernel_map(func_map: dict, shape, kernel_size, strides, offset, relat
 
 
 def _write_back(x, res, shape, strides, offset, what):
-    if tuple(res.shape) > tuple(x.shape):  # lexicographic, as the reference (map.py:152)
+    if tuple(res.shape) > tuple(x.shape) or res.dim() != x.dim():  # lexicographic, as the reference (map.py:152)
         raise ValueError(f"{what} operation output must be scalar. Found result.shape={tuple(res.shape)}")
     out = x.clone()
     sl = tuple(slice(o0, n - o1, s) for n, s, (o0, o1) in zip(shape, strides, offset))
