@@ -58,11 +58,34 @@ patch2d_kernel(const __grid_constant__ P2Args a) {
     }
   };
 
+  // software pipeline: the next input row travels global -> registers while this row's
+  // patches are built and written out, and only then registers -> ring (its slot still holds
+  // the oldest row of the current window until every thread has finished building)
+  constexpr int NLD = (kTW + KX - 1 + kPT - 1) / kPT;
+  uint32_t nextv[NLD];
+  auto fetch_row = [&](int iy) {
+    const bool row_ok = (iy >= 0) && (iy < a.hin);
+    const uint32_t* rp = in + (int64_t)iy * a.win;
 #pragma unroll
-  for (int ky = 0; ky < KY - 1; ++ky) load_row(r0 - a.ly + ky, (r0 + ky) % KY);
+    for (int k = 0; k < NLD; ++k) {
+      const int c = tid + k * kPT;
+      const int gx = x0 - a.lx + c;
+      nextv[k] = (row_ok && c < kTW + KX - 1 && gx >= 0 && gx < a.win) ? __ldg(rp + gx) : 0u;
+    }
+  };
+  auto commit_row = [&](int slot) {
+#pragma unroll
+    for (int k = 0; k < NLD; ++k) {
+      const int c = tid + k * kPT;
+      if (c < kTW + KX - 1) rows[slot][c] = nextv[k];
+    }
+  };
+
+#pragma unroll
+  for (int ky = 0; ky < KY; ++ky) load_row(r0 - a.ly + ky, (r0 + ky) % KY);
 
   for (int r = r0; r < r1; ++r) {
-    load_row(r - a.ly + KY - 1, (r + KY - 1) % KY);
+    if (r + 1 < r1) fetch_row(r + 1 - a.ly + KY - 1);
     __syncthreads();                               // ring complete; previous row's staging drained
     // ---- build this thread's 4 windows --------------------------------------------------
     uint32_t v[KY][NC];
@@ -94,6 +117,7 @@ patch2d_kernel(const __grid_constant__ P2Args a) {
     for (int q = 0; q < kWPT * NT / 4; ++q)
       *reinterpret_cast<uint4*>(sp + 4 * q) = make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
     __syncthreads();
+    if (r + 1 < r1) commit_row((r + KY) % KY);     // every thread has finished reading the ring
     // ---- coalesced write-out of the row segment ------------------------------------------
     uint32_t* dst = out + ((int64_t)r * a.wout + x0) * NT;
     if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
