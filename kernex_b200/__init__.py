@@ -8,9 +8,10 @@ Public surface = the reference's (``kernex/__init__.py:15-28``): ``kmap``, ``ksc
 from .engine import kernel_map, kernel_scan, offset_kernel_map, offset_kernel_scan
 from .errors import EngineUnavailableError, UnsupportedStencilError
 from .interface import kmap, kscan, smap, sscan
+from .batching import vmap
 
 __all__ = (
-    "kmap", "kscan", "smap", "sscan",
+    "kmap", "kscan", "smap", "sscan", "vmap",
     "kernel_map", "kernel_scan", "offset_kernel_map", "offset_kernel_scan",
     "UnsupportedStencilError", "EngineUnavailableError",
 )

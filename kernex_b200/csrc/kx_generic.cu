@@ -14,48 +14,6 @@ namespace {
 
 constexpr int kThreads = 256;
 
-// ---- region -> function selection (utils.py:338-382 + lax.switch clamp) ----
-template <typename TC>
-__device__ __forceinline__ int select_func(const DevProgram<TC>& p, const int64_t* centre) {
-  if (p.n_funcs <= 1) return 0;
-  // keys are stored grouped by function in insertion order: scanning them backwards
-  // finds the last-inserted function with any matching key
-  for (int k = p.n_keys - 1; k >= 0; --k) {
-    const KxKey& key = p.key[k];
-    bool ok = true;
-    for (int d = 0; d < key.n_items; ++d) {
-      const KxKeyItem& it = key.item[d];
-      const int64_t c = centre[d];
-      bool m = true;
-      if (it.kind == KX_KEY_EQ) m = (c == it.a);
-      else if (it.kind == KX_KEY_RANGE) m = (it.a <= c) && (c < it.b);
-      else if (it.kind == KX_KEY_RANGE_STEP) m = (it.a <= c) && (c < it.b) && (c % it.step == 0);
-      ok = ok && m;
-    }
-    if (ok) return key.func;
-  }
-  return 0;  // nothing matched: first-inserted function
-}
-
-struct Strides {
-  int64_t v[KX_MAX_DIMS];
-};
-
-__device__ __forceinline__ Strides suffix_strides(const int64_t* shape, int nd) {
-  Strides s;
-  int64_t acc = 1;
-#pragma unroll
-  for (int d = KX_MAX_DIMS - 1; d >= 0; --d) {
-    if (d < nd) {
-      s.v[d] = acc;
-      acc *= shape[d];
-    } else {
-      s.v[d] = 0;
-    }
-  }
-  return s;
-}
-
 // value of one window function at window `origin`, reading `src` with zero fill
 // outside [0, shape) (src_off shifts origin into src coordinates for the scan state)
 template <typename TIN, typename TC, bool kBounds>
@@ -454,7 +412,7 @@ int64_t scan_state_elems(const KxGeom& g) {
 
 int launch_generic_scan(const KxGeom& g, const KxProgram& prog, const void* in, const void* coef_dev,
                         void* state, void* out, int reverse, cudaStream_t s) {
-  const bool fl = program_has_float_coefs(prog) || coef_dev != nullptr;
+  const bool fl = program_has_float_coefs(prog);  // coef_dev carries the compute type
   if (g.in_dtype == KX_F32) return launch_scan_t<float, float>(g, prog, in, coef_dev, state, out, reverse, s);
   if (g.in_dtype == KX_I32 && !fl)
     return launch_scan_t<int32_t, int32_t>(g, prog, in, coef_dev, state, out, reverse, s);

@@ -39,6 +39,48 @@ inline void make_dev_program(const KxProgram& p, int ndim, DevProgram<TC>& d) {
   }
 }
 
+// ---- region -> function selection (utils.py:338-382 + lax.switch clamp) ----
+template <typename TC>
+__device__ __forceinline__ int select_func(const DevProgram<TC>& p, const int64_t* centre) {
+  if (p.n_funcs <= 1) return 0;
+  // keys are stored grouped by function in insertion order: scanning them backwards
+  // finds the last-inserted function with any matching key
+  for (int k = p.n_keys - 1; k >= 0; --k) {
+    const KxKey& key = p.key[k];
+    bool ok = true;
+    for (int d = 0; d < key.n_items; ++d) {
+      const KxKeyItem& it = key.item[d];
+      const int64_t c = centre[d];
+      bool m = true;
+      if (it.kind == KX_KEY_EQ) m = (c == it.a);
+      else if (it.kind == KX_KEY_RANGE) m = (it.a <= c) && (c < it.b);
+      else if (it.kind == KX_KEY_RANGE_STEP) m = (it.a <= c) && (c < it.b) && (c % it.step == 0);
+      ok = ok && m;
+    }
+    if (ok) return key.func;
+  }
+  return 0;  // nothing matched: first-inserted function
+}
+
+struct Strides {
+  int64_t v[KX_MAX_DIMS];
+};
+
+__device__ __forceinline__ Strides suffix_strides(const int64_t* shape, int nd) {
+  Strides s;
+  int64_t acc = 1;
+#pragma unroll
+  for (int d = KX_MAX_DIMS - 1; d >= 0; --d) {
+    if (d < nd) {
+      s.v[d] = acc;
+      acc *= shape[d];
+    } else {
+      s.v[d] = 0;
+    }
+  }
+  return s;
+}
+
 struct MapArgs {
   KxGeom g;
   const void* in;
@@ -76,6 +118,8 @@ int try_conv2d(const MapArgs& a, const KxProgram& prog, cudaStream_t s);
 int64_t conv_wgrad_scratch_bytes(const KxGeom& g, const KxProgram& prog);
 int try_conv_wgrad(const KxGeom& g, const KxProgram& prog, const void* x, const void* gout, void* scratch,
                    void* dcoef, cudaStream_t s);
+int launch_scan_wavefront(const KxGeom& g, const KxProgram& prog, const void* in, const void* coef_dev, void* out,
+                          int reverse, cudaStream_t s);
 int try_scan_rowmarch(const KxGeom& g, const KxProgram& prog, const void* in, const void* coef_dev,
                       void* out, int reverse, cudaStream_t s);
 int scan_rowmarch_shard(const KxGeom& g, const KxProgram& prog, const void* coef_dev, void* out, int reverse,

@@ -1,0 +1,256 @@
+// kscan as a persistent hyperplane-wavefront kernel.
+//
+// kernel_scan (kernex/_src/scan.py:84-113) sweeps all windows in row-major order, carrying the
+// padded array and writing each result at the window centre before the next window is read
+// (scan.py:46-62).  Every cell is written at most once (window j owns the cell j*s - lo + (k-1)/2),
+// so what a window reads from cell x is fully determined by WHO writes x:
+//   * nobody, or a window later in the sweep  -> the original (zero padded) input   [old]
+//   * a window earlier in the sweep           -> that window's result              [new]
+// Reading old values from `in` and new values from `out` removes every write-after-read hazard and
+// leaves only true dependencies.  A tap at centre-relative cell offset `off` depends on window
+// j + delta, delta = off / stride (when divisible in every axis); it is a true dependency when
+// delta is lexicographically negative (positive for lax.scan(reverse=True)).
+//
+// Schedule: t(j) = sum_d a_d * j_d with non-negative integers a_d chosen on the host so that
+// a . delta < 0 for every true dependency of every function of the mesh.  All windows of one
+// hyperplane t are independent and run in parallel; hyperplanes are separated by a block barrier
+// (small fronts: one CTA) or a cooperative grid barrier (large fronts).  Examples: time marching
+// (taps on the row above only) a = (1, 0): a whole row per step; Gauss-Seidel / README RK4
+// (x[0,-1], x[-1,0]) a = (1, 1): anti-diagonals; a 3x3 window reading x[-1,+1] a = (2, 1).
+//
+// The row-marching kernel (kx_scan_rowmarch.cu) takes the HBM-bound time-marching case; this one is
+// the general path and is bit-identical to the one-thread sweep (scan_sequential_kernel), which is
+// kept behind KX_SCAN_SEQUENTIAL=1 as a cross-check.
+#include <cooperative_groups.h>
+
+#include "kx_internal.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace kx {
+
+namespace {
+
+constexpr int kWaveThreads = 256;
+constexpr int kWaveSingleThreads = 1024;
+constexpr int64_t kWaveSingleMax = 16384;  // fronts up to this size run on one CTA (block barrier ~10x cheaper)
+
+struct WaveArgs {
+  KxGeom g;
+  int64_t n_steps;
+  int64_t n_free;                    // threads of work per hyperplane
+  int32_t a[KX_MAX_DIMS];            // hyperplane coefficients
+  int32_t solved;                    // axis recovered from t (a[solved] != 0) or -1
+  int32_t reverse;
+};
+
+template <typename TIN>
+__device__ __forceinline__ TIN ld_new(const TIN* p) {
+  return __ldcg(p);  // results of other threads: L2 is the coherence point
+}
+
+template <typename TIN, typename TC>
+__device__ __forceinline__ void wave_window(const WaveArgs& a, const DevProgram<TC>& p, const Strides& ist,
+                                            const Strides& ost, const TIN* __restrict__ in, TIN* out,
+                                            const TC* __restrict__ coef_dev, const int64_t* j) {
+  const int nd = a.g.ndim;
+  int64_t origin[KX_MAX_DIMS], centre[KX_MAX_DIMS];
+  int64_t w = 0;
+#pragma unroll
+  for (int d = 0; d < KX_MAX_DIMS; ++d) {
+    if (d < nd) {
+      origin[d] = j[d] * a.g.stride[d] - a.g.lo[d];
+      centre[d] = origin[d] + (a.g.ksize[d] - 1) / 2;
+      w += j[d] * ost.v[d];
+    }
+  }
+  const int f = select_func(p, centre);
+  const int kind = p.func[f].kind;
+  const int t0 = p.func[f].tap_begin, t1 = p.func[f].tap_end;
+  TC acc = (kind == KX_AFFINE) ? p.func[f].bias : TC(0);
+  for (int t = t0; t < t1; ++t) {
+    int64_t ioff = 0, woff = 0;
+    bool inb = true, writer = true;
+    int cmp = 0;
+#pragma unroll
+    for (int d = 0; d < KX_MAX_DIMS; ++d) {
+      if (d < nd) {
+        const int64_t c = origin[d] + p.tap_off[t][d];
+        inb = inb && (c >= 0) && (c < a.g.in_shape[d]);
+        ioff += c * ist.v[d];
+        const int64_t q = c - centre[d] + j[d] * a.g.stride[d];  // = jw * stride when x is a window centre
+        const int64_t jw = q / a.g.stride[d];
+        writer = writer && (q >= 0) && (jw * a.g.stride[d] == q) && (jw < a.g.out_shape[d]);
+        woff += jw * ost.v[d];
+        if (cmp == 0) cmp = (jw < j[d]) ? -1 : ((jw > j[d]) ? 1 : 0);
+      }
+    }
+    const bool is_new = writer && (a.reverse ? cmp > 0 : cmp < 0);
+    TC v;
+    if (is_new) v = (TC)ld_new(out + woff);
+    else v = inb ? (TC)in[ioff] : TC(0);
+    if (kind == KX_AFFINE) {
+      const TC c = coef_dev ? coef_dev[t] : p.coef[t];
+      acc = mad_wrap(c, v, acc);
+    } else if (kind == KX_REDUCE_MAX) {
+      acc = (t == t0) ? v : (v > acc ? v : acc);
+    } else if (kind == KX_REDUCE_MIN) {
+      acc = (t == t0) ? v : (v < acc ? v : acc);
+    } else {  // scalar KX_GATHER: x[tap]
+      acc = v;
+    }
+  }
+  if (kind == KX_AFFINE && p.func[f].post_div != 0.f) acc = (TC)((float)acc / p.func[f].post_div);
+  out[w] = (TIN)acc;  // cast to the carried dtype on write (scan.py:50)
+}
+
+template <typename TIN, typename TC>
+__global__ void __launch_bounds__(kWaveSingleThreads)
+scan_wavefront_kernel(const __grid_constant__ WaveArgs a, const __grid_constant__ DevProgram<TC> p,
+                      const TIN* __restrict__ in, TIN* out, const TC* __restrict__ coef_dev) {
+  const int nd = a.g.ndim;
+  const Strides ist = suffix_strides(a.g.in_shape, nd);
+  const Strides ost = suffix_strides(a.g.out_shape, nd);
+  const bool multi = gridDim.x > 1;
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t t = 0; t < a.n_steps; ++t) {
+    for (int64_t i = tid; i < a.n_free; i += nthreads) {
+      int64_t jp[KX_MAX_DIMS];  // sweep-order coordinates (mirrored when reverse)
+      int64_t r = i, rem = t;
+#pragma unroll
+      for (int d = KX_MAX_DIMS - 1; d >= 0; --d) {
+        if (d < nd && d != a.solved) {
+          jp[d] = r % a.g.out_shape[d];
+          r /= a.g.out_shape[d];
+          rem -= (int64_t)a.a[d] * jp[d];
+        }
+      }
+      if (a.solved >= 0) {
+        const int64_t as = a.a[a.solved];
+        if (rem < 0 || rem % as != 0) continue;
+        const int64_t js = rem / as;
+        if (js >= a.g.out_shape[a.solved]) continue;
+#pragma unroll
+        for (int d = 0; d < KX_MAX_DIMS; ++d)
+          if (d == a.solved) jp[d] = js;
+      }
+      int64_t j[KX_MAX_DIMS];
+#pragma unroll
+      for (int d = 0; d < KX_MAX_DIMS; ++d)
+        if (d < nd) j[d] = a.reverse ? a.g.out_shape[d] - 1 - jp[d] : jp[d];
+      wave_window<TIN, TC>(a, p, ist, ost, in, out, coef_dev, j);
+    }
+    if (t + 1 < a.n_steps) {
+      if (multi) {
+        cg::this_grid().sync();
+      } else {
+        __threadfence_block();
+        __syncthreads();
+      }
+    }
+  }
+}
+
+// smallest non-negative integer hyperplane a with a . delta < 0 for every true dependency
+bool plan_wavefront(const KxGeom& g, const KxProgram& prog, int reverse, WaveArgs& a) {
+  const int nd = g.ndim;
+  int64_t acoef[KX_MAX_DIMS] = {0, 0, 0, 0};
+  for (int d = nd - 1; d >= 0; --d) {
+    int64_t need = 0;
+    for (int f = 0; f < prog.n_funcs; ++f) {
+      for (int t = prog.func[f].tap_begin; t < prog.func[f].tap_end; ++t) {
+        int64_t delta[KX_MAX_DIMS];
+        bool hits = true;
+        for (int e = 0; e < nd; ++e) {
+          const int off = prog.tap_off[t][e] - (g.ksize[e] - 1) / 2;
+          if (off % g.stride[e] != 0) hits = false;
+          delta[e] = (off / g.stride[e]) * (reverse ? -1 : 1);
+        }
+        if (!hits) continue;
+        int first = -1;
+        for (int e = 0; e < nd; ++e)
+          if (delta[e] != 0) {
+            first = e;
+            break;
+          }
+        if (first != d || delta[d] >= 0) continue;  // not a true dependency led by axis d
+        int64_t rhs = 0;
+        for (int e = d + 1; e < nd; ++e) rhs += acoef[e] * delta[e];
+        if (rhs >= 0) {
+          const int64_t v = rhs / (-delta[d]) + 1;
+          if (v > need) need = v;
+        }
+      }
+    }
+    acoef[d] = need;
+  }
+  memset(&a, 0, sizeof(a));
+  a.g = g;
+  a.reverse = reverse;
+  a.n_steps = 1;
+  a.solved = -1;
+  for (int d = 0; d < nd; ++d) {
+    if (acoef[d] > 0x7fffffff) return false;
+    a.a[d] = (int32_t)acoef[d];
+    a.n_steps += acoef[d] * (g.out_shape[d] - 1);
+    // solve for the longest dependent axis: fewest idle threads per hyperplane
+    if (acoef[d] != 0 && (a.solved < 0 || g.out_shape[d] >= g.out_shape[a.solved])) a.solved = d;
+  }
+  a.n_free = 1;
+  for (int d = 0; d < nd; ++d)
+    if (d != a.solved) a.n_free *= g.out_shape[d];
+  return true;
+}
+
+template <typename TIN, typename TC>
+int launch_wave_t(const KxGeom& g, const KxProgram& prog, const void* in, const void* coef_dev, void* out,
+                  int reverse, cudaStream_t s) {
+  static thread_local DevProgram<TC> dp;
+  static thread_local WaveArgs a;
+  make_dev_program<TC>(prog, g.ndim, dp);
+  if (!plan_wavefront(g, prog, reverse, a)) return KX_ERR_UNSUPPORTED;
+  if (prod(g.out_shape, g.ndim) <= 0) return KX_OK;
+  const TIN* in_p = (const TIN*)in;
+  TIN* out_p = (TIN*)out;
+  const TC* coef_p = (const TC*)coef_dev;
+  auto kern = scan_wavefront_kernel<TIN, TC>;
+  if (a.n_free <= kWaveSingleMax || a.n_steps == 1) {
+    int threads = kWaveSingleThreads;
+    int64_t blocks = 1;
+    if (a.n_steps == 1) {  // no dependencies at all: a plain parallel map over the windows
+      threads = kWaveThreads;
+      blocks = (a.n_free + threads - 1) / threads;
+      const int64_t cap = (int64_t)sm_count() * 8;
+      if (blocks > cap) blocks = cap;
+    } else if (a.n_free < kWaveSingleThreads) {
+      threads = (int)((a.n_free + 31) / 32 * 32);
+    }
+    kern<<<(unsigned)blocks, threads, 0, s>>>(a, dp, in_p, out_p, coef_p);
+    return after_launch("scan_wavefront_kernel");
+  }
+  int per_sm = 0;
+  KX_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kWaveThreads, 0));
+  if (per_sm < 1) return fail(KX_ERR_CUDA, "scan_wavefront_kernel does not fit an SM");
+  int64_t blocks = (a.n_free + kWaveThreads - 1) / kWaveThreads;
+  const int64_t cap = (int64_t)sm_count() * per_sm;
+  if (blocks > cap) blocks = cap;
+  void* params[] = {(void*)&a, (void*)&dp, (void*)&in_p, (void*)&out_p, (void*)&coef_p};
+  KX_CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)kern, dim3((unsigned)blocks), dim3(kWaveThreads), params, 0, s));
+  return after_launch("scan_wavefront_kernel");
+}
+
+}  // namespace
+
+int launch_scan_wavefront(const KxGeom& g, const KxProgram& prog, const void* in, const void* coef_dev, void* out,
+                          int reverse, cudaStream_t s) {
+  bool fl = false;  // coef_dev carries the compute type
+  for (int f = 0; f < prog.n_funcs; ++f)
+    if (prog.func[f].kind == KX_AFFINE && !prog.func[f].coef_is_int) fl = true;
+  if (g.in_dtype == KX_F32) return launch_wave_t<float, float>(g, prog, in, coef_dev, out, reverse, s);
+  if (g.in_dtype == KX_I32 && !fl) return launch_wave_t<int32_t, int32_t>(g, prog, in, coef_dev, out, reverse, s);
+  if (g.in_dtype == KX_I32) return launch_wave_t<int32_t, float>(g, prog, in, coef_dev, out, reverse, s);
+  return KX_ERR_UNSUPPORTED;
+}
+
+}  // namespace kx

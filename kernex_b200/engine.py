@@ -186,7 +186,7 @@ class _Program:
                     raise UnsupportedStencilError("a device-resident additive term (bias) is not supported")
                 f.bias = float(s.bias.const)
                 f.post_div = float(s.post_div)
-                f.coef_is_int = int(s.integral)
+                f.coef_is_int = int(s.integral or not s.weak_float)  # integer device weights stay integer
             else:
                 f.coef_is_int = 1
         p.n_taps = t

@@ -106,6 +106,7 @@ class KernelInterface:
                                 self.transform_kind, self.transform_kwargs)
             return op(array, *args, **kwargs)
 
+        call._kx_interface, call._kx_func = self, func  # lets batching.vmap fold a batch axis into the launch
         return call
 
     def __call__(self, *args, **kwargs):

@@ -612,10 +612,13 @@ def trace_function(func: Callable, kernel_size, relative: bool, args=(), kwargs=
         raise
     except TypeError as e:  # e.g. math.sqrt(Affine)
         raise UnsupportedStencilError(f"window function is outside the affine / reduce / gather classes: {e}") from e
-    return classify(result, kernel_size), device_args
+    int_args = {i for i, t in device_args.items() if not (t.dtype.is_floating_point or t.dtype.is_complex)}
+    return classify(result, kernel_size, int_args), device_args
 
 
-def classify(result, kernel_size) -> FuncSpec:
+def classify(result, kernel_size, int_device_args=frozenset()) -> FuncSpec:
+    """``int_device_args``: indices of device-resident arguments of integer dtype (they keep an
+    integer stencil integer, like host integer weights do)."""
     if isinstance(result, Reduce):
         return FuncSpec(kind=result.op, taps=list(result.taps))
     if isinstance(result, SymArray) or (isinstance(result, np.ndarray) and result.dtype == object):
@@ -624,7 +627,7 @@ def classify(result, kernel_size) -> FuncSpec:
         if all(isinstance(v, Affine) and v.is_single_tap() for v in flat):
             return FuncSpec(kind="gather", taps=[next(iter(v.terms)) for v in flat], out_shape=tuple(data.shape))
         if data.ndim == 0:
-            return classify(flat[0], kernel_size)
+            return classify(flat[0], kernel_size, int_device_args)
         raise UnsupportedStencilError(
             "vector-valued window functions are only supported when every element is a plain window element "
             "(patch extraction)")
@@ -638,7 +641,8 @@ def classify(result, kernel_size) -> FuncSpec:
             taps.append(t)
             coefs.append(c)
         weak_float = any(isinstance(c.const, float) for c in coefs + [result.bias]) or \
-            any(not c.is_const for c in coefs + [result.bias]) or result.post_div is not None
+            any(isinstance(sc, float) or arg not in int_device_args
+                for c in coefs + [result.bias] for (arg, _), sc in c.w.items()) or result.post_div is not None
         return FuncSpec(kind="affine", taps=taps, coefs=coefs, bias=result.bias, weak_float=weak_float,
                         post_div=float(result.post_div or 0.0))
     raise UnsupportedStencilError(

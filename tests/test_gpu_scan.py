@@ -1,5 +1,5 @@
 """GPU parity of kscan: the row-marching fast path (time-marching stencils that read only
-the row above) and the generic plane-parallel / sequential kernels, against the oracle."""
+the row above) and the general wavefront kernel, against the oracle."""
 from __future__ import annotations
 
 import numpy as np
@@ -85,11 +85,11 @@ def test_rowmarch_random_meshes_match_literal_oracle(kex, seed):
     np.testing.assert_allclose(got, want, rtol=2e-5, atol=2e-5)
 
 
-def test_scan_reading_same_row_uses_the_sequential_kernel(kex):
+def test_scan_reading_same_row_uses_the_wavefront_kernel(kex):
     # README kscan sum (README.md:63-69): reads the just-written left neighbour -> serial
     x = np.array([1, 2, 3, 4, 5], dtype=np.int32)
     out = kex.kscan(kernel_size=(3,))(lambda v: np.sum(v))(x)
-    assert _last_kernel() == "scan_sequential_kernel"
+    assert _last_kernel() == "scan_wavefront_kernel"
     np.testing.assert_array_equal(out, [6, 13, 22])
     rng = np.random.default_rng(2)
     x2 = rng.integers(-3, 4, (6, 7)).astype(np.int32)
@@ -101,7 +101,7 @@ def test_scan_reading_same_row_uses_the_sequential_kernel(kex):
 
 def test_diffusion_sscan_matches_numpy_fdm(kex):
     """tests/test_interface.py:28-97: 3-D sscan with named axes and 4 runtime scalars vs the
-    NumPy FDM loop (plane-parallel generic scan kernel + offset write-back)."""
+    NumPy FDM loop (wavefront kernel, one plane per step, + offset write-back)."""
     nx = ny = 10
     nt, nu = 5, 1.0
     dx, dy = 2 / (nx - 1), 2 / (ny - 1)
@@ -124,7 +124,7 @@ def test_diffusion_sscan_matches_numpy_fdm(kex):
                          + nu * dt / dy ** 2 * (un[2:, 1:-1] - 2 * un[1:-1, 1:-1] + un[0:-2, 1:-1]))
         u[0, :] = u[-1, :] = u[:, 0] = u[:, -1] = 1
     got = diffusion(U, nu, dt, dx, dy)
-    assert _last_kernel() in ("scan_plane_kernel", "scan_sequential_kernel")
+    assert _last_kernel() == "scan_wavefront_kernel"
     np.testing.assert_allclose(got[-2], u, rtol=1e-5, atol=1e-5)
 
 
