@@ -219,6 +219,291 @@ conv_wgrad_kernel(const __grid_constant__ ConvArgs<float> a) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Aligned-row variants (rows 16-byte aligned, the usual case).  The register-queue kernels above
+// fetch 3 vectors per channel row for 'same' padding, keep C*KY rows live (96-115 registers) and
+// consume every load right after issuing it: ncu shows them latency-bound at ~4.7 TB/s with 20
+// warps per SM.  Here
+//   * every WARP owns a private shared-memory ring of kRing input rows (C channels [+ the
+//     cotangent row for the weight gradient] x (128 + 2*4) columns).  Lane l copies its own 16
+//     bytes of each channel row with cp.async.cg (LDGSTS, zero-fill = the reference's zero
+//     padding), lanes 0 / 31 also copy the left / right halo vector; rows are requested
+//     kRing-1 iterations before they are used, so the in-flight bytes cost no registers and the
+//     only synchronisation is __syncwarp (no block barrier, warps drift freely);
+//   * a thread reads back only its own vector (one conflict-free LDS.128 per channel row); the
+//     x halo comes from the neighbouring lanes by shuffle, the warp-edge lanes read the halo
+//     vector copied above;
+//   * the kernels are input-row stationary: the forward pass keeps 3 rows of 4 output
+//     accumulators (input row iy feeds output rows iy+ly-ky), the weight gradient keeps the last 3
+//     cotangent rows, so there is no input row queue at all;
+//   * the band height is chosen so that the grid is close to a whole number of resident waves.
+// Accumulation order of one output: bias, then input rows as they stream in (ky = 2, 1, 0),
+// channels, kx; integer results are order-independent.
+constexpr int kRing = 4;
+constexpr int kRowW = 128 + 8;   // floats per channel row in the ring: [4 left halo | 128 own | 4 right halo]
+
+__device__ __forceinline__ void cpa16(unsigned smem_addr, const void* gmem, int src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_addr), "l"(gmem), "r"(src_bytes)
+               : "memory");
+}
+__device__ __forceinline__ void cpa_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cpa_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+template <typename T>
+__device__ __forceinline__ void lds_v4(unsigned addr, T (&d)[4]) {
+  int4 raw;
+  asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(raw.x), "=r"(raw.y), "=r"(raw.z), "=r"(raw.w) : "r"(addr));
+  d[0] = reinterpret_cast<const T&>(raw.x);
+  d[1] = reinterpret_cast<const T&>(raw.y);
+  d[2] = reinterpret_cast<const T&>(raw.z);
+  d[3] = reinterpret_cast<const T&>(raw.w);
+}
+template <typename T>
+__device__ __forceinline__ T lds_1(unsigned addr) {
+  int raw;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(raw) : "r"(addr));
+  return reinterpret_cast<const T&>(raw);
+}
+
+// Per-warp row streamer: NCH "channels" per row (the C input planes, optionally + the cotangent).
+template <typename T, int NCH, int LX>
+struct RowRing {
+  unsigned base;        // shared address of this warp's ring
+  unsigned own;         // byte offset of this lane's vector inside a channel row
+  const T* src[NCH];    // global pointer of this lane's vector in row 0 of each channel
+  int pitch[NCH];       // row pitch (elements) of each channel
+  int nrow[NCH];        // rows of each channel (rows outside [0, nrow) are zero-filled)
+  int roff[NCH];        // row of channel ch = iy + roff[ch]
+  bool col_ok[NCH];     // this lane's vector lies inside the row
+  bool halo_ok[NCH];    // edge lanes: the halo vector lies inside the row
+  int lane;
+
+  __device__ __forceinline__ void issue(int iy, int stage) const {
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) {
+      const int r = iy + roff[ch];
+      const bool row_ok = (r >= 0) && (r < nrow[ch]);
+      const T* rp = src[ch] + (int64_t)(row_ok ? r : 0) * pitch[ch];
+      const unsigned dst = base + (unsigned)((stage * NCH + ch) * kRowW * 4);
+      cpa16(dst + own, col_ok[ch] ? rp : src[ch], (row_ok && col_ok[ch]) ? 16 : 0);
+      if (LX > 0 && lane == 0) cpa16(dst, halo_ok[ch] ? rp - 4 : src[ch], (row_ok && halo_ok[ch]) ? 16 : 0);
+      if (LX < 2 && lane == 31) cpa16(dst + (kRowW - 4) * 4, halo_ok[ch] ? rp + 4 : src[ch], (row_ok && halo_ok[ch]) ? 16 : 0);
+    }
+    cpa_commit();
+  }
+
+  // e[0..5] = columns j0-LX .. j0-LX+5 of channel ch in `stage`
+  __device__ __forceinline__ void window(int stage, int ch, T (&e)[6]) const {
+    const unsigned row = base + (unsigned)((stage * NCH + ch) * kRowW * 4);
+    T v[4];
+    lds_v4(row + own, v);
+#pragma unroll
+    for (int k = 0; k < LX; ++k) {
+      const T up = __shfl_up_sync(0xffffffffu, v[4 - LX + k], 1);
+      T edge = T(0);
+      if (lane == 0) edge = lds_1<T>(row + (4 - LX + k) * 4);
+      e[k] = lane == 0 ? edge : up;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) e[LX + k] = v[k];
+#pragma unroll
+    for (int k = 0; k < 2 - LX; ++k) {
+      const T dn = __shfl_down_sync(0xffffffffu, v[k], 1);
+      T edge = T(0);
+      if (lane == 31) edge = lds_1<T>(row + (kRowW - 4 + k) * 4);
+      e[LX + 4 + k] = lane == 31 ? edge : dn;
+    }
+  }
+
+  __device__ __forceinline__ void own4(int stage, int ch, T (&v)[4]) const {
+    lds_v4(base + (unsigned)((stage * NCH + ch) * kRowW * 4) + own, v);
+  }
+};
+
+template <typename T, int C, int LX>
+__global__ void __launch_bounds__(kTX)
+conv_fwd_rows_kernel(const __grid_constant__ ConvArgs<T> a) {
+  constexpr int NT = C * 9;
+  __shared__ __align__(16) T smem[(kTX / 32) * kRing * C * kRowW];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int j0 = (blockIdx.x * kTX + threadIdx.x) * kCols;   // whole warps stay alive for the shuffles
+  const int r0 = blockIdx.y * a.th, r1 = min(r0 + a.th, a.hout);
+  const T* __restrict__ in = a.in + (int64_t)blockIdx.z * a.in_batch;
+  T* __restrict__ out = a.out + (int64_t)blockIdx.z * a.out_batch;
+  const int n_valid = min(kCols, a.wout - j0);
+
+  RowRing<T, C, LX> ring;
+  ring.base = (unsigned)__cvta_generic_to_shared(smem) + (unsigned)(warp * kRing * C * kRowW * 4);
+  ring.own = (unsigned)((4 + 4 * lane) * 4);
+  ring.lane = lane;
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    ring.src[c] = in + c * a.plane + j0;
+    ring.pitch[c] = a.win;
+    ring.nrow[c] = a.hin;
+    ring.roff[c] = 0;
+    ring.col_ok[c] = j0 < a.win;
+    ring.halo_ok[c] = lane == 0 ? (j0 >= 4 && j0 - 4 < a.win) : (j0 + 4 < a.win);
+  }
+
+  T w[NT];
+  if (a.coef_dev) {
+#pragma unroll
+    for (int i = 0; i < NT; ++i) w[i] = a.coef_dev[a.coef_rev ? NT - 1 - i : i];
+  } else {
+#pragma unroll
+    for (int i = 0; i < NT; ++i) w[i] = a.coef[i];
+  }
+
+  const int iy0 = r0 - a.ly, iy1 = r1 - 1 - a.ly + 2;  // first / last input row of the band
+#pragma unroll
+  for (int k = 0; k < kRing - 1; ++k) ring.issue(iy0 + k, k);
+
+  T acc[3][kCols];  // acc[s]: output row iy + ly - 2 + s while input row iy is processed
+#pragma unroll
+  for (int s = 0; s < 3; ++s)
+#pragma unroll
+    for (int i = 0; i < kCols; ++i) acc[s][i] = a.bias;
+
+  int stage = 0;
+  T* orow = out + (int64_t)(iy0 + a.ly - 2) * a.wout + j0;
+#pragma unroll 1
+  for (int iy = iy0; iy <= iy1; ++iy) {
+    __syncwarp();  // every lane is done reading the stage that is refilled now
+    ring.issue(iy + kRing - 1, stage == 0 ? kRing - 1 : stage - 1);
+    cpa_wait<kRing - 1>();
+    __syncwarp();  // row iy of all lanes has landed
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      T e[6];
+      ring.window(stage, c, e);
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+          for (int i = 0; i < kCols; ++i)
+            acc[2 - ky][i] = mad_wrap(w[(c * 3 + ky) * 3 + kx], e[kx + i], acc[2 - ky][i]);
+    }
+    if (iy >= iy0 + 2 && n_valid > 0) {  // output row iy + ly - 2 is complete
+      const uintptr_t addr = reinterpret_cast<uintptr_t>(orow);
+      if (n_valid == 4 && (addr & 15) == 0) {
+        int4 raw;
+        raw.x = reinterpret_cast<const int&>(acc[0][0]);
+        raw.y = reinterpret_cast<const int&>(acc[0][1]);
+        raw.z = reinterpret_cast<const int&>(acc[0][2]);
+        raw.w = reinterpret_cast<const int&>(acc[0][3]);
+        __stcs(reinterpret_cast<int4*>(orow), raw);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (i < n_valid) orow[i] = acc[0][i];
+      }
+    }
+    orow += a.wout;
+#pragma unroll
+    for (int i = 0; i < kCols; ++i) {
+      acc[0][i] = acc[1][i];
+      acc[1][i] = acc[2][i];
+      acc[2][i] = a.bias;
+    }
+    stage = stage == kRing - 1 ? 0 : stage + 1;
+  }
+  cpa_wait<0>();
+}
+
+template <int C, int LX>
+__global__ void __launch_bounds__(kTX)
+conv_wgrad_rows_kernel(const __grid_constant__ ConvArgs<float> a) {
+  constexpr int NT = C * 9;
+  constexpr int NCH = C + 1;  // channel C of the ring = the cotangent row
+  __shared__ __align__(16) float smem[(kTX / 32) * kRing * NCH * kRowW];
+  __shared__ float red[kTX / 32][NT];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int j0 = (blockIdx.x * kTX + threadIdx.x) * kCols;
+  const int r0 = blockIdx.y * a.th, r1 = min(r0 + a.th, a.hout);
+  float acc[NT];
+#pragma unroll
+  for (int t = 0; t < NT; ++t) acc[t] = 0.f;
+
+  RowRing<float, NCH, LX> ring;
+  ring.base = (unsigned)__cvta_generic_to_shared(smem) + (unsigned)(warp * kRing * NCH * kRowW * 4);
+  ring.own = (unsigned)((4 + 4 * lane) * 4);
+  ring.lane = lane;
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    ring.src[c] = a.in + c * a.plane + j0;
+    ring.pitch[c] = a.win;
+    ring.nrow[c] = a.hin;
+    ring.roff[c] = 0;
+    ring.col_ok[c] = j0 < a.win;
+    ring.halo_ok[c] = lane == 0 ? (j0 >= 4 && j0 - 4 < a.win) : (j0 + 4 < a.win);
+  }
+  // cotangent row iy + ly travels with input row iy; only rows of this band count and only whole
+  // in-range vectors are copied (the launcher guarantees wout % 4 == 0 and 16-byte aligned rows)
+  ring.src[C] = a.g + j0;
+  ring.pitch[C] = a.wout;
+  ring.nrow[C] = r1;
+  ring.roff[C] = a.ly;
+  ring.col_ok[C] = j0 + 3 < a.wout;
+  ring.halo_ok[C] = false;
+
+  const int iy0 = r0 - a.ly, iy1 = r1 - 1 - a.ly + 2;
+#pragma unroll
+  for (int k = 0; k < kRing - 1; ++k) ring.issue(iy0 + k, k);
+  float g[3][kCols];  // g[ky]: cotangent row iy + ly - ky
+#pragma unroll
+  for (int s = 0; s < 3; ++s)
+#pragma unroll
+    for (int i = 0; i < kCols; ++i) g[s][i] = 0.f;
+
+  int stage = 0;
+#pragma unroll 1
+  for (int iy = iy0; iy <= iy1; ++iy) {
+    __syncwarp();
+    ring.issue(iy + kRing - 1, stage == 0 ? kRing - 1 : stage - 1);
+    cpa_wait<kRing - 1>();
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < kCols; ++i) {
+      g[2][i] = g[1][i];
+      g[1][i] = g[0][i];
+    }
+    ring.own4(stage, C, g[0]);
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      float e[6];
+      ring.window(stage, c, e);
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+          for (int i = 0; i < kCols; ++i)
+            acc[(c * 3 + ky) * 3 + kx] = fmaf(g[ky][i], e[kx + i], acc[(c * 3 + ky) * 3 + kx]);
+    }
+    stage = stage == kRing - 1 ? 0 : stage + 1;
+  }
+  cpa_wait<0>();
+#pragma unroll
+  for (int t = 0; t < NT; ++t) {
+    float v = acc[t];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) red[warp][t] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < NT) {
+    float v = 0.f;
+#pragma unroll
+    for (int wv = 0; wv < kTX / 32; ++wv) v += red[wv][threadIdx.x];
+    const int64_t blk = (int64_t)blockIdx.y * gridDim.x + blockIdx.x;
+    a.out[blk * NT + threadIdx.x] = v;
+  }
+}
+
 // fixed-order sum of the per-block partials; slot order -> program tap order through `perm`
 struct PermArgs {
   int n_taps;
@@ -283,11 +568,69 @@ void fill_common(ConvArgs<T>& a, const KxGeom& g, const ConvGeom& cg) {
   a.in_batch = a.plane * cg.C;
   a.out_batch = (int64_t)a.hout * a.wout;
   a.th = a.hout >= 512 ? 32 : (a.hout >= 64 ? 16 : 8);
+  if (const char* e = getenv("KX_CONV_TH")) a.th = atoi(e) > 0 ? atoi(e) : a.th;  // tuning knob
   while ((a.hout + a.th - 1) / a.th > 65535) a.th *= 2;
+}
+
+inline bool conv_rows_enabled() {
+  static int on = -1;
+  if (on < 0) on = getenv("KX_CONV_LEGACY") ? 0 : 1;  // A/B switch for the register-queue kernels
+  return on == 1;
+}
+
+constexpr int kMinTH = 16;  // the weight-gradient scratch is sized for bands of at least this many rows
+
+// Band height for the row-streaming kernels: every band re-reads 2 halo rows (th/(th+2)) and the
+// grid should fill a whole number of resident waves (148 SMs x blocks per SM).
+template <typename K>
+int pick_band_rows(K kernel, int hout, int64_t tiles_per_band, int fallback) {
+  if (getenv("KX_CONV_TH")) return fallback;
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kTX, 0) != cudaSuccess || per_sm < 1) {
+    cudaGetLastError();
+    return fallback;
+  }
+  const int64_t resident = (int64_t)sm_count() * per_sm;
+  if (tiles_per_band * ((hout + kMinTH - 1) / kMinTH) <= resident) return fallback;  // small problem
+  int best = fallback;
+  double best_eff = 0.0;
+  for (int th = kMinTH; th <= 96; ++th) {
+    const int64_t tiles = tiles_per_band * ((hout + th - 1) / th);
+    if ((hout + th - 1) / th > 65535) continue;
+    const int64_t waves = (tiles + resident - 1) / resident;
+    const double eff = (double)tiles / (double)(waves * resident) * th / (th + 2.0);
+    if (eff >= best_eff) {
+      best_eff = eff;
+      best = th;
+    }
+  }
+  return best;
+}
+
+template <typename T, int C, int LX>
+int launch_fwd_rows(ConvArgs<T> a, dim3 grid, cudaStream_t s) {
+  a.th = pick_band_rows(conv_fwd_rows_kernel<T, C, LX>, a.hout, (int64_t)grid.x * grid.z, a.th);
+  grid.y = (a.hout + a.th - 1) / a.th;
+  conv_fwd_rows_kernel<T, C, LX><<<grid, kTX, 0, s>>>(a);
+  return after_launch("conv_fwd_rows_kernel");
+}
+
+template <int C, int LX>
+int launch_wgrad_rows(ConvArgs<float> a, dim3& grid, cudaStream_t s) {
+  const int th = pick_band_rows(conv_wgrad_rows_kernel<C, LX>, a.hout, (int64_t)grid.x * grid.z, a.th);
+  if (th >= kMinTH) a.th = th;
+  grid.y = (a.hout + a.th - 1) / a.th;
+  conv_wgrad_rows_kernel<C, LX><<<grid, kTX, 0, s>>>(a);
+  return after_launch("conv_wgrad_rows_kernel");
 }
 
 template <typename T, int C>
 int launch_fwd(const ConvArgs<T>& a, dim3 grid, bool vec, cudaStream_t s) {
+  if (vec && conv_rows_enabled() && a.lx >= 0 && a.lx <= 2) {
+    if (a.lx == 0) return launch_fwd_rows<T, C, 0>(a, grid, s);
+    if (a.lx == 1) return launch_fwd_rows<T, C, 1>(a, grid, s);
+    return launch_fwd_rows<T, C, 2>(a, grid, s);
+  }
   const int shift = vec ? (((-a.lx) % 4) + 4) % 4 : 0;
   if (!vec) conv_fwd_kernel<T, C, 3, 3, 0, false><<<grid, kTX, 0, s>>>(a);
   else if (shift == 0) conv_fwd_kernel<T, C, 3, 3, 0, true><<<grid, kTX, 0, s>>>(a);
@@ -298,7 +641,13 @@ int launch_fwd(const ConvArgs<T>& a, dim3 grid, bool vec, cudaStream_t s) {
 }
 
 template <int C>
-int launch_wgrad(const ConvArgs<float>& a, dim3 grid, bool vec, cudaStream_t s) {
+int launch_wgrad(const ConvArgs<float>& a, dim3& grid, bool vec, cudaStream_t s) {
+  if (vec && conv_rows_enabled() && a.lx >= 0 && a.lx <= 2 && a.wout % 4 == 0 &&
+      (reinterpret_cast<uintptr_t>(a.g) & 15) == 0) {
+    if (a.lx == 0) return launch_wgrad_rows<C, 0>(a, grid, s);
+    if (a.lx == 1) return launch_wgrad_rows<C, 1>(a, grid, s);
+    return launch_wgrad_rows<C, 2>(a, grid, s);
+  }
   const int shift = vec ? (((-a.lx) % 4) + 4) % 4 : 0;
   if (!vec) conv_wgrad_kernel<C, 3, 3, 0, false><<<grid, kTX, 0, s>>>(a);
   else if (shift == 0) conv_wgrad_kernel<C, 3, 3, 0, true><<<grid, kTX, 0, s>>>(a);
@@ -387,7 +736,8 @@ int64_t conv_wgrad_scratch_bytes(const KxGeom& g, const KxProgram& p) {
   ConvArgs<float> a;
   fill_common(a, g, cg);
   const dim3 grid = wgrad_grid(a);
-  return (int64_t)grid.x * grid.y * cg.C * 9 * (int64_t)sizeof(float);
+  const int64_t bands = a.th < kMinTH ? (int64_t)grid.y : (int64_t)(a.hout + kMinTH - 1) / kMinTH;  // upper bound
+  return (int64_t)grid.x * bands * cg.C * 9 * (int64_t)sizeof(float);
 }
 
 int try_conv_wgrad(const KxGeom& g, const KxProgram& p, const void* x, const void* gout, void* scratch, void* dcoef,
@@ -410,7 +760,7 @@ int try_conv_wgrad(const KxGeom& g, const KxProgram& p, const void* x, const voi
   a.g = (const float*)gout;
   a.out = (float*)scratch;
   const bool vec = (a.win % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
-  const dim3 grid = wgrad_grid(a);
+  dim3 grid = wgrad_grid(a);
   int rc = KX_ERR_UNSUPPORTED;
   switch (cg.C) {
     case 1: rc = launch_wgrad<1>(a, grid, vec, s); break;

@@ -179,10 +179,10 @@ def test_conv_as_kmap_config3a_shape(kex):
     taps = list(itertools.product(range(C), range(3), range(3)))
     b = ((0, 0), (1, 1), (1, 1))
     got_host_w = conv(x, w)                                   # weights known on the host
-    assert _last_kernel() == "conv_fwd_kernel" and got_host_w.shape == (1, H, W)
+    assert _last_kernel() in ("conv_fwd_kernel", "conv_fwd_rows_kernel") and got_host_w.shape == (1, H, W)
     _check_affine(got_host_w, x, (C, 3, 3), (1, 1, 1), b, taps, [float(w[t]) for t in taps])
     got_dev_w = conv(torch.from_numpy(x).cuda(), torch.from_numpy(w).cuda())   # device weights
-    assert _last_kernel() == "conv_fwd_kernel"
+    assert _last_kernel() in ("conv_fwd_kernel", "conv_fwd_rows_kernel")
     _check_affine(got_dev_w.cpu().numpy(), x, (C, 3, 3), (1, 1, 1), b, taps, [float(w[t]) for t in taps])
 
 
@@ -227,3 +227,53 @@ def test_weight_gradient_matches_oracle(kex):
                 # x[c, i+a-1, j+bb-1] contributes w[c,a,bb] to out[i,j]
                 dx[c] += w[c, a, bb] * gp[2 - a:2 - a + H, 2 - bb:2 - bb + H]
     np.testing.assert_allclose(xt.grad.cpu().numpy(), dx, rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize("case", range(12))
+def test_conv_rows_kernels_geometry(kex, case):
+    """The per-warp cp.async ring kernels (aligned rows): every x border class (lx = 0, 1, 2),
+    y borders, several warps / column blocks / bands, warp-edge halo lanes, fp32 and int32,
+    forward against the oracle and the weight gradient against the oracle's correlation."""
+    rng = np.random.default_rng(4200 + case)
+    C = [3, 2, 4, 3][case % 4]
+    H = [200, 97, 150, 64][case % 4]
+    W = [1028, 516, 132, 260][(case // 2) % 4]
+    bx = [(1, 1), (0, 0), (2, 0), (0, 2), (2, 2), (1, 0)][case % 6]
+    by = [(1, 1), (0, 0), (2, 1), (0, 2)][(case // 3) % 4]
+    border = ((0, 0), by, bx)
+    integer = case % 5 == 4
+    taps = list(itertools.product(range(C), range(3), range(3)))
+    if integer:
+        x = rng.integers(-50, 50, (C, H, W)).astype(np.int32)
+        w = rng.integers(-5, 6, (C, 3, 3)).astype(np.int32)
+    else:
+        x = rng.standard_normal((C, H, W)).astype(np.float32)
+        w = rng.standard_normal((C, 3, 3)).astype(np.float32)
+    op = kex.kernel_map({(lambda v, w: np.sum(v * w)): ()}, (C, H, W), (C, 3, 3), (1, 1, 1), border, False)
+    xt = torch.from_numpy(x).cuda()
+    wt = torch.from_numpy(w).cuda()
+    if not integer:
+        wt.requires_grad_()
+    got = op(xt, wt)
+    assert _last_kernel() == "conv_fwd_rows_kernel"
+    coefs = [w[t].item() for t in taps]
+    _check_affine(got.detach().cpu().numpy(), x, (C, 3, 3), (1, 1, 1), border, taps, coefs)
+    if not integer:
+        g = rng.standard_normal(tuple(got.shape)).astype(np.float32)
+        (dw,) = torch.autograd.grad(got, wt, torch.from_numpy(g).cuda())
+        want = ko.weight_grad(x, g, (C, 3, 3), (1, 1, 1), border)
+        np.testing.assert_allclose(dw.cpu().numpy(), want, rtol=2e-4, atol=2e-4 * float(np.sqrt(H * W)))
+
+
+def test_conv_rows_batched_and_host_weights(kex):
+    rng = np.random.default_rng(4300)
+    B, C, H, W = 3, 3, 80, 384
+    x = rng.standard_normal((B, C, H, W)).astype(np.float32)
+    w = rng.standard_normal((C, 3, 3)).astype(np.float32)
+    border = ((0, 0), (0, 0), (1, 1), (1, 1))
+    op = kex.kernel_map({(lambda v, w: np.sum(v[0] * w)): ()}, (B, C, H, W), (1, C, 3, 3), (1, 1, 1, 1), border, False)
+    got = op(torch.from_numpy(x).cuda(), w)     # host weights -> constant-bank coefficients
+    assert _last_kernel() == "conv_fwd_rows_kernel"
+    taps = list(itertools.product(range(C), range(3), range(3)))
+    for b in range(B):
+        _check_affine(got[b].cpu().numpy(), x[b], (C, 3, 3), (1, 1, 1), border[1:], taps, [float(w[t]) for t in taps])
