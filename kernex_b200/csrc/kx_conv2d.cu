@@ -15,6 +15,8 @@
 //                        accumulates C*KY*KX partial sums in registers, blocks reduce through
 //                        shuffles + shared memory into partial[block][tap]; a second kernel sums
 //                        the partials in a fixed order (deterministic, no atomics).
+#include <type_traits>
+
 #include "kx_internal.cuh"
 
 namespace kx {
@@ -228,7 +230,7 @@ conv_wgrad_kernel(const __grid_constant__ ConvArgs<float> a) {
 //     cotangent row for the weight gradient] x (128 + 2*4) columns).  Lane l copies its own 16
 //     bytes of each channel row with cp.async.cg (LDGSTS, zero-fill = the reference's zero
 //     padding), lanes 0 / 31 also copy the left / right halo vector; rows are requested
-//     kRing-1 iterations before they are used, so the in-flight bytes cost no registers and the
+//     kRing-1 = 2 iterations before they are used, so the in-flight bytes cost no registers and the
 //     only synchronisation is __syncwarp (no block barrier, warps drift freely);
 //   * a thread reads back only its own vector (one conflict-free LDS.128 per channel row); the
 //     x halo comes from the neighbouring lanes by shuffle, the warp-edge lanes read the halo
@@ -239,18 +241,36 @@ conv_wgrad_kernel(const __grid_constant__ ConvArgs<float> a) {
 //   * the band height is chosen so that the grid is close to a whole number of resident waves.
 // Accumulation order of one output: bias, then input rows as they stream in (ky = 2, 1, 0),
 // channels, kx; integer results are order-independent.
-constexpr int kRing = 4;
+constexpr int kRing = 3;         // the row loop is unrolled by kRing: stages and queues rotate by renaming
 constexpr int kRowW = 128 + 8;   // floats per channel row in the ring: [4 left halo | 128 own | 4 right halo]
 
-__device__ __forceinline__ void cpa16(unsigned smem_addr, const void* gmem, int src_bytes) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_addr), "l"(gmem), "r"(src_bytes)
+// ---- TMA bulk copy + mbarrier primitives (cp.async.bulk = UBLKCP, no tensor map needed for rows) ----
+__device__ __forceinline__ void mbar_init(unsigned mbar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned mbar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned mbar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mbar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned mbar, unsigned parity) {
+  unsigned done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(mbar), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned mbar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(mbar)
                : "memory");
 }
-__device__ __forceinline__ void cpa_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cpa_wait() {
-  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 template <typename T>
 __device__ __forceinline__ void lds_v4(unsigned addr, T (&d)[4]) {
   int4 raw;
@@ -266,45 +286,99 @@ __device__ __forceinline__ T lds_1(unsigned addr) {
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(raw) : "r"(addr));
   return reinterpret_cast<const T&>(raw);
 }
+__device__ __forceinline__ void sts_zero16(unsigned addr) {
+  asm volatile("st.shared.v4.b32 [%0], {%1,%1,%1,%1};" ::"r"(addr), "r"(0) : "memory");
+}
 
-// Per-warp row streamer: NCH "channels" per row (the C input planes, optionally + the cotangent).
-template <typename T, int NCH, int LX>
+// Per-warp streamer of the C input planes.  One elected lane issues one bulk copy per channel row:
+// the warp's 128 columns plus the 4-column halo vectors on either side, clipped to the row (the
+// clipped-away part of the ring is zeroed once and never overwritten = zero padding in x).  Rows
+// outside the image are zero-filled by the lanes themselves.  Completion is tracked by one
+// mbarrier per stage (expect_tx = C * bytes).
+template <typename T, int C, int LX>
 struct RowRing {
-  unsigned base;        // shared address of this warp's ring
-  unsigned own;         // byte offset of this lane's vector inside a channel row
-  const T* src[NCH];    // global pointer of this lane's vector in row 0 of each channel
-  int pitch[NCH];       // row pitch (elements) of each channel
-  int nrow[NCH];        // rows of each channel (rows outside [0, nrow) are zero-filled)
-  int roff[NCH];        // row of channel ch = iy + roff[ch]
-  bool col_ok[NCH];     // this lane's vector lies inside the row
-  bool halo_ok[NCH];    // edge lanes: the halo vector lies inside the row
-  int lane;
+  unsigned own;        // shared address of this lane's vector in channel row 0 of stage 0
+  unsigned row0;       // shared address of the warp's ring
+  unsigned mbar;       // shared address of the warp's kRing mbarriers
+  unsigned dst_off;    // byte offset inside a channel row where the copy lands
+  unsigned bytes;      // bytes per channel-row copy (0 = the warp lies outside the image)
+  const T* src;        // first copied column in row 0 of channel 0
+  int64_t plane;
+  int pitch, nrow, last;   // rows outside [0, nrow) or after `last` are zero-filled, never read
+  bool lane_first, lane_last;
 
-  __device__ __forceinline__ void issue(int iy, int stage) const {
-#pragma unroll
-    for (int ch = 0; ch < NCH; ++ch) {
-      const int r = iy + roff[ch];
-      const bool row_ok = (r >= 0) && (r < nrow[ch]);
-      const T* rp = src[ch] + (int64_t)(row_ok ? r : 0) * pitch[ch];
-      const unsigned dst = base + (unsigned)((stage * NCH + ch) * kRowW * 4);
-      cpa16(dst + own, col_ok[ch] ? rp : src[ch], (row_ok && col_ok[ch]) ? 16 : 0);
-      if (LX > 0 && lane == 0) cpa16(dst, halo_ok[ch] ? rp - 4 : src[ch], (row_ok && halo_ok[ch]) ? 16 : 0);
-      if (LX < 2 && lane == 31) cpa16(dst + (kRowW - 4) * 4, halo_ok[ch] ? rp + 4 : src[ch], (row_ok && halo_ok[ch]) ? 16 : 0);
-    }
-    cpa_commit();
+  __device__ __forceinline__ void init(T* smem, uint64_t* bars, int warp, int lane, const T* in, int64_t plane_,
+                                       int wj0, int win, int hin, int last_) {
+    row0 = (unsigned)__cvta_generic_to_shared(smem) + (unsigned)(warp * kRing * C * kRowW * 4);
+    own = row0 + (unsigned)((4 + 4 * lane) * 4);
+    mbar = (unsigned)__cvta_generic_to_shared(bars) + (unsigned)(warp * kRing * 8);
+    const int c_lo = max(wj0 - 4, 0), c_hi = min(wj0 + 132, win);
+    bytes = c_hi > c_lo ? (unsigned)((c_hi - c_lo) * 4) : 0u;
+    dst_off = (unsigned)((c_lo - (wj0 - 4)) * 4);
+    src = in + c_lo;
+    plane = plane_;
+    pitch = win;
+    nrow = hin;
+    last = last_;
+    lane_first = lane == 0;
+    lane_last = lane == 31;
+    // zero the whole ring once (x padding + rows never copied), initialise the barriers
+    for (int i = lane; i < kRing * C * kRowW / 4; i += 32) sts_zero16(row0 + (unsigned)(i * 16));
+    if (lane < kRing) mbar_init(mbar + lane * 8, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    fence_proxy_async();
+    __syncwarp();
   }
 
-  // e[0..5] = columns j0-LX .. j0-LX+5 of channel ch in `stage`
-  __device__ __forceinline__ void window(int stage, int ch, T (&e)[6]) const {
-    const unsigned row = base + (unsigned)((stage * NCH + ch) * kRowW * 4);
+  __device__ __forceinline__ bool row_ok(int iy) const { return (iy >= 0) && (iy < nrow) && (iy <= last); }
+
+  // request row iy into STAGE (`extra` more bytes will be added to the same barrier by the caller)
+  template <int STAGE>
+  __device__ __forceinline__ void issue(int iy, unsigned extra = 0) const {
+    const bool ok = row_ok(iy) && bytes != 0;
+    if (lane_first) {
+      const unsigned bar = mbar + STAGE * 8;
+      if (ok) {
+        mbar_expect_tx(bar, bytes * C + extra);
+        const T* rp = src + (int64_t)iy * pitch;
+#pragma unroll
+        for (int ch = 0; ch < C; ++ch)
+          bulk_g2s(row0 + (unsigned)((STAGE * C + ch) * kRowW * 4) + dst_off, rp + ch * plane, bytes, bar);
+      } else if (extra) {
+        mbar_expect_tx(bar, extra);
+      } else {
+        mbar_arrive(bar);
+      }
+    }
+    if (!ok) {  // a padding row: every lane clears what it will read back (own vector, edge lanes the halo)
+#pragma unroll
+      for (int ch = 0; ch < C; ++ch) {
+        const unsigned off = (unsigned)((STAGE * C + ch) * kRowW * 4);
+        sts_zero16(own + off);
+        if (lane_first) sts_zero16(own + off - 16);
+        if (lane_last) sts_zero16(own + off + 16);
+      }
+      fence_proxy_async();
+    }
+  }
+
+  template <int STAGE>
+  __device__ __forceinline__ void wait(unsigned parity) const {
+    mbar_wait(mbar + STAGE * 8, parity);
+  }
+
+  // e[0..5] = columns j0-LX .. j0-LX+5 of channel ch in STAGE
+  template <int STAGE>
+  __device__ __forceinline__ void window(int ch, T (&e)[6]) const {
+    const unsigned off = (unsigned)((STAGE * C + ch) * kRowW * 4);
     T v[4];
-    lds_v4(row + own, v);
+    lds_v4(own + off, v);
 #pragma unroll
     for (int k = 0; k < LX; ++k) {
       const T up = __shfl_up_sync(0xffffffffu, v[4 - LX + k], 1);
       T edge = T(0);
-      if (lane == 0) edge = lds_1<T>(row + (4 - LX + k) * 4);
-      e[k] = lane == 0 ? edge : up;
+      if (lane_first) edge = lds_1<T>(own + off - (LX - k) * 4);
+      e[k] = lane_first ? edge : up;
     }
 #pragma unroll
     for (int k = 0; k < 4; ++k) e[LX + k] = v[k];
@@ -312,41 +386,45 @@ struct RowRing {
     for (int k = 0; k < 2 - LX; ++k) {
       const T dn = __shfl_down_sync(0xffffffffu, v[k], 1);
       T edge = T(0);
-      if (lane == 31) edge = lds_1<T>(row + (kRowW - 4 + k) * 4);
-      e[LX + 4 + k] = lane == 31 ? edge : dn;
+      if (lane_last) edge = lds_1<T>(own + off + 16 + k * 4);
+      e[LX + 4 + k] = lane_last ? edge : dn;
     }
   }
-
-  __device__ __forceinline__ void own4(int stage, int ch, T (&v)[4]) const {
-    lds_v4(base + (unsigned)((stage * NCH + ch) * kRowW * 4) + own, v);
-  }
 };
+
+template <typename T>
+__device__ __forceinline__ void st_out4(T* o, const T (&v)[4], int n_valid) {
+  const uintptr_t addr = reinterpret_cast<uintptr_t>(o);
+  if (n_valid == 4 && (addr & 15) == 0) {
+    int4 raw;
+    raw.x = reinterpret_cast<const int&>(v[0]);
+    raw.y = reinterpret_cast<const int&>(v[1]);
+    raw.z = reinterpret_cast<const int&>(v[2]);
+    raw.w = reinterpret_cast<const int&>(v[3]);
+    __stcs(reinterpret_cast<int4*>(o), raw);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (i < n_valid) o[i] = v[i];
+  }
+}
 
 template <typename T, int C, int LX>
 __global__ void __launch_bounds__(kTX)
 conv_fwd_rows_kernel(const __grid_constant__ ConvArgs<T> a) {
   constexpr int NT = C * 9;
-  __shared__ __align__(16) T smem[(kTX / 32) * kRing * C * kRowW];
+  __shared__ __align__(128) T smem[(kTX / 32) * kRing * C * kRowW];
+  __shared__ __align__(8) uint64_t bars[(kTX / 32) * kRing];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int j0 = (blockIdx.x * kTX + threadIdx.x) * kCols;   // whole warps stay alive for the shuffles
   const int r0 = blockIdx.y * a.th, r1 = min(r0 + a.th, a.hout);
   const T* __restrict__ in = a.in + (int64_t)blockIdx.z * a.in_batch;
   T* __restrict__ out = a.out + (int64_t)blockIdx.z * a.out_batch;
   const int n_valid = min(kCols, a.wout - j0);
+  const int iy0 = r0 - a.ly, iy1 = r1 - 1 - a.ly + 2;  // first / last input row of the band
 
   RowRing<T, C, LX> ring;
-  ring.base = (unsigned)__cvta_generic_to_shared(smem) + (unsigned)(warp * kRing * C * kRowW * 4);
-  ring.own = (unsigned)((4 + 4 * lane) * 4);
-  ring.lane = lane;
-#pragma unroll
-  for (int c = 0; c < C; ++c) {
-    ring.src[c] = in + c * a.plane + j0;
-    ring.pitch[c] = a.win;
-    ring.nrow[c] = a.hin;
-    ring.roff[c] = 0;
-    ring.col_ok[c] = j0 < a.win;
-    ring.halo_ok[c] = lane == 0 ? (j0 >= 4 && j0 - 4 < a.win) : (j0 + 4 < a.win);
-  }
+  ring.init(smem, bars, warp, lane, in, a.plane, j0 - 4 * lane, a.win, a.hin, iy1);
 
   T w[NT];
   if (a.coef_dev) {
@@ -357,136 +435,133 @@ conv_fwd_rows_kernel(const __grid_constant__ ConvArgs<T> a) {
     for (int i = 0; i < NT; ++i) w[i] = a.coef[i];
   }
 
-  const int iy0 = r0 - a.ly, iy1 = r1 - 1 - a.ly + 2;  // first / last input row of the band
-#pragma unroll
-  for (int k = 0; k < kRing - 1; ++k) ring.issue(iy0 + k, k);
+  ring.template issue<0>(iy0);
+  ring.template issue<1>(iy0 + 1);
 
-  T acc[3][kCols];  // acc[s]: output row iy + ly - 2 + s while input row iy is processed
+  // acc[(P + s) % 3] is output row iy + ly - 2 + s while input row iy is processed in phase P
+  T acc[3][kCols];
 #pragma unroll
   for (int s = 0; s < 3; ++s)
 #pragma unroll
     for (int i = 0; i < kCols; ++i) acc[s][i] = a.bias;
-
-  int stage = 0;
   T* orow = out + (int64_t)(iy0 + a.ly - 2) * a.wout + j0;
-#pragma unroll 1
-  for (int iy = iy0; iy <= iy1; ++iy) {
+
+  unsigned parity = 0;
+  auto step = [&](auto phase, int iy) {
+    constexpr int P = decltype(phase)::value;
     __syncwarp();  // every lane is done reading the stage that is refilled now
-    ring.issue(iy + kRing - 1, stage == 0 ? kRing - 1 : stage - 1);
-    cpa_wait<kRing - 1>();
-    __syncwarp();  // row iy of all lanes has landed
+    ring.template issue<(P + 2) % 3>(iy + 2);
+    ring.template wait<P>(parity);  // row iy has landed
 #pragma unroll
     for (int c = 0; c < C; ++c) {
       T e[6];
-      ring.window(stage, c, e);
+      ring.template window<P>(c, e);
 #pragma unroll
       for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
         for (int kx = 0; kx < 3; ++kx)
 #pragma unroll
           for (int i = 0; i < kCols; ++i)
-            acc[2 - ky][i] = mad_wrap(w[(c * 3 + ky) * 3 + kx], e[kx + i], acc[2 - ky][i]);
+            acc[(P + 2 - ky) % 3][i] = mad_wrap(w[(c * 3 + ky) * 3 + kx], e[kx + i], acc[(P + 2 - ky) % 3][i]);
     }
-    if (iy >= iy0 + 2 && n_valid > 0) {  // output row iy + ly - 2 is complete
-      const uintptr_t addr = reinterpret_cast<uintptr_t>(orow);
-      if (n_valid == 4 && (addr & 15) == 0) {
-        int4 raw;
-        raw.x = reinterpret_cast<const int&>(acc[0][0]);
-        raw.y = reinterpret_cast<const int&>(acc[0][1]);
-        raw.z = reinterpret_cast<const int&>(acc[0][2]);
-        raw.w = reinterpret_cast<const int&>(acc[0][3]);
-        __stcs(reinterpret_cast<int4*>(orow), raw);
-      } else {
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-          if (i < n_valid) orow[i] = acc[0][i];
-      }
-    }
+    if (iy >= iy0 + 2 && n_valid > 0) st_out4(orow, acc[P % 3], n_valid);  // output row iy + ly - 2 is complete
     orow += a.wout;
 #pragma unroll
-    for (int i = 0; i < kCols; ++i) {
-      acc[0][i] = acc[1][i];
-      acc[1][i] = acc[2][i];
-      acc[2][i] = a.bias;
-    }
-    stage = stage == kRing - 1 ? 0 : stage + 1;
+    for (int i = 0; i < kCols; ++i) acc[P % 3][i] = a.bias;
+  };
+
+#pragma unroll 1
+  for (int iy = iy0; iy <= iy1; iy += 3) {
+    step(std::integral_constant<int, 0>{}, iy);
+    if (iy + 1 > iy1) break;
+    step(std::integral_constant<int, 1>{}, iy + 1);
+    if (iy + 2 > iy1) break;
+    step(std::integral_constant<int, 2>{}, iy + 2);
+    parity ^= 1u;
   }
-  cpa_wait<0>();
 }
 
 template <int C, int LX>
 __global__ void __launch_bounds__(kTX)
 conv_wgrad_rows_kernel(const __grid_constant__ ConvArgs<float> a) {
   constexpr int NT = C * 9;
-  constexpr int NCH = C + 1;  // channel C of the ring = the cotangent row
-  __shared__ __align__(16) float smem[(kTX / 32) * kRing * NCH * kRowW];
+  __shared__ __align__(128) float smem[(kTX / 32) * kRing * C * kRowW];
+  __shared__ __align__(128) float gsm[(kTX / 32) * kRing * 128];   // cotangent rows, own vectors only
+  __shared__ __align__(8) uint64_t bars[(kTX / 32) * kRing];
   __shared__ float red[kTX / 32][NT];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int j0 = (blockIdx.x * kTX + threadIdx.x) * kCols;
   const int r0 = blockIdx.y * a.th, r1 = min(r0 + a.th, a.hout);
+  const int iy0 = r0 - a.ly, iy1 = r1 - 1 - a.ly + 2;
   float acc[NT];
 #pragma unroll
   for (int t = 0; t < NT; ++t) acc[t] = 0.f;
 
-  RowRing<float, NCH, LX> ring;
-  ring.base = (unsigned)__cvta_generic_to_shared(smem) + (unsigned)(warp * kRing * NCH * kRowW * 4);
-  ring.own = (unsigned)((4 + 4 * lane) * 4);
-  ring.lane = lane;
-#pragma unroll
-  for (int c = 0; c < C; ++c) {
-    ring.src[c] = a.in + c * a.plane + j0;
-    ring.pitch[c] = a.win;
-    ring.nrow[c] = a.hin;
-    ring.roff[c] = 0;
-    ring.col_ok[c] = j0 < a.win;
-    ring.halo_ok[c] = lane == 0 ? (j0 >= 4 && j0 - 4 < a.win) : (j0 + 4 < a.win);
-  }
-  // cotangent row iy + ly travels with input row iy; only rows of this band count and only whole
-  // in-range vectors are copied (the launcher guarantees wout % 4 == 0 and 16-byte aligned rows)
-  ring.src[C] = a.g + j0;
-  ring.pitch[C] = a.wout;
-  ring.nrow[C] = r1;
-  ring.roff[C] = a.ly;
-  ring.col_ok[C] = j0 + 3 < a.wout;
-  ring.halo_ok[C] = false;
+  RowRing<float, C, LX> ring;
+  ring.init(smem, bars, warp, lane, a.in, a.plane, j0 - 4 * lane, a.win, a.hin, iy1);
+  // cotangent row iy + ly travels with input row iy on the same barrier; rows outside this band
+  // read as zero.  The launcher guarantees wout % 4 == 0 and 16-byte aligned rows.
+  const int wj0 = j0 - 4 * lane;
+  const unsigned grow0 = (unsigned)__cvta_generic_to_shared(gsm) + (unsigned)(warp * kRing * 128 * 4);
+  const unsigned gown = grow0 + (unsigned)(4 * lane * 4);
+  const unsigned gbytes = wj0 < a.wout ? (unsigned)(min(128, a.wout - wj0) * 4) : 0u;
+  const float* gsrc = a.g + wj0;
+  for (int i = lane; i < kRing * 128 / 4; i += 32) sts_zero16(grow0 + (unsigned)(i * 16));
+  fence_proxy_async();
+  __syncwarp();
+  auto issue_row = [&](auto stage, int iy) {
+    constexpr int S = decltype(stage)::value;
+    const int r = iy + a.ly;
+    const bool gok = r >= r0 && r < r1 && gbytes != 0;
+    ring.template issue<S>(iy, gok ? gbytes : 0u);
+    if (gok) {
+      if (lane == 0) bulk_g2s(grow0 + (unsigned)(S * 128 * 4), gsrc + (int64_t)r * a.wout, gbytes, ring.mbar + S * 8);
+    } else {
+      sts_zero16(gown + (unsigned)(S * 128 * 4));
+      fence_proxy_async();
+    }
+  };
 
-  const int iy0 = r0 - a.ly, iy1 = r1 - 1 - a.ly + 2;
-#pragma unroll
-  for (int k = 0; k < kRing - 1; ++k) ring.issue(iy0 + k, k);
-  float g[3][kCols];  // g[ky]: cotangent row iy + ly - ky
+  issue_row(std::integral_constant<int, 0>{}, iy0);
+  issue_row(std::integral_constant<int, 1>{}, iy0 + 1);
+
+  // g[(P + 3 - ky) % 3]: cotangent row iy + ly - ky while input row iy is processed in phase P
+  float g[3][kCols];
 #pragma unroll
   for (int s = 0; s < 3; ++s)
 #pragma unroll
     for (int i = 0; i < kCols; ++i) g[s][i] = 0.f;
 
-  int stage = 0;
-#pragma unroll 1
-  for (int iy = iy0; iy <= iy1; ++iy) {
+  unsigned parity = 0;
+  auto step = [&](auto phase, int iy) {
+    constexpr int P = decltype(phase)::value;
     __syncwarp();
-    ring.issue(iy + kRing - 1, stage == 0 ? kRing - 1 : stage - 1);
-    cpa_wait<kRing - 1>();
-    __syncwarp();
-#pragma unroll
-    for (int i = 0; i < kCols; ++i) {
-      g[2][i] = g[1][i];
-      g[1][i] = g[0][i];
-    }
-    ring.own4(stage, C, g[0]);
+    issue_row(std::integral_constant<int, (P + 2) % 3>{}, iy + 2);
+    ring.template wait<P>(parity);
+    lds_v4(gown + (unsigned)(P * 128 * 4), g[P % 3]);
 #pragma unroll
     for (int c = 0; c < C; ++c) {
       float e[6];
-      ring.window(stage, c, e);
+      ring.template window<P>(c, e);
 #pragma unroll
       for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
         for (int kx = 0; kx < 3; ++kx)
 #pragma unroll
           for (int i = 0; i < kCols; ++i)
-            acc[(c * 3 + ky) * 3 + kx] = fmaf(g[ky][i], e[kx + i], acc[(c * 3 + ky) * 3 + kx]);
+            acc[(c * 3 + ky) * 3 + kx] = fmaf(g[(P + 3 - ky) % 3][i], e[kx + i], acc[(c * 3 + ky) * 3 + kx]);
     }
-    stage = stage == kRing - 1 ? 0 : stage + 1;
+  };
+
+#pragma unroll 1
+  for (int iy = iy0; iy <= iy1; iy += 3) {
+    step(std::integral_constant<int, 0>{}, iy);
+    if (iy + 1 > iy1) break;
+    step(std::integral_constant<int, 1>{}, iy + 1);
+    if (iy + 2 > iy1) break;
+    step(std::integral_constant<int, 2>{}, iy + 2);
+    parity ^= 1u;
   }
-  cpa_wait<0>();
 #pragma unroll
   for (int t = 0; t < NT; ++t) {
     float v = acc[t];
