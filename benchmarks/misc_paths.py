@@ -1,0 +1,75 @@
+#!/usr/bin/env python
+"""Throughput of the paths next to the BASELINE configs: pooling (strided mean / max),
+batched depthwise conv through vmap, smap write-back, the wavefront kscan."""
+import os, sys, json
+import numpy as np, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import kernex_b200 as kex
+from kernex_b200 import _lib
+from run_configs import timeit, peak
+
+dev = torch.device("cuda")
+g = torch.Generator(device=dev).manual_seed(0)
+
+
+def rep(name, nbytes, med, lups):
+    gbs = nbytes / (med * 1e-3) / 1e9
+    print(json.dumps({"path": name, "ms": med, "glups": lups / (med * 1e-3) / 1e9, "alg_gbs": gbs,
+                      "frac_of_measured_peak": gbs / peak(), "kernel": _lib.last_kernel()}), flush=True)
+
+
+only = set(filter(None, (sys.argv[1] if len(sys.argv) > 1 else "").split(",")))
+want = lambda c: not only or c in only
+
+if want("pool"):
+    x = torch.randn((8, 8192, 8192), device=dev, generator=g)
+    for name, fn, k, s in [("avgpool 3x3 s2", lambda v: np.mean(v), 3, 2), ("maxpool 2x2 s2", lambda v: np.max(v), 2, 2),
+                           ("maxpool 3x3 s2", lambda v: np.max(v), 3, 2), ("maxpool 3x3 s1 same", lambda v: np.max(v), 3, 1)]:
+        f = kex.vmap(kex.kmap(kernel_size=(k, k), strides=(s, s), padding="same" if s == 1 else 0)(fn))
+        y = f(x)
+        med, _ = timeit(lambda: f(x), 6)
+        rep(f"{name} on (8,8192,8192)", x.numel() * 4 + y.numel() * 4, med, y.numel())
+    del x, y
+    torch.cuda.empty_cache()
+
+if want("depthwise"):
+    x = torch.randn((16, 4096, 4096), device=dev, generator=g)
+    w = torch.randn((16, 3, 3), device=dev, generator=g)
+    f = kex.vmap(kex.kmap(kernel_size=(3, 3), padding="same")(lambda v, w: np.sum(v * w)))
+    y = f(x, w)
+    med, _ = timeit(lambda: f(x, w), 6)
+    rep("depthwise conv 3x3 same on (16,4096,4096), per-channel device weights", x.numel() * 8, med, y.numel())
+    del x, y
+    torch.cuda.empty_cache()
+
+if want("smap"):
+    x = torch.randn((16384, 16384), device=dev, generator=g)
+    f = kex.smap(kernel_size=(3, 3), offset=1, relative=True)(lambda v: v[0, 1] + v[0, -1] + v[1, 0] + v[-1, 0] - 4 * v[0, 0])
+    y = f(x)
+    med, _ = timeit(lambda: f(x), 6)
+    rep("smap 5-pt Laplacian 16384^2 (offset write-back)", x.numel() * 8, med, y.numel())
+    del x, y
+    torch.cuda.empty_cache()
+
+if want("wave"):
+    for n in (1024, 4096):
+        x = torch.randn((n, n), device=dev, generator=g)
+        f = kex.kscan(kernel_size=(3, 3), padding="same", relative=True)(
+            lambda u: 0.25 * (u[0, -1] + u[-1, 0] + u[0, 1] + u[1, 0]))
+        y = f(x)
+        med, _ = timeit(lambda: f(x), 3, warm=1, inner=1)
+        rep(f"Gauss-Seidel sweep kscan {n}^2 (wavefront)", x.numel() * 8, med, y.numel())
+    del x, y
+    torch.cuda.empty_cache()
+
+if want("vjp"):
+    n = 16384
+    x = torch.randn((n, n), device=dev, generator=g).requires_grad_()
+    def lap2(v):
+        return v[1, 0] + v[0, -1] - 4 * v[0, 0] + v[0, 1] + v[-1, 0]
+    for pad in ("valid", "same"):
+        f = kex.kmap(kernel_size=(3, 3), padding=pad, relative=True)(lap2)
+        y = f(x)
+        gy = torch.randn(y.shape, device=dev, generator=g)
+        med, _ = timeit(lambda: torch.autograd.grad(y, x, gy, retain_graph=True), 6)
+        rep(f"C2 VJP wrt x, padding={pad}", n * n * 8, med, n * n)

@@ -1,0 +1,115 @@
+"""GPU parity of the strided-window / window-reduction kernel (kx_pool2d.cu): average, sum,
+max and min pooling, strided weighted windows and stride-1 max / min filters against the
+oracle, over every window misalignment (left border 0..3), ragged heights / widths, several
+bands, warps and column blocks, fp32 and int32, plus batched (vmap) and 1-D forms."""
+from __future__ import annotations
+
+import itertools
+
+import numpy as np
+import pytest
+
+from oracle import kx_oracle as ko
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+
+@pytest.fixture(scope="module")
+def kex():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import kernex_b200
+    return kernex_b200
+
+
+def _last_kernel():
+    from kernex_b200 import _lib
+    return _lib.last_kernel()
+
+
+GEOMS = [((2, 2), (2, 2)), ((3, 3), (2, 2)), ((3, 3), (3, 3)), ((3, 3), (1, 1)), ((2, 2), (1, 1)),
+         ((1, 3), (1, 2)), ((1, 2), (1, 2)), ((1, 3), (1, 1))]
+FNS = {"max": lambda v: np.max(v), "min": lambda v: np.min(v), "mean": lambda v: np.mean(v),
+       "sum": lambda v: np.sum(v)}
+
+
+@pytest.mark.parametrize("gi", range(len(GEOMS)))
+@pytest.mark.parametrize("op", ["max", "min", "mean", "sum"])
+@pytest.mark.parametrize("case", range(4))
+def test_pool2d_matches_oracle(kex, gi, op, case):
+    ksize, strides = GEOMS[gi]
+    if strides == (1, 1) and op in ("mean", "sum"):
+        pytest.skip("stride-1 affine windows belong to stencil2d")
+    rng = np.random.default_rng(7000 + 100 * gi + case)
+    h = [70, 33, 129, 200][case]
+    w = [516, 132, 1028, 260][(case + gi) % 4]
+    border = ((int(rng.integers(0, 3)), int(rng.integers(0, 3))), (case % 4, int(rng.integers(0, 3))))
+    if ksize[0] == 1:
+        border = ((0, 0), border[1])
+    integer = (case % 2 == 1) and op != "mean"
+    if integer:
+        x = rng.integers(-1000, 1000, (h, w)).astype(np.int32)
+    else:
+        x = rng.standard_normal((h, w)).astype(np.float32)
+    got = kex.kernel_map({FNS[op]: ()}, (h, w), ksize, strides, border, False)(x)
+    assert _last_kernel() == "pool2d_kernel"
+    want = ko.reduce_map(x, ksize, strides, border, op)
+    assert got.shape == want.shape and got.dtype == want.dtype
+    if integer or op in ("max", "min"):
+        np.testing.assert_array_equal(got, want)
+    else:
+        tol = 1e-5 * float(np.abs(x).max()) * ksize[0] * ksize[1]
+        np.testing.assert_allclose(got, want, rtol=0, atol=tol)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_strided_weighted_window(kex, seed):
+    rng = np.random.default_rng(7700 + seed)
+    ksize, strides = [((3, 3), (2, 2)), ((2, 2), (2, 2)), ((3, 3), (3, 3))][seed % 3]
+    h, w = int(rng.integers(40, 150)), 4 * int(rng.integers(40, 300))
+    border = ((int(rng.integers(0, 2)), int(rng.integers(0, 2))), (int(rng.integers(0, 4)), 1))
+    taps = list(itertools.product(range(ksize[0]), range(ksize[1])))
+    integer = seed % 2 == 0
+    if integer:
+        x = rng.integers(-100, 100, (h, w)).astype(np.int32)
+        coefs, bias = [int(c) or 1 for c in rng.integers(-5, 6, len(taps))], 7
+    else:
+        x = rng.standard_normal((h, w)).astype(np.float32)
+        coefs, bias = [float(c) for c in rng.standard_normal(len(taps))], 0.5
+
+    def fn(v):
+        acc = bias
+        for t, c in zip(taps, coefs):
+            acc = acc + c * v[t]
+        return acc
+
+    got = kex.kernel_map({fn: ()}, (h, w), ksize, strides, border, False)(x)
+    assert _last_kernel() == "pool2d_kernel"
+    want = ko.affine_map(x, ksize, strides, border, taps, coefs, bias)
+    if integer:
+        np.testing.assert_array_equal(got, want)
+    else:
+        scale = ko.affine_map(np.abs(x), ksize, strides, border, taps, np.abs(coefs), abs(bias))
+        assert np.all(np.abs(got.astype(np.float64) - want) <= 1e-5 * scale + 1e-30)
+
+
+def test_batched_and_1d_pooling(kex):
+    rng = np.random.default_rng(7800)
+    x = rng.standard_normal((5, 64, 256)).astype(np.float32)
+    pool = kex.vmap(kex.kmap(kernel_size=(3, 3), strides=(2, 2))(lambda v: np.mean(v)))   # README.md:331-336
+    got = pool(torch.from_numpy(x).cuda())
+    assert _last_kernel() == "pool2d_kernel"
+    want = np.stack([ko.reduce_map(x[b], (3, 3), (2, 2), ((0, 0), (0, 0)), "mean") for b in range(5)])
+    np.testing.assert_allclose(got.cpu().numpy(), want, rtol=0, atol=1e-5 * 9 * float(np.abs(x).max()))
+    x1 = rng.integers(-50, 50, (4096,)).astype(np.int32)
+    got1 = kex.kmap(kernel_size=(2,), strides=(2,))(lambda v: np.max(v))(x1)
+    assert _last_kernel() == "pool2d_kernel"
+    np.testing.assert_array_equal(got1, x1.reshape(-1, 2).max(axis=1))
+
+
+def test_unaligned_rows_fall_back_to_the_generic_kernel(kex):
+    x = np.random.default_rng(1).standard_normal((40, 131)).astype(np.float32)   # rows not 16-byte aligned
+    got = kex.kmap(kernel_size=(2, 2), strides=(2, 2))(lambda v: np.max(v))(x)
+    assert _last_kernel() == "generic_map_kernel"
+    np.testing.assert_array_equal(got, ko.reduce_map(x, (2, 2), (2, 2), ((0, 0), (0, 0)), "max"))
