@@ -136,10 +136,12 @@ const char* kx_last_kernel(void);
 int kx_map(const KxGeom* geom, const KxProgram* prog, const void* in, const void* coef_dev,
            int64_t coef_batch_stride, void* out, int64_t batch, void* stream);
 
-/* Writes the result of a scalar kmap into a COPY of the input at the strided
- * interior [o0, n-o1) (offset_kernel_map, kernex/_src/map.py:150-154).
- * `out` has geom.in_shape and geom.in_dtype and must already hold a copy of `in`
- * (the host does one cudaMemcpyAsync D2D); off0[d] is the per-axis start offset. */
+/* offset_kernel_map (kernex/_src/map.py:127-156): the result of a scalar kmap written into a copy of
+ * the input at the strided interior [off0[d] : off0[d] + out_shape[d]*stride[d] : stride[d]].
+ * `out` has geom.in_shape and geom.in_dtype (== out_dtype) and is WRITTEN COMPLETELY by the call: the
+ * launcher either runs one fused pass (stride 1, single AFFINE function: every cell is produced by
+ * the stencil kernel, cells outside the interior copy their input value) or enqueues the
+ * device-to-device copy itself followed by the strided write-back kernel. */
 int kx_map_offset(const KxGeom* geom, const KxProgram* prog, const void* in, const void* coef_dev,
                   const int32_t* off0, void* out, void* stream);
 

@@ -94,6 +94,10 @@ struct MapArgs {
   int64_t out_pitch[KX_MAX_DIMS];  // element pitch of the window index along each axis
   int64_t out_base;
   int32_t fn_elems;            // 1, or n_taps for KX_GATHER
+  // offset maps (smap) fused into one pass: windows whose centre lies outside [box_lo, box_hi) copy the
+  // centre input element instead of evaluating the function ('same'-style geometry only)
+  int32_t use_box;
+  int64_t box_lo[KX_MAX_DIMS], box_hi[KX_MAX_DIMS];
 };
 
 // generic (any rank <= 4, stride, border, multi-function) kernels -- kx_generic.cu

@@ -36,6 +36,7 @@ struct S2Args {
   int ly, lx;                  // left borders
   int th;                      // output rows per block
   uint32_t mask;               // bit ky*KX+kx set = tap present
+  int use_box, by0, by1, bx0, bx1;  // offset maps: outputs outside the box copy the window centre
   T bias;
   T coef[kMaxK * kMaxK];
 };
@@ -156,6 +157,12 @@ stencil2d_kernel(const __grid_constant__ S2Args<T> a) {
             }
           }
         }
+        if (a.use_box) {  // block-uniform: smap / offset_kernel_map fused into one pass
+          const bool rin = (r + u >= a.by0) && (r + u < a.by1);
+#pragma unroll
+          for (int i = 0; i < kCols; ++i)
+            if (!(rin && j0 + i >= a.bx0 && j0 + i < a.bx1)) acc[i] = q[u + (KY - 1) / 2][SHIFT + (KX - 1) / 2 + i];
+        }
         st_row4(out + (int64_t)(r + u) * a.wout + j0, acc, n_valid);
       }
     }
@@ -210,6 +217,13 @@ int run(const MapArgs& m, const KxProgram& p, int ay, int ax, int64_t batch, cud
   a.in_batch = (int64_t)a.hin * a.win;
   a.out_batch = (int64_t)a.hout * a.wout;
   a.bias = (T)f.bias;
+  if (m.use_box) {
+    a.use_box = 1;
+    a.by0 = ay >= 0 ? (int)m.box_lo[ay] : 0;
+    a.by1 = ay >= 0 ? (int)m.box_hi[ay] : 1;
+    a.bx0 = (int)m.box_lo[ax];
+    a.bx1 = (int)m.box_hi[ax];
+  }
   a.th = a.hout >= 512 ? 32 : (a.hout >= 64 ? 16 : 8);
   while ((a.hout + a.th - 1) / a.th > 65535) a.th *= 2;
   const bool dev = m.coef_dev != nullptr;
@@ -249,6 +263,7 @@ int try_stencil2d(const MapArgs& m, const KxProgram& p, cudaStream_t s) {
   int64_t lead = 1;
   for (int d = 0; d < nd - 2; ++d) {
     if (g.ksize[d] != 1 || g.stride[d] != 1 || g.lo[d] != 0 || g.hi[d] != 0) return KX_ERR_UNSUPPORTED;
+    if (m.use_box && (m.box_lo[d] != 0 || m.box_hi[d] != g.in_shape[d])) return KX_ERR_UNSUPPORTED;
     lead *= g.in_shape[d];
   }
   if (g.stride[ax] != 1 || (ay >= 0 && g.stride[ay] != 1)) return KX_ERR_UNSUPPORTED;

@@ -501,7 +501,23 @@ def offset_kernel_map(func_map: dict, shape, kernel_size, strides, offset, relat
     inner = kernel_map(func_map, shape, kernel_size, strides, border, relative, map_kind, map_kwargs)
 
     def call(array, *a, **k):
-        arr, res = _run_map(func_map, shape, kernel_size, strides, border, relative, array, a, k)
+        arr = _Arr(array)
+        if tuple(arr.t.shape) != tuple(shape):
+            raise ValueError(f"array shape {tuple(arr.t.shape)} != declared shape {tuple(shape)}")
+        specs, device_args, out_kx, prog, geom, full_shape = _map_plan(
+            func_map, shape, kernel_size, strides, border, relative, arr.kx_dtype, a, k)
+        scalar = len(full_shape) == len(shape)
+        needs_grad = torch.is_grad_enabled() and (arr.t.requires_grad or any(
+            isinstance(v, torch.Tensor) and v.requires_grad for v in device_args.values()))
+        if scalar and out_kx == arr.kx_dtype and not needs_grad and arr.t.numel():
+            # one library call writes the whole result (fused pass, or copy + strided write-back)
+            coef = prog.coef_tensor(device_args, _KX2TORCH[out_kx], arr.t.device)
+            out = torch.empty_like(arr.t)
+            off0 = (C.c_int32 * len(shape))(*[int(o[0]) for o in offset])
+            _lib.check(_lib.load().kx_map_offset(C.byref(geom), C.byref(prog.c), _ptr(arr.t), _ptr(coef), off0,
+                                                 _ptr(out), _stream_ptr(arr.t.device)))
+            return arr.give_back(out)
+        _, res = _run_map(func_map, shape, kernel_size, strides, border, relative, arr.t, a, k)
         return arr.give_back(_write_back(arr.t, res, shape, strides, offset, "map"))
 
     del inner

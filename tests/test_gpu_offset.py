@@ -1,0 +1,86 @@
+"""GPU parity of the offset variants (smap / offset_kernel_map, kernex/_src/map.py:127-156):
+the fused single-pass path (stride 1, affine: every cell written by the stencil kernel, cells
+outside the interior keep their input) and the copy + strided write-back path, vs the oracle."""
+from __future__ import annotations
+
+import numpy as np
+import pytest
+
+from oracle import kx_oracle as ko
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+
+@pytest.fixture(scope="module")
+def kex():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import kernex_b200
+    return kernex_b200
+
+
+def _last_kernel():
+    from kernex_b200 import _lib
+    return _lib.last_kernel()
+
+
+@pytest.mark.parametrize("seed", range(16))
+def test_offset_map_matches_oracle(kex, seed):
+    rng = np.random.default_rng(8100 + seed)
+    nd = 1 + seed % 2
+    ksize = tuple(int(rng.integers(1, 4)) for _ in range(nd)) if seed % 4 else (3,) * nd
+    shape = (int(rng.integers(20, 90)), 4 * int(rng.integers(8, 80)))[-nd:]
+    offset = tuple((int(rng.integers(0, 3)), int(rng.integers(0, 3))) for _ in range(nd))
+    strides = (1,) * nd if seed % 3 else tuple(int(rng.integers(1, 3)) for _ in range(nd))
+    integer = seed % 2 == 0
+    taps = [tuple(int(rng.integers(0, k)) for k in ksize) for _ in range(3)]
+    taps = list(dict.fromkeys(taps))
+    if integer:
+        x = rng.integers(-50, 50, shape).astype(np.int32)
+        coefs, bias = [int(c) or 2 for c in rng.integers(-4, 5, len(taps))], 3
+    else:
+        x = rng.standard_normal(shape).astype(np.float32)
+        coefs, bias = [float(c) for c in rng.standard_normal(len(taps))], 0.25
+
+    def fn(v):
+        acc = bias
+        for t, c in zip(taps, coefs):
+            acc = acc + c * v[t]
+        return acc
+
+    want = ko.offset_kernel_map({fn: ()}, shape, ksize, strides, offset, False)(x)
+    got = kex.offset_kernel_map({fn: ()}, shape, ksize, strides, offset, False)(x)
+    if all(s == 1 for s in strides):
+        assert _last_kernel() == "stencil2d_kernel"      # fused pass
+    assert got.shape == want.shape and got.dtype == want.dtype
+    if integer:
+        np.testing.assert_array_equal(got, want)
+    else:
+        np.testing.assert_allclose(got, want, rtol=1e-5, atol=1e-5)
+
+
+def test_smap_laplacian_large_and_device_resident(kex):
+    rng = np.random.default_rng(8200)
+    x = rng.standard_normal((300, 1028)).astype(np.float32)
+    f = lambda v: v[0, 1] + v[0, -1] + v[1, 0] + v[-1, 0] - 4 * v[0, 0]
+    got = kex.smap(kernel_size=(3, 3), offset=1, relative=True)(f)(torch.from_numpy(x).cuda())
+    assert got.is_cuda and _last_kernel() == "stencil2d_kernel"
+    want = x.copy()
+    want[1:-1, 1:-1] = x[1:-1, 2:] + x[1:-1, :-2] + x[2:, 1:-1] + x[:-2, 1:-1] - 4 * x[1:-1, 1:-1]
+    np.testing.assert_allclose(got.cpu().numpy(), want, rtol=1e-5, atol=1e-5)
+    np.testing.assert_array_equal(got.cpu().numpy()[0], x[0])          # untouched border = input bits
+    np.testing.assert_array_equal(got.cpu().numpy()[:, -1], x[:, -1])
+
+
+def test_smap_max_and_mean_use_the_write_back_path(kex):
+    x = np.random.default_rng(8300).integers(-9, 9, (12, 16)).astype(np.int32)
+    f = lambda v: np.max(v)
+    got = kex.smap(kernel_size=(3, 3), offset=1)(f)(x)
+    want = ko.offset_kernel_map({f: ()}, x.shape, (3, 3), (1, 1), ((1, 1), (1, 1)), False)(x)
+    np.testing.assert_array_equal(got, want)
+    xf = x.astype(np.float32)
+    g = lambda v: np.mean(v)
+    got = kex.smap(kernel_size=(3, 3), offset=1)(g)(xf)
+    want = ko.offset_kernel_map({g: ()}, x.shape, (3, 3), (1, 1), ((1, 1), (1, 1)), False)(xf)
+    np.testing.assert_allclose(got, want, rtol=1e-5, atol=1e-5)
