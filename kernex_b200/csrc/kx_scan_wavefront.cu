@@ -33,7 +33,7 @@ namespace {
 
 constexpr int kWaveThreads = 256;
 constexpr int kWaveSingleThreads = 1024;
-constexpr int64_t kWaveSingleMax = 16384;  // fronts up to this size run on one CTA (block barrier ~10x cheaper)
+constexpr int64_t kWaveSingleMax = 8192;  // fronts up to this size run on one CTA (block barrier ~10x cheaper)
 
 struct WaveArgs {
   KxGeom g;
@@ -49,19 +49,22 @@ __device__ __forceinline__ TIN ld_new(const TIN* p) {
   return __ldcg(p);  // results of other threads: L2 is the coherence point
 }
 
-template <typename TIN, typename TC>
+// IDX = int32_t when every extent and the window count fit 31 bits (64-bit divisions cost ~100
+// instructions each on the GPU); UNIT = all strides are 1 (the writer of a cell needs no division).
+template <typename TIN, typename TC, typename IDX, bool UNIT>
 __device__ __forceinline__ void wave_window(const WaveArgs& a, const DevProgram<TC>& p, const Strides& ist,
                                             const Strides& ost, const TIN* __restrict__ in, TIN* out,
-                                            const TC* __restrict__ coef_dev, const int64_t* j) {
+                                            const TC* __restrict__ coef_dev, const IDX* j) {
   const int nd = a.g.ndim;
-  int64_t origin[KX_MAX_DIMS], centre[KX_MAX_DIMS];
+  int64_t centre[KX_MAX_DIMS];
+  IDX origin[KX_MAX_DIMS];
   int64_t w = 0;
 #pragma unroll
   for (int d = 0; d < KX_MAX_DIMS; ++d) {
     if (d < nd) {
-      origin[d] = j[d] * a.g.stride[d] - a.g.lo[d];
-      centre[d] = origin[d] + (a.g.ksize[d] - 1) / 2;
-      w += j[d] * ost.v[d];
+      origin[d] = j[d] * (IDX)a.g.stride[d] - (IDX)a.g.lo[d];
+      centre[d] = (int64_t)origin[d] + (a.g.ksize[d] - 1) / 2;
+      w += (int64_t)j[d] * ost.v[d];
     }
   }
   const int f = select_func(p, centre);
@@ -75,13 +78,14 @@ __device__ __forceinline__ void wave_window(const WaveArgs& a, const DevProgram<
 #pragma unroll
     for (int d = 0; d < KX_MAX_DIMS; ++d) {
       if (d < nd) {
-        const int64_t c = origin[d] + p.tap_off[t][d];
-        inb = inb && (c >= 0) && (c < a.g.in_shape[d]);
-        ioff += c * ist.v[d];
-        const int64_t q = c - centre[d] + j[d] * a.g.stride[d];  // = jw * stride when x is a window centre
-        const int64_t jw = q / a.g.stride[d];
-        writer = writer && (q >= 0) && (jw * a.g.stride[d] == q) && (jw < a.g.out_shape[d]);
-        woff += jw * ost.v[d];
+        const IDX c = origin[d] + (IDX)p.tap_off[t][d];
+        inb = inb && (c >= 0) && (c < (IDX)a.g.in_shape[d]);
+        ioff += (int64_t)c * ist.v[d];
+        // q = jw * stride when the cell is a window centre
+        const IDX q = (IDX)p.tap_off[t][d] - (IDX)((a.g.ksize[d] - 1) / 2) + j[d] * (IDX)a.g.stride[d];
+        const IDX jw = UNIT ? q : q / (IDX)a.g.stride[d];
+        writer = writer && (q >= 0) && (UNIT || jw * (IDX)a.g.stride[d] == q) && (jw < (IDX)a.g.out_shape[d]);
+        woff += (int64_t)jw * ost.v[d];
         if (cmp == 0) cmp = (jw < j[d]) ? -1 : ((jw > j[d]) ? 1 : 0);
       }
     }
@@ -104,7 +108,7 @@ __device__ __forceinline__ void wave_window(const WaveArgs& a, const DevProgram<
   out[w] = (TIN)acc;  // cast to the carried dtype on write (scan.py:50)
 }
 
-template <typename TIN, typename TC>
+template <typename TIN, typename TC, typename IDX, bool UNIT>
 __global__ void __launch_bounds__(kWaveSingleThreads)
 scan_wavefront_kernel(const __grid_constant__ WaveArgs a, const __grid_constant__ DevProgram<TC> p,
                       const TIN* __restrict__ in, TIN* out, const TC* __restrict__ coef_dev) {
@@ -112,34 +116,41 @@ scan_wavefront_kernel(const __grid_constant__ WaveArgs a, const __grid_constant_
   const Strides ist = suffix_strides(a.g.in_shape, nd);
   const Strides ost = suffix_strides(a.g.out_shape, nd);
   const bool multi = gridDim.x > 1;
-  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+  const IDX tid = (IDX)blockIdx.x * (IDX)blockDim.x + (IDX)threadIdx.x;
+  const IDX nthreads = (IDX)gridDim.x * (IDX)blockDim.x;
+  const IDX n_free = (IDX)a.n_free;
   for (int64_t t = 0; t < a.n_steps; ++t) {
-    for (int64_t i = tid; i < a.n_free; i += nthreads) {
-      int64_t jp[KX_MAX_DIMS];  // sweep-order coordinates (mirrored when reverse)
-      int64_t r = i, rem = t;
+    for (IDX i = tid; i < n_free; i += nthreads) {
+      IDX jp[KX_MAX_DIMS];  // sweep-order coordinates (mirrored when reverse)
+      IDX r = i;
+      int64_t rem = t;
 #pragma unroll
       for (int d = KX_MAX_DIMS - 1; d >= 0; --d) {
         if (d < nd && d != a.solved) {
-          jp[d] = r % a.g.out_shape[d];
-          r /= a.g.out_shape[d];
+          const IDX n = (IDX)a.g.out_shape[d];
+          const IDX qd = r / n;
+          jp[d] = r - qd * n;
+          r = qd;
           rem -= (int64_t)a.a[d] * jp[d];
         }
       }
       if (a.solved >= 0) {
         const int64_t as = a.a[a.solved];
-        if (rem < 0 || rem % as != 0) continue;
-        const int64_t js = rem / as;
-        if (js >= a.g.out_shape[a.solved]) continue;
+        if (rem < 0 || rem >= as * a.g.out_shape[a.solved]) continue;
+        IDX js = (IDX)rem;
+        if (as != 1) {
+          js = (IDX)(rem / as);
+          if ((int64_t)js * as != rem) continue;
+        }
 #pragma unroll
         for (int d = 0; d < KX_MAX_DIMS; ++d)
           if (d == a.solved) jp[d] = js;
       }
-      int64_t j[KX_MAX_DIMS];
+      IDX j[KX_MAX_DIMS];
 #pragma unroll
       for (int d = 0; d < KX_MAX_DIMS; ++d)
-        if (d < nd) j[d] = a.reverse ? a.g.out_shape[d] - 1 - jp[d] : jp[d];
-      wave_window<TIN, TC>(a, p, ist, ost, in, out, coef_dev, j);
+        if (d < nd) j[d] = a.reverse ? (IDX)a.g.out_shape[d] - 1 - jp[d] : jp[d];
+      wave_window<TIN, TC, IDX, UNIT>(a, p, ist, ost, in, out, coef_dev, j);
     }
     if (t + 1 < a.n_steps) {
       if (multi) {
@@ -203,8 +214,8 @@ bool plan_wavefront(const KxGeom& g, const KxProgram& prog, int reverse, WaveArg
   return true;
 }
 
-template <typename TIN, typename TC>
-int launch_wave_t(const KxGeom& g, const KxProgram& prog, const void* in, const void* coef_dev, void* out,
+template <typename TIN, typename TC, typename IDX, bool UNIT>
+int launch_wave_x(const KxGeom& g, const KxProgram& prog, const void* in, const void* coef_dev, void* out,
                   int reverse, cudaStream_t s) {
   static thread_local DevProgram<TC> dp;
   static thread_local WaveArgs a;
@@ -214,7 +225,7 @@ int launch_wave_t(const KxGeom& g, const KxProgram& prog, const void* in, const 
   const TIN* in_p = (const TIN*)in;
   TIN* out_p = (TIN*)out;
   const TC* coef_p = (const TC*)coef_dev;
-  auto kern = scan_wavefront_kernel<TIN, TC>;
+  auto kern = scan_wavefront_kernel<TIN, TC, IDX, UNIT>;
   if (a.n_free <= kWaveSingleMax || a.n_steps == 1) {
     int threads = kWaveSingleThreads;
     int64_t blocks = 1;
@@ -238,6 +249,19 @@ int launch_wave_t(const KxGeom& g, const KxProgram& prog, const void* in, const 
   void* params[] = {(void*)&a, (void*)&dp, (void*)&in_p, (void*)&out_p, (void*)&coef_p};
   KX_CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)kern, dim3((unsigned)blocks), dim3(kWaveThreads), params, 0, s));
   return after_launch("scan_wavefront_kernel");
+}
+
+template <typename TIN, typename TC>
+int launch_wave_t(const KxGeom& g, const KxProgram& prog, const void* in, const void* coef_dev, void* out,
+                  int reverse, cudaStream_t s) {
+  bool small = prod(g.out_shape, g.ndim) < 0x40000000 && prod(g.in_shape, g.ndim) < 0x40000000, unit = true;
+  for (int d = 0; d < g.ndim; ++d) {
+    if (g.stride[d] != 1) unit = false;
+    if (g.in_shape[d] + g.lo[d] + g.hi[d] + g.ksize[d] >= 0x40000000) small = false;
+  }
+  if (small && unit) return launch_wave_x<TIN, TC, int32_t, true>(g, prog, in, coef_dev, out, reverse, s);
+  if (small) return launch_wave_x<TIN, TC, int32_t, false>(g, prog, in, coef_dev, out, reverse, s);
+  return launch_wave_x<TIN, TC, int64_t, false>(g, prog, in, coef_dev, out, reverse, s);
 }
 
 }  // namespace
