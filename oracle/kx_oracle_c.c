@@ -134,3 +134,73 @@ void kxo_rowmarch_f32(int64_t nt, int64_t nx, int nreg, const KxoRegion* reg, fl
   }
   free(prev);
 }
+
+/* ------------------------------------------------------------------------------------------
+ * kxo_map_views_f32 -- the reference's kmap ALGORITHM, step by step, instead of the streaming
+ * stencil above (which is what a hand-written CPU code does, not what kernex does):
+ *   1. jnp.pad with ALL padding appended at the end of each axis (kernex/_src/utils.py:43-53,
+ *      map.py:85); the low-side pad cells are reached through negative-index wraparound;
+ *   2. _generate_views (utils.py:74-90): per axis an int32 table [out_d][k_d] of window indices
+ *      -lo + j*s + i (general_arange, utils.py:205-242), then the Cartesian product over the
+ *      axes in row-major window order (general_product, utils.py:259-280): N_win x k_d int32 per
+ *      axis, MATERIALISED, rebuilt on every call (kernel_interface.py:130-157);
+ *   3. per window (vmap): gather the patch array[ix_(*view)] (map.py:46, utils.py:184-192), roll it
+ *      by -((k-1)//2) per axis when `relative` (utils.py:147-181), then evaluate the window
+ *      function on the patch: sum_t coef[t] * patch[tap[t]] with taps in PATCH coordinates (after
+ *      the roll) -- the caller lists every term the user wrote, zero coefficients included.
+ * Used by bench.py's reference arm / cpu_baseline as the closest CPU stand-in for kernex on
+ * JAX's CPU backend (JAX itself is not installable here).  2-D only (config 2 of BASELINE.json).
+ * `views` is caller-provided scratch of n_win * (k0 + k1) int32; `padded` of (n0+p0)*(n1+p1) floats.
+ */
+void kxo_map_views_f32(const KxoGeom* g, const int32_t* ksize, const int32_t* hi, const float* in, float* out,
+                       int ntaps, const int32_t* tap /*[ntaps][2], patch coords*/, const float* coef, float bias,
+                       int relative, float* padded, int32_t* views, int nthreads) {
+  if (g->ndim != 2) return;
+  if (nthreads < 1) nthreads = 1;
+  const int64_t n0 = g->in_shape[0], n1 = g->in_shape[1];
+  const int k0 = ksize[0], k1 = ksize[1];
+  const int64_t p0 = (g->lo[0] > 0 ? g->lo[0] : 0) + (hi[0] > 0 ? hi[0] : 0);
+  const int64_t p1 = (g->lo[1] > 0 ? g->lo[1] : 0) + (hi[1] > 0 ? hi[1] : 0);
+  const int64_t m0 = n0 + p0, m1 = n1 + p1;             /* padded shape */
+  const int64_t o0 = g->out_shape[0], o1 = g->out_shape[1], nwin = o0 * o1;
+  /* 1. pad at the end */
+#pragma omp parallel for schedule(static) num_threads(nthreads)
+  for (int64_t r = 0; r < m0; ++r) {
+    float* dst = padded + r * m1;
+    if (r < n0) {
+      memcpy(dst, in + r * n1, (size_t)n1 * sizeof(float));
+      for (int64_t c = n1; c < m1; ++c) dst[c] = 0.0f;
+    } else {
+      for (int64_t c = 0; c < m1; ++c) dst[c] = 0.0f;
+    }
+  }
+  /* 2. views: product of the per-axis index tables, materialised per window */
+  int32_t* v0 = views;                  /* [nwin][k0] */
+  int32_t* v1 = views + nwin * k0;      /* [nwin][k1] */
+#pragma omp parallel for schedule(static) num_threads(nthreads)
+  for (int64_t w = 0; w < nwin; ++w) {
+    const int64_t j0 = w / o1, j1 = w % o1;
+    for (int i = 0; i < k0; ++i) v0[w * k0 + i] = (int32_t)(-g->lo[0] + j0 * g->stride[0] + i);
+    for (int i = 0; i < k1; ++i) v1[w * k1 + i] = (int32_t)(-g->lo[1] + j1 * g->stride[1] + i);
+  }
+  /* 3. gather -> roll -> function, one window at a time */
+  const int r0 = relative ? (k0 - 1) / 2 : 0, r1 = relative ? (k1 - 1) / 2 : 0;
+#pragma omp parallel for schedule(static) num_threads(nthreads)
+  for (int64_t w = 0; w < nwin; ++w) {
+    float patch[25], rolled[25];
+    for (int a = 0; a < k0; ++a) {
+      int64_t ia = v0[w * k0 + a];
+      if (ia < 0) ia += m0;             /* negative index = from the end (the appended zeros) */
+      for (int b = 0; b < k1; ++b) {
+        int64_t ib = v1[w * k1 + b];
+        if (ib < 0) ib += m1;
+        patch[a * k1 + b] = padded[ia * m1 + ib];
+      }
+    }
+    for (int a = 0; a < k0; ++a)       /* roll by -r: rolled[a] = patch[(a + r) mod k] */
+      for (int b = 0; b < k1; ++b) rolled[a * k1 + b] = patch[((a + r0) % k0) * k1 + (b + r1) % k1];
+    float acc = bias;
+    for (int t = 0; t < ntaps; ++t) acc += coef[t] * rolled[tap[2 * t] * k1 + tap[2 * t + 1]];
+    out[w] = acc;
+  }
+}

@@ -91,3 +91,31 @@ def rowmarch(nt, nx, regions, nthreads=None, out=None):
     load().kxo_rowmarch_f32(C.c_int64(nt), C.c_int64(nx), C.c_int(len(regions)), arr, out.ctypes.data_as(C.c_void_p),
                             C.c_int(nthreads or max_threads()))
     return out
+
+
+def map_views(x, kernel_size, strides, border, taps, coefs, bias=0.0, relative=False, nthreads=None, out=None,
+              scratch=None):
+    """The reference's own kmap algorithm (pad at the end + materialised int32 views + per-window gather
+    + roll + function), 2-D float32.  ``taps`` are PATCH coordinates after the roll (non-negative:
+    relative index -1 is k-1) and list every term the user wrote.  ``scratch`` = (padded, views)
+    arrays to reuse between calls."""
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    assert x.ndim == 2 and max(kernel_size) <= 5
+    g, out_shape = _geom(x.shape, kernel_size, strides, border)
+    if out is None:
+        out = np.empty(out_shape, dtype=np.float32)
+    nwin = int(np.prod(out_shape))
+    pads = [max(lo, 0) + max(hi, 0) for lo, hi in border]
+    if scratch is None:
+        scratch = (np.empty((x.shape[0] + pads[0]) * (x.shape[1] + pads[1]), np.float32),
+                   np.empty(nwin * (kernel_size[0] + kernel_size[1]), np.int32))
+    padded, views = scratch
+    ks = (C.c_int32 * 2)(*kernel_size)
+    hi = (C.c_int32 * 2)(*[b[1] for b in border])
+    tap = np.ascontiguousarray(np.asarray(taps, dtype=np.int32).reshape(len(taps), 2))
+    coef = np.ascontiguousarray(np.asarray(coefs, dtype=np.float32))
+    load().kxo_map_views_f32(C.byref(g), ks, hi, x.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p),
+                             C.c_int(len(taps)), tap.ctypes.data_as(C.c_void_p), coef.ctypes.data_as(C.c_void_p),
+                             C.c_float(bias), C.c_int(int(bool(relative))), padded.ctypes.data_as(C.c_void_p),
+                             views.ctypes.data_as(C.c_void_p), C.c_int(nthreads or max_threads()))
+    return out

@@ -59,3 +59,41 @@ def test_rowmarch_matches_literal_scan():
     ]
     got = kc.rowmarch(nt, nx, regions)
     np.testing.assert_allclose(got, want, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_views_gather_restatement_matches_literal_oracle(seed):
+    """kxo_map_views_f32 (pad at the end + materialised views + gather + roll + function, the
+    reference's own algorithm, used by bench.py's reference arm) against the literal NumPy oracle."""
+    rng = np.random.default_rng(300 + seed)
+    shape = (int(rng.integers(5, 14)), int(rng.integers(5, 14)))
+    ksize = (int(rng.integers(1, 4)), int(rng.integers(1, 4)))
+    strides = (int(rng.integers(1, 3)), int(rng.integers(1, 3)))
+    border = tuple((int(rng.integers(0, 3)), int(rng.integers(0, 3))) for _ in shape)
+    relative = bool(seed % 2)
+    if any(o <= 0 for o in ko.output_shape(shape, ksize, strides, border)):
+        pytest.skip("empty")
+    taps = list(itertools.product(range(ksize[0]), range(ksize[1])))   # patch coordinates
+    w = rng.standard_normal(len(taps)).astype(np.float32)
+    x = rng.standard_normal(shape).astype(np.float32)
+
+    def fn(p):
+        acc = np.float32(0.5)
+        for t, c in zip(taps, w):
+            acc = acc + c * p[t]
+        return acc
+
+    want = ko.kernel_map({fn: ()}, shape, ksize, strides, border, relative)(x)
+    got = kc.map_views(x, ksize, strides, border, taps, w, bias=0.5, relative=relative)
+    np.testing.assert_allclose(got, want, rtol=1e-6, atol=1e-6)
+
+
+def test_views_gather_restatement_readme_laplacian():
+    # README.md:122-143: Laplacian of ones (valid) is zero; relative indices -1 -> patch index k-1
+    x = np.ones((10, 10), np.float32)
+    rel = {-1: 2, 0: 0, 1: 1}
+    terms = [((1, -1), 0), ((1, 0), 1), ((1, 1), 0), ((0, -1), 1), ((0, 0), -4), ((0, 1), 1), ((-1, -1), 0),
+             ((-1, 0), 1), ((-1, 1), 0)]
+    taps = [(rel[a], rel[b]) for (a, b), _ in terms]
+    got = kc.map_views(x, (3, 3), (1, 1), ((0, 0), (0, 0)), taps, [c for _, c in terms], relative=True)
+    np.testing.assert_array_equal(got, np.zeros((8, 8), np.float32))
