@@ -8,7 +8,9 @@ python benchmarks/run_configs.py --reps 6 > gpurun_out/configs_plain.jsonl 2> gp
 $NCU -k regex:stencil2d -s 8 -c 1 -o gpurun_out/p_stencil2d python benchmarks/run_configs.py --only C2 --reps 2 > /dev/null 2>&1
 $NCU -k regex:stencil3d_star -s 3 -c 1 -o gpurun_out/p_stencil3d_star python benchmarks/run_configs.py --only C5 --reps 2 > /dev/null 2>&1
 $NCU -k regex:scan_rowmarch -s 70 -c 1 -o gpurun_out/p_rowmarch python benchmarks/run_configs.py --only C4 --reps 2 > /dev/null 2>&1
-$NCU -k regex:conv_fwd -s 8 -c 1 -o gpurun_out/p_conv_fwd python benchmarks/run_configs.py --only C3a --reps 2 > /dev/null 2>&1
-$NCU -k regex:conv_wgrad_kernel -s 3 -c 1 -o gpurun_out/p_conv_wgrad python benchmarks/run_configs.py --only C3a --reps 2 > /dev/null 2>&1
+$NCU -k regex:conv_fwd_rows -s 8 -c 1 -o gpurun_out/p_conv_fwd python benchmarks/run_configs.py --only C3a --reps 2 > /dev/null 2>&1
+$NCU -k regex:conv_wgrad_rows -s 3 -c 1 -o gpurun_out/p_conv_wgrad python benchmarks/run_configs.py --only C3a --reps 2 > /dev/null 2>&1
 $NCU -k regex:patch2d -s 8 -c 1 -o gpurun_out/p_patch2d python benchmarks/run_configs.py --only C3b --reps 2 > /dev/null 2>&1
+(cd benchmarks && python misc_paths.py > ../gpurun_out/misc_paths.jsonl 2> ../gpurun_out/misc_paths.err)
+(cd benchmarks && $NCU -k regex:pool2d -s 12 -c 1 -o ../gpurun_out/p_pool2d_s2 python misc_paths.py pool > /dev/null 2>&1)
 ls -la gpurun_out/p_*.ncu-rep
