@@ -82,12 +82,14 @@ __device__ __forceinline__ void st_row4(T* p, const T (&a)[4], int n_valid) {
   }
 }
 
-// SHIFT = (-lx) mod 4 when the input rows are 16-byte aligned (VEC), else 0.
-template <typename T, int KY, int KX, int SHIFT, bool VEC, int U>
+// VW = elements per load: 4 when the input rows are 16-byte aligned, 2 when they are 8-byte aligned
+// (even widths such as the 16382-wide cotangent of the C2 backward pass), else 1.
+// SHIFT = (-lx) mod VW: misalignment of the window inside the thread's aligned row buffer.
+template <typename T, int KY, int KX, int SHIFT, int VW, int U>
 __global__ void __launch_bounds__(kTX)
 stencil2d_kernel(const __grid_constant__ S2Args<T> a) {
-  constexpr int NV = (SHIFT + KX + kCols - 1 + 3) / 4;  // aligned vectors per row per thread
-  constexpr int NE = NV * 4;
+  constexpr int NV = (SHIFT + KX + kCols - 1 + VW - 1) / VW;  // aligned vectors per row per thread
+  constexpr int NE = NV * VW;
   const int j0 = (blockIdx.x * kTX + threadIdx.x) * kCols;  // first output column
   if (j0 >= a.wout) return;
   const int r0 = blockIdx.y * a.th;
@@ -110,7 +112,7 @@ stencil2d_kernel(const __grid_constant__ S2Args<T> a) {
   auto load_row = [&](int iy, T(&dst)[NE]) {
     const bool row_ok = (iy >= 0) && (iy < a.hin);
     const T* rp = in + (int64_t)iy * a.win;
-    if (VEC) {
+    if (VW == 4) {
 #pragma unroll
       for (int v = 0; v < NV; ++v) {
         const int c = xa + 4 * v;
@@ -121,6 +123,19 @@ stencil2d_kernel(const __grid_constant__ S2Args<T> a) {
         } else {
 #pragma unroll
           for (int e = 0; e < 4; ++e) dst[4 * v + e] = T(0);
+        }
+      }
+    } else if (VW == 2) {
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        const int c = xa + 2 * v;
+        if (row_ok && c >= 0 && c + 1 < a.win) {  // win % 2 == 0: a pair is all in or all out
+          const int2 raw = __ldg(reinterpret_cast<const int2*>(rp + c));
+          dst[2 * v] = reinterpret_cast<const T&>(raw.x);
+          dst[2 * v + 1] = reinterpret_cast<const T&>(raw.y);
+        } else {
+          dst[2 * v] = T(0);
+          dst[2 * v + 1] = T(0);
         }
       }
     } else {
@@ -175,22 +190,24 @@ stencil2d_kernel(const __grid_constant__ S2Args<T> a) {
 }
 
 template <typename T, int KY, int KX>
-int launch_kk(const S2Args<T>& a, int batch, bool vec, cudaStream_t s) {
+int launch_kk(const S2Args<T>& a, int batch, int vw, cudaStream_t s) {
   constexpr int U = (KY * KX >= 15) ? 2 : 4;
   dim3 grid((a.wout + kTX * kCols - 1) / (kTX * kCols), (a.hout + a.th - 1) / a.th, batch);
-  const int shift = vec ? (((-a.lx) % 4) + 4) % 4 : 0;
-  if (!vec) stencil2d_kernel<T, KY, KX, 0, false, U><<<grid, kTX, 0, s>>>(a);
-  else if (shift == 0) stencil2d_kernel<T, KY, KX, 0, true, U><<<grid, kTX, 0, s>>>(a);
-  else if (shift == 1) stencil2d_kernel<T, KY, KX, 1, true, U><<<grid, kTX, 0, s>>>(a);
-  else if (shift == 2) stencil2d_kernel<T, KY, KX, 2, true, U><<<grid, kTX, 0, s>>>(a);
-  else stencil2d_kernel<T, KY, KX, 3, true, U><<<grid, kTX, 0, s>>>(a);
+  const int shift = vw > 1 ? (((-a.lx) % vw) + vw) % vw : 0;
+  if (vw == 1) stencil2d_kernel<T, KY, KX, 0, 1, U><<<grid, kTX, 0, s>>>(a);
+  else if (vw == 2 && shift == 0) stencil2d_kernel<T, KY, KX, 0, 2, U><<<grid, kTX, 0, s>>>(a);
+  else if (vw == 2) stencil2d_kernel<T, KY, KX, 1, 2, U><<<grid, kTX, 0, s>>>(a);
+  else if (shift == 0) stencil2d_kernel<T, KY, KX, 0, 4, U><<<grid, kTX, 0, s>>>(a);
+  else if (shift == 1) stencil2d_kernel<T, KY, KX, 1, 4, U><<<grid, kTX, 0, s>>>(a);
+  else if (shift == 2) stencil2d_kernel<T, KY, KX, 2, 4, U><<<grid, kTX, 0, s>>>(a);
+  else stencil2d_kernel<T, KY, KX, 3, 4, U><<<grid, kTX, 0, s>>>(a);
   return after_launch("stencil2d_kernel");
 }
 
 template <typename T>
-int launch_t(const S2Args<T>& a, int ky, int kx, int batch, bool vec, cudaStream_t s) {
+int launch_t(const S2Args<T>& a, int ky, int kx, int batch, int vw, cudaStream_t s) {
 #define KX_CASE(Y, X) \
-  if (ky == Y && kx == X) return launch_kk<T, Y, X>(a, batch, vec, s);
+  if (ky == Y && kx == X) return launch_kk<T, Y, X>(a, batch, vw, s);
   KX_CASE(1, 1) KX_CASE(1, 2) KX_CASE(1, 3) KX_CASE(1, 5)
   KX_CASE(2, 1) KX_CASE(2, 2) KX_CASE(2, 3)
   KX_CASE(3, 1) KX_CASE(3, 2) KX_CASE(3, 3)
@@ -246,8 +263,11 @@ int run(const MapArgs& m, const KxProgram& p, int ay, int ax, int64_t batch, cud
     a.coef_batch = m.coef_batch_stride;
   }
   for (int i = 0; i < KY * KX; ++i) a.coef[i] = dense[i];
-  const bool vec = (a.win % 4 == 0) && ((reinterpret_cast<uintptr_t>(m.in) & 15) == 0) && (a.in_batch % 4 == 0);
-  return launch_t<T>(a, KY, KX, (int)batch, vec, s);
+  const uintptr_t base = reinterpret_cast<uintptr_t>(m.in);
+  int vw = 1;
+  if (a.win % 4 == 0 && (base & 15) == 0 && a.in_batch % 4 == 0) vw = 4;
+  else if (a.win % 2 == 0 && (base & 7) == 0 && a.in_batch % 2 == 0) vw = 2;
+  return launch_t<T>(a, KY, KX, (int)batch, vw, s);
 }
 
 }  // namespace
