@@ -90,6 +90,18 @@ __device__ __forceinline__ int32_t mad_wrap(int32_t c, int32_t v, int32_t acc) {
 }
 __device__ __forceinline__ float mad_wrap(float c, float v, float acc) { return fmaf(c, v, acc); }
 
+// Packed fp32 FMA (sm_100 FFMA2): (d0, d1) = (a0 * b0 + d0, a1 * b1 + d1), each half rounded exactly like
+// fmaf.  One issue slot for two FMAs: what the issue-bound kernels (27 FMA per conv output) need.  ptxas
+// broadcasts a scalar operand (a0 == a1) without building a register pair.
+__device__ __forceinline__ void ffma2(float& d0, float& d1, float a0, float a1, float b0, float b1) {
+  unsigned long long a, b, c;
+  asm("mov.b64 %0, {%1,%2};" : "=l"(a) : "f"(a0), "f"(a1));
+  asm("mov.b64 %0, {%1,%2};" : "=l"(b) : "f"(b0), "f"(b1));
+  asm("mov.b64 %0, {%1,%2};" : "=l"(c) : "f"(d0), "f"(d1));
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(c) : "l"(a), "l"(b));
+  asm("mov.b64 {%0,%1}, %2;" : "=f"(d0), "=f"(d1) : "l"(c));
+}
+
 // streaming (read-once / write-once) vector accesses: keep L1 for the halo re-reads
 __device__ __forceinline__ float4 ldg_stream4(const float* p) {
   float4 r;

@@ -414,10 +414,17 @@ conv_fwd_rows_kernel(const __grid_constant__ ConvArgs<T> a) {
 #pragma unroll
       for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-        for (int kx = 0; kx < 3; ++kx)
+        for (int kx = 0; kx < 3; ++kx) {
+          if constexpr (std::is_same<T, float>::value) {  // two packed FMAs instead of four scalar ones
+            const float wk = w[(c * 3 + ky) * 3 + kx];
+            ffma2(acc[(P + 2 - ky) % 3][0], acc[(P + 2 - ky) % 3][1], wk, wk, e[kx], e[kx + 1]);
+            ffma2(acc[(P + 2 - ky) % 3][2], acc[(P + 2 - ky) % 3][3], wk, wk, e[kx + 2], e[kx + 3]);
+          } else {
 #pragma unroll
-          for (int i = 0; i < kCols; ++i)
-            acc[(P + 2 - ky) % 3][i] = mad_wrap(w[(c * 3 + ky) * 3 + kx], e[kx + i], acc[(P + 2 - ky) % 3][i]);
+            for (int i = 0; i < kCols; ++i)
+              acc[(P + 2 - ky) % 3][i] = mad_wrap(w[(c * 3 + ky) * 3 + kx], e[kx + i], acc[(P + 2 - ky) % 3][i]);
+          }
+        }
     }
     if (iy >= iy0 + 2 && n_valid > 0) st_out4(orow, acc[P % 3], n_valid);  // output row iy + ly - 2 is complete
     orow += a.wout;
@@ -499,12 +506,15 @@ conv_wgrad_rows_kernel(const __grid_constant__ ConvArgs<float> a) {
       float e[6];
       ring.template window<P>(c, e);
 #pragma unroll
-      for (int ky = 0; ky < 3; ++ky)
+      for (int ky = 0; ky < 3; ++ky) {
+        // taps kx = 0, 1 share the cotangent factor: one packed FMA per column; kx = 2 stays scalar
 #pragma unroll
-        for (int kx = 0; kx < 3; ++kx)
-#pragma unroll
-          for (int i = 0; i < kCols; ++i)
-            acc[(c * 3 + ky) * 3 + kx] = fmaf(g[(P + 3 - ky) % 3][i], e[kx + i], acc[(c * 3 + ky) * 3 + kx]);
+        for (int i = 0; i < kCols; ++i) {
+          const float gi = g[(P + 3 - ky) % 3][i];
+          ffma2(acc[(c * 3 + ky) * 3 + 0], acc[(c * 3 + ky) * 3 + 1], gi, gi, e[i], e[i + 1]);
+          acc[(c * 3 + ky) * 3 + 2] = fmaf(gi, e[2 + i], acc[(c * 3 + ky) * 3 + 2]);
+        }
+      }
     }
   };
 
