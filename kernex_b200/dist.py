@@ -112,7 +112,7 @@ class SlabStencil:
     """A kmap applied to a row-slab-decomposed global array on CUDA."""
 
     def __init__(self, func, kernel_size, relative, rows_per_rank, width=None, device=None, padding="valid",
-                 trailing_shape=None, group=None):
+                 trailing_shape=None, group=None, args=()):
         from .engine import PreparedMap
         from .resolve import resolve_padding
 
@@ -131,7 +131,8 @@ class SlabStencil:
         out_trailing = None
         for p in L.pieces:
             shape = (p.in1 - p.in0,) + trailing
-            pm = PreparedMap({func: ()}, shape, kernel_size, strides, (p.border0,) + tuple(border[1:]), relative)
+            pm = PreparedMap({func: ()}, shape, kernel_size, strides, (p.border0,) + tuple(border[1:]), relative,
+                             args=tuple(args))
             self.maps.append((p, pm))
             out_trailing = tuple(pm.out_shape[1:])
         self.out = torch.empty((L.out_rows,) + out_trailing, dtype=torch.float32, device=self.device)
@@ -165,6 +166,64 @@ class SlabStencil:
         if self.world > 1:
             main.wait_stream(self.side)
         return self.out
+
+
+    def vjp(self, g_local: torch.Tensor, want_input=True, want_coef=False):
+        """Adjoint of :meth:`step`: ``g_local`` is the cotangent of this rank's output rows.
+
+        * input: every piece's flipped-tap stencil of its cotangent rows is accumulated into an
+          ext-shaped buffer; the rows that landed in the halos belong to the neighbours, so they travel
+          back with the transposed halo exchange (``isend`` of my halo rows, ``irecv`` + add into my
+          edge rows).  Returns the cotangent of the OWN rows.
+        * coefficients (device weights): per-piece window correlations summed locally, then one
+          ``all_reduce`` of ``n_taps`` floats.
+        """
+        L = self.layout
+        g_local = g_local.contiguous()
+        dx_own = dcoef = None
+        if want_input:
+            dext = torch.zeros_like(self.ext)
+            for p, pm in self.maps:
+                gp = g_local[p.out0:p.out1]
+                if gp.shape[0] == 0:
+                    continue
+                if not p.needs_halo and p.in0 == L.halo_top and p.in1 == L.halo_top + L.rows:
+                    pm.vjp_input(gp, out=dext[p.in0:p.in1])       # interior piece: written in place
+            for p, pm in self.maps:
+                gp = g_local[p.out0:p.out1]
+                if gp.shape[0] == 0 or (not p.needs_halo and p.in0 == L.halo_top and p.in1 == L.halo_top + L.rows):
+                    continue
+                dext[p.in0:p.in1] += pm.vjp_input(gp)             # O(halo)-row strips
+            if self.world > 1:
+                ht, hb, R = L.halo_top, L.halo_bot, L.rows
+                ops, adds = [], []
+                if not L.first:
+                    buf = torch.empty_like(dext[ht:ht + L.send_up])
+                    ops.append(dist.P2POp(dist.irecv, buf, self.rank - 1, self.group))
+                    ops.append(dist.P2POp(dist.isend, dext[0:ht].contiguous(), self.rank - 1, self.group))
+                    adds.append((slice(ht, ht + L.send_up), buf))
+                if not L.last:
+                    buf = torch.empty_like(dext[ht + R - L.send_down:ht + R])
+                    ops.append(dist.P2POp(dist.irecv, buf, self.rank + 1, self.group))
+                    ops.append(dist.P2POp(dist.isend, dext[ht + R:ht + R + hb].contiguous(), self.rank + 1, self.group))
+                    adds.append((slice(ht + R - L.send_down, ht + R), buf))
+                ops = [op for op in ops if op.tensor.numel() > 0]
+                for r in (dist.batch_isend_irecv(ops) if ops else []):
+                    r.wait()
+                for sl, buf in adds:
+                    if buf.numel():
+                        dext[sl] += buf
+            dx_own = dext[L.own]
+        if want_coef:
+            for p, pm in self.maps:
+                gp = g_local[p.out0:p.out1]
+                if gp.shape[0] == 0:
+                    continue
+                part = pm.vjp_coef(self.ext[p.in0:p.in1], gp)
+                dcoef = part if dcoef is None else dcoef + part
+            if self.world > 1:
+                dist.all_reduce(dcoef, op=dist.ReduceOp.SUM, group=self.group)
+        return dx_own, dcoef
 
 
 # --------------------------------------------------------------------------- #

@@ -451,6 +451,37 @@ class PreparedMap:
                                         1, _stream_ptr(x.device)))
         return out
 
+    def _check_vjp(self, g):
+        if len(self.specs) != 1 or self.specs[0].kind != "affine" or self.out_dtype != torch.float32 \
+                or self.in_dtype != torch.float32:
+            raise UnsupportedStencilError("gradients are implemented for single-function float32 affine stencils")
+        if tuple(g.shape) != tuple(self.out_shape) or g.dtype != torch.float32 or not g.is_contiguous():
+            raise ValueError(f"cotangent must be contiguous float32 {tuple(self.out_shape)}")
+
+    def vjp_input(self, g, out=None, coef=None):
+        """Cotangent of the input: the flipped-tap stencil of ``g`` (``kx_map_vjp_input``)."""
+        self._check_vjp(g)
+        if out is None:
+            out = torch.empty(self.shape, dtype=torch.float32, device=g.device)
+        if coef is None:
+            coef = self.prog.coef_tensor(self.device_args, torch.float32, g.device)
+        if out.numel():
+            _lib.check(self._lib.kx_map_vjp_input(C.byref(self.geom), C.byref(self.prog.c), _ptr(g), _ptr(coef), _ptr(out),
+                                                  _stream_ptr(g.device)))
+        return out
+
+    def vjp_coef(self, x, g):
+        """Cotangent of the coefficient table ``[n_taps]`` (``kx_map_vjp_coef``: fused window correlation,
+        deterministic two-stage reduction)."""
+        self._check_vjp(g)
+        nbytes = int(self._lib.kx_vjp_coef_scratch_bytes(C.byref(self.geom), C.byref(self.prog.c)))
+        scratch = torch.empty(max(nbytes, 4), dtype=torch.uint8, device=x.device)
+        dcoef = torch.zeros(self.prog.c.n_taps, dtype=torch.float32, device=x.device)
+        if g.numel():
+            _lib.check(self._lib.kx_map_vjp_coef(C.byref(self.geom), C.byref(self.prog.c), _ptr(x), _ptr(g), _ptr(scratch),
+                                                 _ptr(dcoef), _stream_ptr(x.device)))
+        return dcoef
+
 
 def kernel_map(func_map: dict, shape, kernel_size, strides, border, relative: bool = False,
                map_kind: str = "vmap", map_kwargs: dict | None = None) -> Callable:

@@ -59,6 +59,58 @@ def main():
         if rank == 0:
             print(f"{fn.__name__} {ksize} rows={rows} trailing={trailing} padding={padding}: "
                   f"{'bit-identical' if flag.item() else 'MISMATCH'}", flush=True)
+    # ---- adjoint: dx through the transposed halo exchange, dw through one all-reduce ----
+    import numpy as np
+
+    def conv(x, w):
+        return np.sum(x * w)
+
+    for (fn, ksize, rows, trailing, padding, wshape) in [
+        (lap, (3, 3), 48, (256,), "same", None), (lap, (3, 3), 40, (132,), "valid", None),
+        (conv, (3, 3), 64, (260,), "same", (3, 3)), (conv, (3, 3, 3), 16, (24, 64), "valid", (3, 3, 3)),
+    ]:
+        gen = torch.Generator(device=dev).manual_seed(300 + rank)
+        w = None
+        if wshape is not None:
+            w = torch.randn(wshape, device=dev, generator=torch.Generator(device=dev).manual_seed(7))
+        slab = SlabStencil(fn, kernel_size=ksize, relative=wshape is None, rows_per_rank=rows, trailing_shape=trailing,
+                           device=dev, padding=padding, args=() if w is None else (w,))
+        slab.fill_random(gen)
+        out = slab.step()
+        g_local = torch.randn(out.shape, device=dev, generator=gen)
+        dx, dw = slab.vjp(g_local, want_input=True, want_coef=w is not None)
+        torch.cuda.synchronize()
+        own = slab.ext[slab.layout.own].contiguous()
+        parts = [torch.empty_like(own) for _ in range(world)]
+        dist.all_gather(parts, own)
+        glob = torch.cat(parts, dim=0).requires_grad_()
+        counts = torch.tensor([out.shape[0]], device=dev)
+        allc = [torch.zeros_like(counts) for _ in range(world)]
+        dist.all_gather(allc, counts)
+        gparts = []
+        for r in range(world):
+            buf = torch.empty((int(allc[r].item()),) + tuple(out.shape[1:]), device=dev)
+            if r == rank:
+                buf.copy_(g_local)
+            dist.broadcast(buf, src=r)
+            gparts.append(buf)
+        g_glob = torch.cat(gparts, dim=0)
+        wg = None if w is None else w.clone().requires_grad_()
+        f1 = kex.kmap(kernel_size=ksize, padding=padding, relative=wshape is None)(fn)
+        y = f1(glob) if w is None else f1(glob, wg)
+        grads = torch.autograd.grad(y, [glob] if w is None else [glob, wg], g_glob)
+        want_dx = grads[0][rank * rows:(rank + 1) * rows]
+        scale = float(g_glob.abs().max()) * 30
+        same = bool(torch.allclose(dx, want_dx, rtol=1e-5, atol=1e-5 * scale))
+        if w is not None:
+            tol = 1e-4 * float(np.sqrt(g_glob.numel())) * 4
+            same = same and bool(torch.allclose(dw.reshape(wshape), grads[1], rtol=1e-4, atol=tol))
+        flag = torch.tensor([1 if same else 0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        ok = ok and bool(flag.item())
+        if rank == 0:
+            print(f"VJP {fn.__name__} {ksize} rows={rows} padding={padding}: {'ok' if flag.item() else 'MISMATCH'}",
+                  flush=True)
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)
 
