@@ -108,6 +108,14 @@ def main():
         ms = timed(sh.run, max(args.reps // 2, 3), dev, world)
         emit("c4", total(sh.local_windows), 4, ms, {"nt": nt, "nx_global": nx, "held_columns": sh.width,
                                                     "recomputed_cone_columns": sh.keep_lo})
+        del sh
+        torch.cuda.empty_cache()
+        if world > 1:   # halo-EXCHANGE form: T*R ghost values per neighbour per 64-row block (NCCL send/recv)
+            sh = ColumnShardedScan(F, nt, nx, rank=rank, world=world, device=dev, exchange=True)
+            ms = timed(sh.run, max(args.reps // 2, 3), dev, world)
+            emit("c4_exchange", total(sh.local_windows), 4, ms,
+                 {"nt": nt, "nx_global": nx, "held_columns": sh.width, "ghost_columns": sh.ghost_l,
+                  "exchanges": (nt - 1) // sh.t_rows, "bytes_per_exchange": sh.ghost_l * 4})
     if world > 1:
         dist.destroy_process_group()
 

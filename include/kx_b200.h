@@ -186,6 +186,16 @@ int kx_scan(const KxGeom* geom, const KxProgram* prog, const void* in, const voi
 int kx_scan_rowmarch_shard(const KxGeom* geom, const KxProgram* prog, int64_t col_base, int64_t global_nx,
                            void* out, void* stream);
 
+/* The same shard advanced over rows [row_begin, row_end) only: row row_begin-1 of `out` (all held
+ * columns, ghost columns included) must already be final.  This is the building block of the
+ * halo-EXCHANGE form of the multi-GPU kscan: a shard over-allocated by only
+ * T*R ghost columns per side, T = kx_scan_rowmarch_rows_per_launch(), receives row n0-1 of its ghost
+ * columns from the neighbouring rank (T*R*4 bytes, NCCL send/recv) before each T-row block; inside the
+ * block the ghost columns decay with the dependency cone exactly like the per-CTA halo does. */
+int kx_scan_rowmarch_rows_per_launch(void);
+int kx_scan_rowmarch_shard_rows(const KxGeom* geom, const KxProgram* prog, int64_t col_base, int64_t global_nx,
+                                int32_t row_begin, int32_t row_end, void* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -92,6 +92,9 @@ _SIGNATURES = {
                           C.c_void_p, C.c_int32, C.c_void_p]),
     "kx_scan_rowmarch_shard": (C.c_int, [C.POINTER(KxGeom), C.POINTER(KxProgram), C.c_int64, C.c_int64,
                                          C.c_void_p, C.c_void_p]),
+    "kx_scan_rowmarch_rows_per_launch": (C.c_int, []),
+    "kx_scan_rowmarch_shard_rows": (C.c_int, [C.POINTER(KxGeom), C.POINTER(KxProgram), C.c_int64, C.c_int64,
+                                              C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
 }
 
 _lock = threading.Lock()

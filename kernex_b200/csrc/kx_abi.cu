@@ -265,7 +265,25 @@ int kx_scan_rowmarch_shard(const KxGeom* geom, const KxProgram* prog, int64_t co
   if (geom->ndim != 2 || col_base + geom->in_shape[1] > global_nx + (int64_t)geom->in_shape[0] * 4 || global_nx < 1)
     return fail(KX_ERR_INVALID, "shard [%lld, %lld) does not belong to a scan of width %lld", (long long)col_base,
                 (long long)(col_base + (geom->ndim == 2 ? geom->in_shape[1] : 0)), (long long)global_nx);
-  rc = scan_rowmarch_shard(*geom, *prog, nullptr, out, 0, col_base, global_nx, (cudaStream_t)stream);
+  rc = scan_rowmarch_shard(*geom, *prog, nullptr, out, 0, col_base, global_nx, (cudaStream_t)stream, 0, -1);
+  if (rc == KX_ERR_UNSUPPORTED)
+    return fail(KX_ERR_UNSUPPORTED,
+                "row-march sharding needs a 2-D float32 kscan with 'same'-style borders whose functions read only "
+                "the row above");
+  return rc;
+}
+
+int kx_scan_rowmarch_rows_per_launch(void) { return scan_rowmarch_rows_per_launch(); }
+
+int kx_scan_rowmarch_shard_rows(const KxGeom* geom, const KxProgram* prog, int64_t col_base, int64_t global_nx,
+                                int32_t row_begin, int32_t row_end, void* out, void* stream) {
+  int rc = validate(geom, prog);
+  if (rc) return rc;
+  if (!out) return fail(KX_ERR_INVALID, "null device pointer");
+  if (geom->ndim != 2 || global_nx < 1 || row_begin < 0 || row_end > geom->in_shape[0] || row_begin > row_end)
+    return fail(KX_ERR_INVALID, "rows [%d, %d) of a %lld-row shard", row_begin, row_end,
+                (long long)(geom->ndim == 2 ? geom->in_shape[0] : 0));
+  rc = scan_rowmarch_shard(*geom, *prog, nullptr, out, 0, col_base, global_nx, (cudaStream_t)stream, row_begin, row_end);
   if (rc == KX_ERR_UNSUPPORTED)
     return fail(KX_ERR_UNSUPPORTED,
                 "row-march sharding needs a 2-D float32 kscan with 'same'-style borders whose functions read only "

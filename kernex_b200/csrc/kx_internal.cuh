@@ -128,6 +128,7 @@ int launch_scan_wavefront(const KxGeom& g, const KxProgram& prog, const void* in
 int try_scan_rowmarch(const KxGeom& g, const KxProgram& prog, const void* in, const void* coef_dev,
                       void* out, int reverse, cudaStream_t s);
 int scan_rowmarch_shard(const KxGeom& g, const KxProgram& prog, const void* coef_dev, void* out, int reverse,
-                        int64_t col_base, int64_t gnx, cudaStream_t s);
+                        int64_t col_base, int64_t gnx, cudaStream_t s, int row_begin, int row_end);
+int scan_rowmarch_rows_per_launch();
 
 }  // namespace kx

@@ -409,7 +409,7 @@ bool add_break(int* br, int& n, int64_t v, int nt) {
 // does not hold read as zero, so the first nt*RL (last nt*RR) local columns of a shard that does not
 // start (end) at the global edge are only valid if the caller overlaps shards by that much.
 int scan_rowmarch_shard(const KxGeom& g, const KxProgram& p, const void* coef_dev, void* out, int reverse,
-                        int64_t col_base, int64_t gnx, cudaStream_t s) {
+                        int64_t col_base, int64_t gnx, cudaStream_t s, int row_begin, int row_end) {
   if (g.ndim != 2 || g.in_dtype != KX_F32 || reverse || coef_dev) return KX_ERR_UNSUPPORTED;
   const int c0 = (g.ksize[0] - 1) / 2, c1 = (g.ksize[1] - 1) / 2;
   // every in-bounds cell is a window centre exactly once ('same'-style borders), stride 1
@@ -434,6 +434,8 @@ int scan_rowmarch_shard(const KxGeom& g, const KxProgram& p, const void* coef_de
     }
   }
   const int nt = (int)g.in_shape[0];
+  if (row_end < 0 || row_end > nt) row_end = nt;
+  if (row_begin < 0 || row_begin > row_end) return KX_ERR_UNSUPPORTED;
   a.n_breaks = 1;
   a.row_break[0] = 0;
   for (int k = 0; k < p.n_keys; ++k) {
@@ -479,9 +481,9 @@ int scan_rowmarch_shard(const KxGeom& g, const KxProgram& p, const void* coef_de
       a.own = fat_own;
       a.ntiles = (int)ntiles;
       const unsigned grid = ntiles <= 148 ? (unsigned)ntiles : 128u;
-      for (int n0 = 0; n0 < nt; n0 += kT) {
+      for (int n0 = row_begin; n0 < row_end; n0 += kT) {
         a.n0 = n0;
-        a.n1 = n0 + kT < nt ? n0 + kT : nt;
+        a.n1 = n0 + kT < row_end ? n0 + kT : row_end;
         int rc = launch_fat(a, rl, rr, grid, s);
         if (rc) return rc;
       }
@@ -500,9 +502,9 @@ int scan_rowmarch_shard(const KxGeom& g, const KxProgram& p, const void* coef_de
   a.own = own;
   const int64_t blocks = (nx + own - 1) / own;
   if (blocks > 0x7fffffff) return KX_ERR_UNSUPPORTED;
-  for (int n0 = 0; n0 < nt; n0 += kT) {
+  for (int n0 = row_begin; n0 < row_end; n0 += kT) {
     a.n0 = n0;
-    a.n1 = n0 + kT < nt ? n0 + kT : nt;
+    a.n1 = n0 + kT < row_end ? n0 + kT : row_end;
     int rc = (G == 1) ? launch_g<1>(a, rl, rr, (unsigned)blocks, s) : launch_g<2>(a, rl, rr, (unsigned)blocks, s);
     if (rc) return rc;
   }
@@ -512,7 +514,9 @@ int scan_rowmarch_shard(const KxGeom& g, const KxProgram& p, const void* coef_de
 int try_scan_rowmarch(const KxGeom& g, const KxProgram& p, const void* in, const void* coef_dev, void* out,
                       int reverse, cudaStream_t s) {
   (void)in;
-  return scan_rowmarch_shard(g, p, coef_dev, out, reverse, 0, g.ndim == 2 ? g.in_shape[1] : 0, s);
+  return scan_rowmarch_shard(g, p, coef_dev, out, reverse, 0, g.ndim == 2 ? g.in_shape[1] : 0, s, 0, -1);
 }
+
+int scan_rowmarch_rows_per_launch() { return kT; }
 
 }  // namespace kx

@@ -231,6 +231,20 @@ class SlabStencil:
 # --------------------------------------------------------------------------- #
 
 
+def column_exchange_plan(nx_global: int, world: int, rank: int, t_rows: int, rl: int, rr: int):
+    """Halo-EXCHANGE form: the shard holds its own columns plus ``t_rows*rl`` / ``t_rows*rr`` ghost columns
+    (one temporal block of the dependency cone), refreshed from the neighbours before every block.
+    Returns ``(col_base, width, keep_lo, keep_hi, ghost_l, ghost_r)`` in the style of
+    :func:`column_shard_plan`; ghost widths are rounded up to 4 columns (16-byte rows)."""
+    per = -(-nx_global // world)
+    per += (-per) % 4
+    c0, c1 = min(rank * per, nx_global), min((rank + 1) * per, nx_global)
+    gl = 0 if rank == 0 else -(-t_rows * rl // 4) * 4
+    gr = 0 if c1 >= nx_global else -(-t_rows * rr // 4) * 4
+    lo, hi = c0 - gl, min(nx_global, c1 + gr)
+    return lo, hi - lo, c0 - lo, c1 - lo, gl, hi - c1
+
+
 def column_shard_plan(nx_global: int, world: int, rank: int, nt: int, rl: int, rr: int):
     """Columns a rank must HOLD to produce its own share of a row-marching kscan without
     talking to its neighbours.
@@ -257,7 +271,8 @@ class ColumnShardedScan:
     time-marching meshes qualify (every function reads the row above): the same dependency
     analysis as the single-GPU fast path, enforced by ``kx_scan_rowmarch_shard``."""
 
-    def __init__(self, mesh, nt: int, nx_global: int, rank=None, world=None, device=None):
+    def __init__(self, mesh, nt: int, nx_global: int, rank=None, world=None, device=None, exchange=False,
+                 group=None):
         import ctypes as C
 
         from . import _lib
@@ -282,8 +297,16 @@ class ColumnShardedScan:
         c1 = (ksize[1] - 1) // 2
         offs = [t[1] - c1 for s in specs for t in s.taps]
         self.rl, self.rr = max([0] + [-o for o in offs]), max([0] + offs)
-        self.col_base, self.width, self.keep_lo, self.keep_hi = column_shard_plan(
-            nx_global, world, rank, nt, self.rl, self.rr)
+        self.exchange, self.group = bool(exchange) and world > 1, group
+        if self.exchange:
+            # north-star form: per temporal block, T*R ghost values per side travel by NCCL send/recv
+            self.t_rows = int(_lib.load().kx_scan_rowmarch_rows_per_launch())
+            (self.col_base, self.width, self.keep_lo, self.keep_hi, self.ghost_l, self.ghost_r) = \
+                column_exchange_plan(nx_global, world, rank, self.t_rows, self.rl, self.rr)
+        else:
+            # default: recompute the nt*R-column dependency cone, no communication at all
+            self.col_base, self.width, self.keep_lo, self.keep_hi = column_shard_plan(
+                nx_global, world, rank, nt, self.rl, self.rr)
         self._prog = _Program(specs, [tuple(v) for v in func_map.values()], 2)
         local = (nt, self.width)
         self._geom = _geom(local, local, ksize, strides, border, _lib.KX_F32, _lib.KX_F32)
@@ -297,6 +320,37 @@ class ColumnShardedScan:
         C, L = self._C, self._lib
         lib = L.load()
         stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        if self.exchange:
+            return self._run_exchange(lib, stream)
         L.check(lib.kx_scan_rowmarch_shard(C.byref(self._geom), C.byref(self._prog.c), C.c_int64(self.col_base),
                                            C.c_int64(self.nx_global), C.c_void_p(self.out.data_ptr()), stream))
+        return self.out[:, self.keep_lo:self.keep_hi]
+
+    def _run_exchange(self, lib, stream):
+        """T rows per block; before block b > 0 the ghost columns of row b*T-1 are received from the
+        neighbours (they own them) and my edge columns of that row are sent to them."""
+        C, L, T = self._C, self._lib, self.t_rows
+        for n0 in range(0, self.nt, T):
+            if n0 > 0:
+                row, ops = self.out[n0 - 1], []
+                if self.ghost_l:   # left neighbour owns my left ghost columns; it needs nothing from me unless rr > 0
+                    ops.append(dist.P2POp(dist.irecv, row[0:self.ghost_l], self.rank - 1, self.group))
+                if self.rank + 1 < self.world and self.rl:
+                    nxt = column_exchange_plan(self.nx_global, self.world, self.rank + 1, T, self.rl, self.rr)
+                    if nxt[4]:
+                        ops.append(dist.P2POp(dist.isend, row[self.keep_hi - nxt[4]:self.keep_hi], self.rank + 1,
+                                              self.group))
+                if self.ghost_r:
+                    ops.append(dist.P2POp(dist.irecv, row[self.keep_hi:self.keep_hi + self.ghost_r], self.rank + 1,
+                                          self.group))
+                if self.rank > 0 and self.rr:
+                    prv = column_exchange_plan(self.nx_global, self.world, self.rank - 1, T, self.rl, self.rr)
+                    if prv[5]:
+                        ops.append(dist.P2POp(dist.isend, row[self.keep_lo:self.keep_lo + prv[5]], self.rank - 1,
+                                              self.group))
+                for r in (dist.batch_isend_irecv(ops) if ops else []):
+                    r.wait()
+            L.check(lib.kx_scan_rowmarch_shard_rows(
+                C.byref(self._geom), C.byref(self._prog.c), C.c_int64(self.col_base), C.c_int64(self.nx_global),
+                C.c_int32(n0), C.c_int32(min(n0 + T, self.nt)), C.c_void_p(self.out.data_ptr()), stream))
         return self.out[:, self.keep_lo:self.keep_hi]

@@ -111,6 +111,37 @@ def main():
         if rank == 0:
             print(f"VJP {fn.__name__} {ksize} rows={rows} padding={padding}: {'ok' if flag.item() else 'MISMATCH'}",
                   flush=True)
+    # ---- kscan, axis-1 shards: halo-EXCHANGE form vs the single-GPU scan (bit-identical) ----
+    from kernex_b200.dist import ColumnShardedScan
+
+    def convection_mesh(nt, nx, kappa, two_sided):
+        F = kex.kscan(kernel_size=(3, 3), padding=((1, 1), (1, 1)), named_axis={0: "n", 1: "i"}, relative=True)
+        q1, q2 = int((nx - 1) / 4) + 1, int((nx - 1) / 2)
+        F[:, 0] = F[:, -1] = lambda u: 1
+        F[:, :q1] = F[:, q2:] = lambda u: 1
+        F[0:1, q1:q2] = lambda u: 2
+        if two_sided:   # diffusion-like update: reads both neighbours of the row above (RL = RR = 1)
+            F[1:, 1:-1] = lambda u: u["i", "n-1"] + 0.25 * (u["i-1", "n-1"] - 2 * u["i", "n-1"] + u["i+1", "n-1"])
+        else:
+            F[1:, 1:-1] = lambda u: u["i", "n-1"] - kappa * (u["i", "n-1"] - u["i-1", "n-1"])
+        return F
+
+    for (nt, nx, two_sided) in [(200, 8192, False), (130, 5000, False), (150, 8192, True)]:
+        whole = convection_mesh(nt, nx, 0.5, two_sided)(torch.ones((nt, nx), device=dev))
+        same = True
+        for exchange in (True, False):
+            sh = ColumnShardedScan(convection_mesh(nt, nx, 0.5, two_sided), nt, nx, rank=rank, world=world, device=dev,
+                                   exchange=exchange)
+            mine = sh.run()
+            torch.cuda.synchronize()
+            c0 = sh.col_base + sh.keep_lo
+            same = same and bool(torch.equal(mine, whole[:, c0:c0 + mine.shape[1]]))
+        flag = torch.tensor([1 if same else 0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        ok = ok and bool(flag.item())
+        if rank == 0:
+            print(f"kscan nt={nt} nx={nx} two_sided={two_sided} exchange + recompute: "
+                  f"{'bit-identical' if flag.item() else 'MISMATCH'}", flush=True)
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)
 
