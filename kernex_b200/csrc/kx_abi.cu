@@ -251,7 +251,7 @@ int kx_scan(const KxGeom* geom, const KxProgram* prog, const void* in, const voi
   rc = try_scan_rowmarch(*geom, *prog, in, coef_dev, out, reverse, s);
   if (rc != KX_ERR_UNSUPPORTED) return rc;
   if (!getenv("KX_SCAN_SEQUENTIAL")) {  // cross-check switch: the one-thread sweep of kx_generic.cu
-    rc = launch_scan_wavefront(*geom, *prog, in, coef_dev, out, reverse, s);
+    rc = launch_scan_wavefront(*geom, *prog, in, coef_dev, state, out, reverse, s);
     if (rc != KX_ERR_UNSUPPORTED) return rc;
   }
   return launch_generic_scan(*geom, *prog, in, coef_dev, state, out, reverse, s);

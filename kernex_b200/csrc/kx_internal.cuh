@@ -123,8 +123,8 @@ int try_pool2d(const MapArgs& a, const KxProgram& prog, cudaStream_t s);
 int64_t conv_wgrad_scratch_bytes(const KxGeom& g, const KxProgram& prog);
 int try_conv_wgrad(const KxGeom& g, const KxProgram& prog, const void* x, const void* gout, void* scratch,
                    void* dcoef, cudaStream_t s);
-int launch_scan_wavefront(const KxGeom& g, const KxProgram& prog, const void* in, const void* coef_dev, void* out,
-                          int reverse, cudaStream_t s);
+int launch_scan_wavefront(const KxGeom& g, const KxProgram& prog, const void* in, const void* coef_dev, void* state,
+                          void* out, int reverse, cudaStream_t s);
 int try_scan_rowmarch(const KxGeom& g, const KxProgram& prog, const void* in, const void* coef_dev,
                       void* out, int reverse, cudaStream_t s);
 int scan_rowmarch_shard(const KxGeom& g, const KxProgram& prog, const void* coef_dev, void* out, int reverse,

@@ -251,9 +251,179 @@ int launch_wave_x(const KxGeom& g, const KxProgram& prog, const void* in, const 
   return after_launch("scan_wavefront_kernel");
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Warp-skewed wavefront for 2-D (and 1-D) scans whose functions read cells of the row being
+// written (Gauss-Seidel sweeps, recurrences along a row, README RK4): 'same'-style borders (every
+// cell is a window centre), stride 1.  The hyperplane kernel above pays a block / grid barrier plus
+// an L2 round trip per anti-diagonal (~3.7 us per step); here
+//   * a WARP owns a band of 32 consecutive rows, lane r = row i0 + r, and lane r is `a0` columns
+//     behind lane r-1 (the hyperplane skew), so at step s it computes column s - a0*r: the warp IS the
+//     wavefront and the only synchronisation per step is __syncwarp;
+//   * new values of the band travel through a per-warp shared-memory history (the last 32 columns of
+//     each row), old values come from the input, so a step costs one window evaluation, not a
+//     round trip to L2;
+//   * bands are pipelined over warps / CTAs: band b starts as soon as the last row of band b-1 is
+//     ahead of it (lane 31 publishes its progress in global memory every 8 columns, lane 0 of the next
+//     band polls it; rows above the band are read from `out` with ld.global.cg).  Bands are handed
+//     out by an atomic ticket, so a resident warp only ever waits for bands that already started.
+// Total time ~ (nx + a0*ny) window evaluations of one warp instead of that many grid barriers.
+constexpr int kHistW = 32;
+
+struct WaveRowsArgs {
+  int32_t ni, nj, k0, k1, c0, c1;      // shape, window, centre offsets
+  int32_t a0;                           // column skew per row (hyperplane coefficient of axis 0)
+  int32_t r_above;                      // largest column offset read on earlier rows
+  int32_t reverse, nbands, two_d;
+  int32_t* ticket;                      // [1] next band, then [nbands] progress of each band's last row
+};
+
 template <typename TIN, typename TC>
-int launch_wave_t(const KxGeom& g, const KxProgram& prog, const void* in, const void* coef_dev, void* out,
-                  int reverse, cudaStream_t s) {
+__global__ void __launch_bounds__(128)
+scan_wavefront_rows_kernel(const __grid_constant__ WaveRowsArgs a, const __grid_constant__ DevProgram<TC> p,
+                           const TIN* __restrict__ in, TIN* out, const TC* __restrict__ coef_dev) {
+  __shared__ TIN hist[4][32][kHistW];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  volatile int32_t* progress = a.ticket + 1;
+  const int sgn = a.reverse ? -1 : 1;
+  for (;;) {
+    int band = 0;
+    if (lane == 0) band = atomicAdd(a.ticket, 1);
+    band = __shfl_sync(0xffffffffu, band, 0);
+    if (band >= a.nbands) break;
+    const int il = band * 32 + lane;                   // logical (sweep-order) row of this lane
+    const bool row_ok = il < a.ni;
+    const int ia = a.reverse ? a.ni - 1 - il : il;     // actual row
+    int avail = band == 0 ? a.nj : 0;                  // completed columns of the previous band's last row
+    const int nsteps = a.nj + 31 * a.a0;
+    for (int s = 0; s < nsteps; ++s) {
+      if (band > 0) {
+        const int need = min(s + a.r_above + 1, a.nj);
+        if (need > avail) {                            // warp-uniform
+          if (lane == 0) {
+            int v = progress[band - 1];
+            while (v < need) v = progress[band - 1];
+            __threadfence();
+            avail = v;
+          }
+          avail = __shfl_sync(0xffffffffu, avail, 0);
+        }
+      }
+      const int jl = s - a.a0 * lane;                  // logical column
+      if (row_ok && jl >= 0 && jl < a.nj) {
+        const int ja = a.reverse ? a.nj - 1 - jl : jl;
+        int64_t centre[KX_MAX_DIMS] = {0, 0, 0, 0};
+        if (a.two_d) {
+          centre[0] = ia;
+          centre[1] = ja;
+        } else {
+          centre[0] = ja;
+        }
+        const int f = select_func(p, centre);
+        const int kind = p.func[f].kind;
+        const int t0 = p.func[f].tap_begin, t1 = p.func[f].tap_end;
+        TC acc = (kind == KX_AFFINE) ? p.func[f].bias : TC(0);
+        for (int t = t0; t < t1; ++t) {
+          const int di = a.two_d ? (int)p.tap_off[t][0] - a.c0 : 0;
+          const int dj = (int)p.tap_off[t][a.two_d ? 1 : 0] - a.c1;
+          const int ci = ia + di, cj = ja + dj;        // actual cell
+          const int ldi = sgn * di, ldj = sgn * dj;    // offset in sweep order
+          const bool inside = ci >= 0 && ci < a.ni && cj >= 0 && cj < a.nj;
+          TC v = TC(0);
+          if (inside) {
+            if (ldi < 0 || (ldi == 0 && ldj < 0)) {    // written earlier in the sweep: the new value
+              const int r2 = lane + ldi;
+              if (r2 >= 0) v = (TC)hist[warp][r2][(jl + ldj) & (kHistW - 1)];
+              else v = (TC)__ldcg(out + (int64_t)ci * a.nj + cj);
+            } else {                                   // not written yet (or the centre): the input
+              v = (TC)in[(int64_t)ci * a.nj + cj];
+            }
+          }
+          if (kind == KX_AFFINE) {
+            const TC c = coef_dev ? coef_dev[t] : p.coef[t];
+            acc = mad_wrap(c, v, acc);
+          } else if (kind == KX_REDUCE_MAX) {
+            acc = (t == t0) ? v : (v > acc ? v : acc);
+          } else if (kind == KX_REDUCE_MIN) {
+            acc = (t == t0) ? v : (v < acc ? v : acc);
+          } else {
+            acc = v;
+          }
+        }
+        if (kind == KX_AFFINE && p.func[f].post_div != 0.f) acc = (TC)((float)acc / p.func[f].post_div);
+        const TIN stored = (TIN)acc;                   // cast to the carried dtype on write (scan.py:50)
+        hist[warp][lane][jl & (kHistW - 1)] = stored;
+        out[(int64_t)ia * a.nj + ja] = stored;
+      }
+      const int j31 = s - 31 * a.a0;                   // column just completed by the band's last row
+      const bool pub = j31 >= 0 && (((j31 & 7) == 7) || j31 == a.nj - 1);
+      if (pub) __threadfence();
+      __syncwarp();
+      if (pub && lane == 31) progress[band] = j31 + 1;
+    }
+  }
+}
+
+template <typename TIN, typename TC>
+int try_wave_rows(const KxGeom& g, const KxProgram& prog, const WaveArgs& plan, const void* in, const void* coef_dev,
+                  void* state, void* out, int reverse, cudaStream_t s) {
+  if (getenv("KX_SCAN_NO_ROWS")) return KX_ERR_UNSUPPORTED;   // A/B switch: hyperplane kernel only
+  if (g.ndim < 1 || g.ndim > 2 || !state) return KX_ERR_UNSUPPORTED;
+  const int two_d = g.ndim == 2;
+  for (int d = 0; d < g.ndim; ++d)
+    if (g.stride[d] != 1 || g.lo[d] != (g.ksize[d] - 1) / 2 || g.out_shape[d] != g.in_shape[d]) return KX_ERR_UNSUPPORTED;
+  const int dj_axis = g.ndim - 1;
+  if (plan.a[dj_axis] != 1) return KX_ERR_UNSUPPORTED;        // no in-row dependency: rows are parallel
+  const int64_t ni = two_d ? g.in_shape[0] : 1, nj = g.in_shape[dj_axis];
+  if (ni * nj >= 0x40000000 || nj < 1) return KX_ERR_UNSUPPORTED;
+  static thread_local WaveRowsArgs a;
+  memset(&a, 0, sizeof(a));
+  a.ni = (int)ni;
+  a.nj = (int)nj;
+  a.two_d = two_d;
+  a.k0 = two_d ? g.ksize[0] : 1;
+  a.k1 = g.ksize[dj_axis];
+  a.c0 = (a.k0 - 1) / 2;
+  a.c1 = (a.k1 - 1) / 2;
+  a.a0 = two_d ? plan.a[0] : 0;
+  a.reverse = reverse;
+  a.nbands = (int)((ni + 31) / 32);
+  int max_up = 0, max_back = 0, r_above = 0;
+  const int sgn = reverse ? -1 : 1;
+  for (int f = 0; f < prog.n_funcs; ++f)
+    for (int t = prog.func[f].tap_begin; t < prog.func[f].tap_end; ++t) {
+      const int ldi = sgn * (two_d ? prog.tap_off[t][0] - a.c0 : 0), ldj = sgn * (prog.tap_off[t][dj_axis] - a.c1);
+      if (ldi < 0) {
+        if (-ldi > max_up) max_up = -ldi;
+        if (ldj > r_above) r_above = ldj;
+      }
+      if ((ldi < 0 || (ldi == 0 && ldj < 0)) && -ldj > max_back) max_back = -ldj;
+    }
+  if (a.a0 * max_up + max_back + 1 >= kHistW || max_up > 31) return KX_ERR_UNSUPPORTED;
+  a.r_above = r_above;
+  a.ticket = (int32_t*)state;
+  if ((int64_t)(a.nbands + 1) * 4 > scan_state_elems(g) * 4) return KX_ERR_UNSUPPORTED;
+  KX_CUDA_CHECK(cudaMemsetAsync(state, 0, (size_t)(a.nbands + 1) * 4, s));
+  static thread_local DevProgram<TC> dp;
+  make_dev_program<TC>(prog, g.ndim, dp);
+  int64_t blocks = (a.nbands + 3) / 4;
+  const int64_t cap = (int64_t)sm_count() * 8;
+  if (blocks > cap) blocks = cap;                              // persistent: warps keep taking tickets
+  scan_wavefront_rows_kernel<TIN, TC><<<(unsigned)blocks, 128, 0, s>>>(a, dp, (const TIN*)in, (TIN*)out,
+                                                                      (const TC*)coef_dev);
+  return after_launch("scan_wavefront_rows_kernel");
+}
+
+template <typename TIN, typename TC>
+int launch_wave_t(const KxGeom& g, const KxProgram& prog, const void* in, const void* coef_dev, void* state,
+                  void* out, int reverse, cudaStream_t s) {
+  if (prod(g.out_shape, g.ndim) > 0) {
+    static thread_local WaveArgs plan;
+    if (plan_wavefront(g, prog, reverse, plan)) {
+      const int rc = try_wave_rows<TIN, TC>(g, prog, plan, in, coef_dev, state, out, reverse, s);
+      if (rc != KX_ERR_UNSUPPORTED) return rc;
+    }
+  }
   bool small = prod(g.out_shape, g.ndim) < 0x40000000 && prod(g.in_shape, g.ndim) < 0x40000000, unit = true;
   for (int d = 0; d < g.ndim; ++d) {
     if (g.stride[d] != 1) unit = false;
@@ -266,14 +436,14 @@ int launch_wave_t(const KxGeom& g, const KxProgram& prog, const void* in, const 
 
 }  // namespace
 
-int launch_scan_wavefront(const KxGeom& g, const KxProgram& prog, const void* in, const void* coef_dev, void* out,
-                          int reverse, cudaStream_t s) {
+int launch_scan_wavefront(const KxGeom& g, const KxProgram& prog, const void* in, const void* coef_dev, void* state,
+                          void* out, int reverse, cudaStream_t s) {
   bool fl = false;  // coef_dev carries the compute type
   for (int f = 0; f < prog.n_funcs; ++f)
     if (prog.func[f].kind == KX_AFFINE && !prog.func[f].coef_is_int) fl = true;
-  if (g.in_dtype == KX_F32) return launch_wave_t<float, float>(g, prog, in, coef_dev, out, reverse, s);
-  if (g.in_dtype == KX_I32 && !fl) return launch_wave_t<int32_t, int32_t>(g, prog, in, coef_dev, out, reverse, s);
-  if (g.in_dtype == KX_I32) return launch_wave_t<int32_t, float>(g, prog, in, coef_dev, out, reverse, s);
+  if (g.in_dtype == KX_F32) return launch_wave_t<float, float>(g, prog, in, coef_dev, state, out, reverse, s);
+  if (g.in_dtype == KX_I32 && !fl) return launch_wave_t<int32_t, int32_t>(g, prog, in, coef_dev, state, out, reverse, s);
+  if (g.in_dtype == KX_I32) return launch_wave_t<int32_t, float>(g, prog, in, coef_dev, state, out, reverse, s);
   return KX_ERR_UNSUPPORTED;
 }
 

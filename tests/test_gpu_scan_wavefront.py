@@ -28,6 +28,9 @@ def _last_kernel():
     return _lib.last_kernel()
 
 
+WAVE = ("scan_wavefront_kernel", "scan_wavefront_rows_kernel")
+
+
 def _tap_fn(taps, coefs, bias, integer):
     def fn(x):
         acc = int(bias) if integer else float(bias)
@@ -67,7 +70,7 @@ def test_random_scans_match_literal_oracle(kex, seed):
     kw = {"reverse": True} if reverse else None
     want = ko.kernel_scan({fn: ()}, shape, ksize, strides, border, False, "scan", kw)(x)
     got = kex.kernel_scan({fn: ()}, shape, ksize, strides, border, False, "scan", kw)(x)
-    assert _last_kernel() in ("scan_wavefront_kernel", "scan_rowmarch_kernel")
+    assert _last_kernel() in WAVE + ("scan_rowmarch_kernel",)
     assert got.shape == want.shape and got.dtype == want.dtype
     if integer:
         np.testing.assert_array_equal(got, want)
@@ -90,7 +93,7 @@ def test_random_multi_function_scans(kex, seed, relative):
     x = rng.integers(-4, 5, shape).astype(np.int32)
     want = ko.kernel_scan(keys, shape, ksize, (1, 1), border, relative)(x)
     got = kex.kernel_scan(keys, shape, ksize, (1, 1), border, relative)(x)
-    assert _last_kernel() == "scan_wavefront_kernel"
+    assert _last_kernel() in WAVE
     np.testing.assert_array_equal(got, want)
 
 
@@ -102,7 +105,7 @@ def test_gauss_seidel_sweep(kex):
     fn = lambda u: 0.25 * (u[0, -1] + u[-1, 0] + u[0, 1] + u[1, 0])
     F = kex.kscan(kernel_size=(3, 3), padding="same", relative=True)(fn)
     got = F(x)
-    assert _last_kernel() == "scan_wavefront_kernel"
+    assert _last_kernel() == "scan_wavefront_rows_kernel"     # in-row dependency, 'same' borders: warp-skewed kernel
     want = ko.kernel_scan({fn: ()}, x.shape, (3, 3), (1, 1), ((1, 1), (1, 1)), True)(x)
     np.testing.assert_allclose(got, want, rtol=1e-5, atol=1e-6)
     # independent statement of the same sweep
@@ -154,8 +157,41 @@ def test_wavefront_equals_one_thread_sweep(kex, monkeypatch, shape, fn_taps, rev
     kw = {"reverse": True} if reverse else None
     op = kex.kernel_scan({fn: ()}, shape, ksize, (1,) * len(shape), ((1, 1),) * len(shape), False, "scan", kw)
     got = op(x)
+    assert _last_kernel() in WAVE
+    monkeypatch.setenv("KX_SCAN_NO_ROWS", "1")                # hyperplane kernel only
+    got2 = op(x)
     assert _last_kernel() == "scan_wavefront_kernel"
     monkeypatch.setenv("KX_SCAN_SEQUENTIAL", "1")
     want = op(x)
-    assert _last_kernel() != "scan_wavefront_kernel"
+    assert _last_kernel() not in WAVE
+    assert torch.equal(got, want) and torch.equal(got2, want)
+
+
+@pytest.mark.parametrize("case", range(8))
+def test_warp_skewed_kernel_geometries(kex, monkeypatch, case):
+    """scan_wavefront_rows_kernel: several 32-row bands (inter-warp hand-off through global progress
+    flags), reverse sweeps, 5x5 windows (skew 3, two rows up), 1-D recurrences, multi-function meshes;
+    bit-identical to the one-thread sweep."""
+    rng = np.random.default_rng(9900 + case)
+    shape, ksize = [((200, 150), (3, 3)), ((70, 300), (3, 3)), ((97, 64), (5, 5)), ((1000,), (3,)),
+                    ((33, 40), (3, 5)), ((260, 90), (3, 3)), ((64, 64), (5, 3)), ((5000,), (5,))][case]
+    nd = len(shape)
+    reverse = case in (1, 5, 7)
+    all_taps = list(itertools.product(*[range(k) for k in ksize]))
+    taps = [all_taps[i] for i in rng.choice(len(all_taps), min(6, len(all_taps)), replace=False)]
+    integer = case % 2 == 0
+    if integer:
+        fns = [_tap_fn(taps, rng.integers(-2, 3, len(taps)), 1, True), _tap_fn(taps[:2], [1, -1], 0, True)]
+        x = torch.from_numpy(rng.integers(-3, 4, shape).astype(np.int32)).cuda()
+    else:
+        fns = [_tap_fn(taps, rng.uniform(-0.15, 0.15, len(taps)), 0.5, False), _tap_fn(taps[:2], [0.5, -0.25], 0.0, False)]
+        x = torch.from_numpy(rng.standard_normal(shape).astype(np.float32)).cuda()
+    border = tuple(((k - 1) // 2, k // 2) for k in ksize)
+    keys = {fns[0]: [[]], fns[1]: [[(3, shape[0] - 2, 1)] + ([(0, shape[1], 2)] if nd == 2 else [])]}
+    kw = {"reverse": True} if reverse else None
+    op = kex.kernel_scan(keys, shape, ksize, (1,) * nd, border, False, "scan", kw)
+    got = op(x)
+    monkeypatch.setenv("KX_SCAN_SEQUENTIAL", "1")
+    want = op(x)
+    monkeypatch.delenv("KX_SCAN_SEQUENTIAL")
     assert torch.equal(got, want)
