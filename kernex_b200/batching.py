@@ -91,22 +91,38 @@ def vmap(fn, in_axes=0):
             raise UnsupportedStencilError("vmap over extra arguments needs an affine function of device weights")
         comp = _KX2TORCH[out_kx]
         n, B = prog.c.n_taps, shape[0]
-        coef = torch.tensor([prog.c.coef[i] for i in range(n)], dtype=comp, device=dev).repeat(B, 1)
         by_arg: dict = {}
         for slot, c in prog.device_refs:
             for (ai, flat), scale in c.w.items():
                 by_arg.setdefault(ai, []).append((slot, flat, scale))
-        for ai, refs in by_arg.items():
-            w = full_args[ai].to(device=dev, dtype=comp)
-            slots = torch.tensor([r[0] for r in refs], dtype=torch.long, device=dev)
-            flats = torch.tensor([r[1] for r in refs], dtype=torch.long, device=dev)
-            scales = torch.tensor([r[2] for r in refs], dtype=comp, device=dev)
-            if axes[1 + ai] == 0:
-                contrib = w.reshape(B, -1)[:, flats] * scales
-            else:
-                contrib = (w.reshape(-1)[flats] * scales).expand(B, -1)
-            coef = coef.index_add(1, slots, contrib)
-        coef = coef.contiguous()
+        base = [prog.c.coef[i] for i in range(n)]
+        identity = None
+        if len(by_arg) == 1 and all(v == 0.0 for v in base):
+            (ai, refs), = by_arg.items()
+            if axes[1 + ai] == 0 and [r[0] for r in refs] == list(range(n)) and [r[1] for r in refs] == list(range(n)) \
+                    and all(r[2] == 1 for r in refs) and full_args[ai][0].numel() == n:
+                identity = ai
+        if identity is not None:
+            # the usual `sum(x * w)`: the per-item weight tensor IS the coefficient row, zero extra launches
+            coef = full_args[identity].to(device=dev, dtype=comp).reshape(B, n).contiguous()
+        else:
+            cache = prog.__dict__.setdefault("_vmap_coef_cache", {})
+            ck = (str(dev), comp, B)
+            if ck not in cache:   # index / scale tensors are uploaded once per (plan, device, batch)
+                cache[ck] = (torch.tensor(base, dtype=comp, device=dev).repeat(B, 1),
+                             {ai: (torch.tensor([r[0] for r in refs], dtype=torch.long, device=dev),
+                                   torch.tensor([r[1] for r in refs], dtype=torch.long, device=dev),
+                                   torch.tensor([r[2] for r in refs], dtype=comp, device=dev))
+                              for ai, refs in by_arg.items()})
+            coef, plans = cache[ck]
+            for ai, (slots, flats, scales) in plans.items():
+                w = full_args[ai].to(device=dev, dtype=comp)
+                if axes[1 + ai] == 0:
+                    contrib = w.reshape(B, -1)[:, flats] * scales
+                else:
+                    contrib = (w.reshape(-1)[flats] * scales).expand(B, -1)
+                coef = coef.index_add(1, slots, contrib)
+            coef = coef.contiguous()
         out = torch.empty((B,) + tuple(full_shape), dtype=comp, device=dev)
         if out.numel():
             lib = _lib.load()

@@ -264,7 +264,7 @@ int launch_wave_x(const KxGeom& g, const KxProgram& prog, const void* in, const 
 //     each row), old values come from the input, so a step costs one window evaluation, not a
 //     round trip to L2;
 //   * bands are pipelined over warps / CTAs: band b starts as soon as the last row of band b-1 is
-//     ahead of it (lane 31 publishes its progress in global memory every 8 columns, lane 0 of the next
+//     ahead of it (lane 31 publishes its progress in global memory every 16 columns, lane 0 of the next
 //     band polls it; rows above the band are read from `out` with ld.global.cg).  Bands are handed
 //     out by an atomic ticket, so a resident warp only ever waits for bands that already started.
 // Total time ~ (nx + a0*ny) window evaluations of one warp instead of that many grid barriers.
@@ -275,6 +275,7 @@ struct WaveRowsArgs {
   int32_t a0;                           // column skew per row (hyperplane coefficient of axis 0)
   int32_t r_above;                      // largest column offset read on earlier rows
   int32_t reverse, nbands, two_d;
+  int32_t pub_mask;                     // progress is published every pub_mask + 1 columns
   int32_t* ticket;                      // [1] next band, then [nbands] progress of each band's last row
 };
 
@@ -356,10 +357,12 @@ scan_wavefront_rows_kernel(const __grid_constant__ WaveRowsArgs a, const __grid_
         out[(int64_t)ia * a.nj + ja] = stored;
       }
       const int j31 = s - 31 * a.a0;                   // column just completed by the band's last row
-      const bool pub = j31 >= 0 && (((j31 & 7) == 7) || j31 == a.nj - 1);
-      if (pub) __threadfence();
+      const bool pub = j31 >= 0 && (((j31 & a.pub_mask) == a.pub_mask) || j31 == a.nj - 1);
       __syncwarp();
-      if (pub && lane == 31) progress[band] = j31 + 1;
+      if (pub && lane == 31) {   // the fence is cumulative over the warp's writes ordered by the barrier above
+        __threadfence();
+        progress[band] = j31 + 1;
+      }
     }
   }
 }
@@ -401,6 +404,8 @@ int try_wave_rows(const KxGeom& g, const KxProgram& prog, const WaveArgs& plan, 
     }
   if (a.a0 * max_up + max_back + 1 >= kHistW || max_up > 31) return KX_ERR_UNSUPPORTED;
   a.r_above = r_above;
+  a.pub_mask = 15;
+  if (const char* e = getenv("KX_WAVE_PUB")) a.pub_mask = atoi(e) > 0 ? atoi(e) - 1 : 15;   // tuning knob (power of two)
   a.ticket = (int32_t*)state;
   if ((int64_t)(a.nbands + 1) * 4 > scan_state_elems(g) * 4) return KX_ERR_UNSUPPORTED;
   KX_CUDA_CHECK(cudaMemsetAsync(state, 0, (size_t)(a.nbands + 1) * 4, s));

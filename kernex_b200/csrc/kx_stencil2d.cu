@@ -242,6 +242,7 @@ int run(const MapArgs& m, const KxProgram& p, int ay, int ax, int64_t batch, cud
     a.bx1 = (int)m.box_hi[ax];
   }
   a.th = a.hout >= 512 ? 32 : (a.hout >= 64 ? 16 : 8);
+  if (const char* e = getenv("KX_S2_TH")) a.th = atoi(e) > 0 ? atoi(e) : a.th;   // tuning knob
   while ((a.hout + a.th - 1) / a.th > 65535) a.th *= 2;
   const bool dev = m.coef_dev != nullptr;
   T dense[kMaxK * kMaxK];
