@@ -111,7 +111,12 @@ class _Arr:
 
 
 def _stream_ptr(device):
-    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+    # raw handle of torch's current stream (torch.cuda.current_stream() costs ~7 us of Python per call)
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    try:
+        return C.c_void_p(torch._C._cuda_getCurrentRawStream(idx))
+    except AttributeError:  # pragma: no cover
+        return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
 def _ptr(t):

@@ -98,12 +98,18 @@ class KernelInterface:
         return op(array, *a, **k)
 
     def _wrap_decorator(self, func):
+        ops: dict = {}   # shape -> engine closure: argument resolution and validation happen once per shape
+
         def call(array, *args, **kwargs):
             shape = tuple(array.shape)
-            ksize, strides, border = self._resolved(shape)
-            resolved = {self._named(func, ksize): ()}
-            op = self._engine()(resolved, shape, ksize, strides, border, self.relative,
-                                self.transform_kind, self.transform_kwargs)
+            op = ops.get(shape)
+            if op is None:
+                ksize, strides, border = self._resolved(shape)
+                resolved = {self._named(func, ksize): ()}
+                op = self._engine()(resolved, shape, ksize, strides, border, self.relative,
+                                    self.transform_kind, self.transform_kwargs)
+                if len(ops) < 64:
+                    ops[shape] = op
             return op(array, *args, **kwargs)
 
         call._kx_interface, call._kx_func = self, func  # lets batching.vmap fold a batch axis into the launch
