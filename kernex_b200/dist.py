@@ -24,7 +24,8 @@ from dataclasses import dataclass
 import torch
 import torch.distributed as dist
 
-__all__ = ["SlabLayout", "exchange_halos", "SlabStencil"]
+__all__ = ["SlabLayout", "exchange_halos", "exchange_halo_grads", "SlabStencil", "ColumnShardedScan",
+           "column_shard_plan", "column_exchange_plan"]
 
 
 @dataclass(frozen=True)
@@ -106,6 +107,33 @@ def exchange_halos(ext: torch.Tensor, layout: SlabLayout, group=None):
         ops.append(dist.P2POp(dist.isend, ext[ht + R - layout.send_down:ht + R], r + 1, group))
     ops = [op for op in ops if op.tensor.numel() > 0]
     return dist.batch_isend_irecv(ops) if ops else []
+
+
+def exchange_halo_grads(dext: torch.Tensor, layout: SlabLayout, group=None):
+    """Adjoint of :func:`exchange_halos`: the cotangent rows that landed in my halos belong to the
+    neighbours' edge rows (they were copies of them), so they are sent back and ADDED there; I receive
+    and add the rows my neighbours accumulated for my edge rows.  In place on ``dext``; blocks until
+    the traffic is done.  ``<exchange_halos(x), y> == <x, exchange_halo_grads(y)>`` over the ranks."""
+    L, r = layout, layout.rank
+    ht, hb, R = L.halo_top, L.halo_bot, L.rows
+    ops, adds = [], []
+    if not L.first:
+        buf = torch.empty_like(dext[ht:ht + L.send_up])
+        ops.append(dist.P2POp(dist.irecv, buf, r - 1, group))
+        ops.append(dist.P2POp(dist.isend, dext[0:ht].contiguous(), r - 1, group))
+        adds.append((slice(ht, ht + L.send_up), buf))
+    if not L.last:
+        buf = torch.empty_like(dext[ht + R - L.send_down:ht + R])
+        ops.append(dist.P2POp(dist.irecv, buf, r + 1, group))
+        ops.append(dist.P2POp(dist.isend, dext[ht + R:ht + R + hb].contiguous(), r + 1, group))
+        adds.append((slice(ht + R - L.send_down, ht + R), buf))
+    ops = [op for op in ops if op.tensor.numel() > 0]
+    for req in (dist.batch_isend_irecv(ops) if ops else []):
+        req.wait()
+    for sl, buf in adds:
+        if buf.numel():
+            dext[sl] += buf
+    return dext
 
 
 class SlabStencil:
@@ -195,24 +223,7 @@ class SlabStencil:
                     continue
                 dext[p.in0:p.in1] += pm.vjp_input(gp)             # O(halo)-row strips
             if self.world > 1:
-                ht, hb, R = L.halo_top, L.halo_bot, L.rows
-                ops, adds = [], []
-                if not L.first:
-                    buf = torch.empty_like(dext[ht:ht + L.send_up])
-                    ops.append(dist.P2POp(dist.irecv, buf, self.rank - 1, self.group))
-                    ops.append(dist.P2POp(dist.isend, dext[0:ht].contiguous(), self.rank - 1, self.group))
-                    adds.append((slice(ht, ht + L.send_up), buf))
-                if not L.last:
-                    buf = torch.empty_like(dext[ht + R - L.send_down:ht + R])
-                    ops.append(dist.P2POp(dist.irecv, buf, self.rank + 1, self.group))
-                    ops.append(dist.P2POp(dist.isend, dext[ht + R:ht + R + hb].contiguous(), self.rank + 1, self.group))
-                    adds.append((slice(ht + R - L.send_down, ht + R), buf))
-                ops = [op for op in ops if op.tensor.numel() > 0]
-                for r in (dist.batch_isend_irecv(ops) if ops else []):
-                    r.wait()
-                for sl, buf in adds:
-                    if buf.numel():
-                        dext[sl] += buf
+                exchange_halo_grads(dext, L, self.group)
             dx_own = dext[L.own]
         if want_coef:
             for p, pm in self.maps:
