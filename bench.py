@@ -260,8 +260,8 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     numa_cpus = bind_to_gpu_numa_node(local) if world > 1 else None
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"   # keep NCCL's version banner off stdout: ONE JSON line only
+        # keep NCCL's version banner / logs off stdout: rank 0 prints ONE JSON line there
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     _lib.load()  # no extension -> fail loudly, there is no fallback
 

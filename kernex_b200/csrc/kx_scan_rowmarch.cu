@@ -110,8 +110,39 @@ scan_rowmarch_kernel(const __grid_constant__ RMArgs a) {
   while (iv + 1 < a.n_breaks && a.row_break[iv + 1] <= a.n0) ++iv;
   int next_break = a.n0;   // force a coefficient refresh at the first row
 
-  for (int n = a.n0; n < a.n1; ++n) {
-    if (n == next_break) {
+  // loop invariants the compiler otherwise re-derives every row (ncu/SASS of the first version: three
+  // S2R, ~10 instructions of 64-bit address arithmetic and 5 local-memory loads of spilled
+  // coefficients per row in an issue-bound loop)
+  int lane = tid & 31;
+  const int wrp = tid >> 5;
+  asm volatile("" : "+r"(lane));   // pin it: the compiler otherwise re-reads SR_TID.X every row
+  int store_mode[G];        // 2 = aligned 128-bit store, 1 = element-wise (ragged right edge), 0 = halo column: no store
+  float* optr[G];           // &out[n][c0] of the row being written
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+    const int64_t c0 = span0 + (int64_t)g * kRMThreads * 4 + tid * 4;
+    store_mode[g] = (c0 >= own0 && c0 < own1) ? ((c0 + 3 < own1 && ((a.nx & 3) == 0)) ? 2 : 1) : 0;
+    optr[g] = a.out + (int64_t)a.n0 * a.nx + c0;
+  }
+  unsigned e_wr[G], e_rl[G], e_wl[G], e_rr[G];   // shared-memory byte addresses of this lane's edge slots (parity 0)
+  {
+    const unsigned e0 = (unsigned)__cvta_generic_to_shared(&edge[0][0]);
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      const int slot = 1 + g * (kRMThreads / 32) + wrp;      // slot 0 and the last slot stay zero
+      e_wr[g] = e0 + (unsigned)(2 * slot) * 4;               // my right edge -> read by the warp on my right
+      e_rl[g] = e0 + (unsigned)(2 * (slot - 1)) * 4;         // right edge of the warp on my left
+      e_wl[g] = e0 + (unsigned)(kEdge + 2 * slot) * 4;
+      e_rr[g] = e0 + (unsigned)(kEdge + 2 * (slot + 1)) * 4;
+      asm volatile("" : "+r"(e_wr[g]), "+r"(e_rl[g]), "+r"(e_wl[g]), "+r"(e_rr[g]));   // keep them in registers
+    }
+  }
+  constexpr unsigned kParityBytes = (unsigned)(2 * kEdge * 4);
+  unsigned par = (a.n0 & 1) ? kParityBytes : 0u;
+
+  int n = a.n0;
+  while (n < a.n1) {
+    {   // row n starts a new interval of the region keys: refresh the per-column coefficients
       while (iv + 1 < a.n_breaks && a.row_break[iv + 1] <= n) ++iv;
       next_break = (iv + 1 < a.n_breaks) ? a.row_break[iv + 1] : 0x7fffffff;
 #pragma unroll
@@ -119,59 +150,58 @@ scan_rowmarch_kernel(const __grid_constant__ RMArgs a) {
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const int64_t c = span0 + (int64_t)g * kRMThreads * 4 + tid * 4 + e;
-          RMFunc f;
           const int64_t gc = a.col_base + c;
-          if (c < 0 || c >= a.nx || gc < 0 || gc >= a.gnx) {   // pad (or not-held) column: reads as zero
-            f.bias = 0.f;
-#pragma unroll
-            for (int d = 0; d < 2 * kMaxR + 1; ++d) f.a[d] = 0.f;
-          } else {
-            f = a.func[rm_select(a, n, gc)];
-          }
-          cb[g][e] = f.bias;
-          cl2[g][e] = f.a[0]; cl1[g][e] = f.a[1]; cc[g][e] = f.a[2]; cr1[g][e] = f.a[3]; cr2[g][e] = f.a[4];
+          const bool held = !(c < 0 || c >= a.nx || gc < 0 || gc >= a.gnx);   // else: pad / not-held column, reads as zero
+          const RMFunc& f = a.func[held ? rm_select(a, n, gc) : 0];           // read straight from the parameter bank
+          cb[g][e] = held ? f.bias : 0.f;
+          cl2[g][e] = held ? f.a[0] : 0.f;
+          cl1[g][e] = held ? f.a[1] : 0.f;
+          cc[g][e] = held ? f.a[2] : 0.f;
+          cr1[g][e] = held ? f.a[3] : 0.f;
+          cr2[g][e] = held ? f.a[4] : 0.f;
         }
       }
     }
+    const int stop = min(next_break, a.n1);
+#pragma unroll 2
+    for (; n < stop; ++n) {   // branch-free steady state between two breakpoints
     // neighbours across thread boundaries: warp shuffles inside a warp; only the two edge
     // lanes of every warp go through shared memory (one barrier per row, double buffered)
-    float* eb = edge[n & 1];
-    const int lane = tid & 31, wrp = tid >> 5;
 #pragma unroll
     for (int g = 0; g < G; ++g) {
-      const int slot = 1 + g * (kRMThreads / 32) + wrp;      // slot 0 and the last slot stay zero
-      if (RL >= 1 && lane == 31) {
-        eb[2 * slot] = cur[g][3];
-        if (RL >= 2) eb[2 * slot + 1] = cur[g][2];
+      const bool lane_first = lane == 0, lane_last = lane == 31;
+      if (RL >= 1 && lane_last) {
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(e_wr[g] + par), "f"(cur[g][3]) : "memory");
+        if (RL >= 2) asm volatile("st.shared.f32 [%0+4], %1;" ::"r"(e_wr[g] + par), "f"(cur[g][2]) : "memory");
       }
-      if (RR >= 1 && lane == 0) {
-        eb[kEdge + 2 * slot] = cur[g][0];
-        if (RR >= 2) eb[kEdge + 2 * slot + 1] = cur[g][1];
+      if (RR >= 1 && lane_first) {
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(e_wl[g] + par), "f"(cur[g][0]) : "memory");
+        if (RR >= 2) asm volatile("st.shared.f32 [%0+4], %1;" ::"r"(e_wl[g] + par), "f"(cur[g][1]) : "memory");
       }
     }
     __syncthreads();
     float nxt[G][4];
 #pragma unroll
     for (int g = 0; g < G; ++g) {
-      const int slot = 1 + g * (kRMThreads / 32) + wrp;
+      const bool lane_first = lane == 0, lane_last = lane == 31;
       float w[4 + 2 * kMaxR];  // prev[base-2 .. base+5]
       w[2] = cur[g][0]; w[3] = cur[g][1]; w[4] = cur[g][2]; w[5] = cur[g][3];
       w[0] = w[1] = w[6] = w[7] = 0.f;
       if (RL >= 1) {
         w[1] = __shfl_up_sync(0xffffffffu, cur[g][3], 1);
-        if (lane == 0) w[1] = eb[2 * (slot - 1)];
+        if (lane_first) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(w[1]) : "r"(e_rl[g] + par) : "memory");
       }
       if (RL >= 2) {
         w[0] = __shfl_up_sync(0xffffffffu, cur[g][2], 1);
-        if (lane == 0) w[0] = eb[2 * (slot - 1) + 1];
+        if (lane_first) asm volatile("ld.shared.f32 %0, [%1+4];" : "=f"(w[0]) : "r"(e_rl[g] + par) : "memory");
       }
       if (RR >= 1) {
         w[6] = __shfl_down_sync(0xffffffffu, cur[g][0], 1);
-        if (lane == 31) w[6] = eb[kEdge + 2 * (slot + 1)];
+        if (lane_last) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(w[6]) : "r"(e_rr[g] + par) : "memory");
       }
       if (RR >= 2) {
         w[7] = __shfl_down_sync(0xffffffffu, cur[g][1], 1);
-        if (lane == 31) w[7] = eb[kEdge + 2 * (slot + 1) + 1];
+        if (lane_last) asm volatile("ld.shared.f32 %0, [%1+4];" : "=f"(w[7]) : "r"(e_rr[g] + par) : "memory");
       }
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
@@ -184,21 +214,21 @@ scan_rowmarch_kernel(const __grid_constant__ RMArgs a) {
         nxt[g][e] = v;
       }
     }
-    float* orow = a.out + (int64_t)n * a.nx;
 #pragma unroll
     for (int g = 0; g < G; ++g) {
-      const int64_t c0 = span0 + (int64_t)g * kRMThreads * 4 + tid * 4;
 #pragma unroll
       for (int e = 0; e < 4; ++e) cur[g][e] = nxt[g][e];
-      if (c0 >= own0 && c0 < own1) {
-        if (c0 + 3 < own1 && ((a.nx & 3) == 0)) {
-          __stcs(reinterpret_cast<float4*>(orow + c0), make_float4(nxt[g][0], nxt[g][1], nxt[g][2], nxt[g][3]));
-        } else {
+      if (store_mode[g] == 2) {
+        __stcs(reinterpret_cast<float4*>(optr[g]), make_float4(nxt[g][0], nxt[g][1], nxt[g][2], nxt[g][3]));
+      } else if (store_mode[g] == 1) {
+        const int64_t c0 = span0 + (int64_t)g * kRMThreads * 4 + tid * 4;
 #pragma unroll
-          for (int e = 0; e < 4; ++e)
-            if (c0 + e < own1) orow[c0 + e] = nxt[g][e];
-        }
+        for (int e = 0; e < 4; ++e)
+          if (c0 + e < own1) optr[g][e] = nxt[g][e];
       }
+      optr[g] += a.nx;
+    }
+    par ^= kParityBytes;
     }
   }
 }
