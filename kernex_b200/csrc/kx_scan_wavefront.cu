@@ -367,6 +367,125 @@ scan_wavefront_rows_kernel(const __grid_constant__ WaveRowsArgs a, const __grid_
   }
 }
 
+// Single-function AFFINE scans with at most kFastTaps taps (Gauss-Seidel sweeps, recurrences): the tap
+// table lives in registers (source row in the history, element offset in the arrays, coefficient, new / old
+// flag are loop invariants of a lane), the loop over the taps is fully unrolled so their loads overlap, and
+// the input rows are prefetched into L1 sixteen columns ahead (a lone warp cannot hide an L2 miss).
+constexpr int kFastTaps = 8;
+
+template <typename TIN, typename TC>
+__global__ void __launch_bounds__(128)
+scan_wavefront_rows_affine_kernel(const __grid_constant__ WaveRowsArgs a, const __grid_constant__ DevProgram<TC> p,
+                                  const TIN* __restrict__ in, TIN* out, const TC* __restrict__ coef_dev) {
+  __shared__ TIN hist[4][32][kHistW];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  volatile int32_t* progress = a.ticket + 1;
+  const int sgn = a.reverse ? -1 : 1;
+  const int ntaps = p.func[0].tap_end - p.func[0].tap_begin;
+  const TC bias = p.func[0].bias;
+  const unsigned hist0 = (unsigned)__cvta_generic_to_shared(&hist[warp][0][0]);
+  for (;;) {
+    int band = 0;
+    if (lane == 0) band = atomicAdd(a.ticket, 1);
+    band = __shfl_sync(0xffffffffu, band, 0);
+    if (band >= a.nbands) break;
+    const int il = band * 32 + lane;
+    const bool row_ok = il < a.ni;
+    const int ia = a.reverse ? a.ni - 1 - il : il;
+    // per-lane tap table
+    TC coef[kFastTaps];
+    int ldj[kFastTaps], goff[kFastTaps], src[kFastTaps];   // src: 0 = zero (row outside), 1 = input, 2 = history, 3 = `out` (band above)
+    unsigned hrow[kFastTaps];
+#pragma unroll
+    for (int t = 0; t < kFastTaps; ++t) {
+      coef[t] = TC(0);
+      ldj[t] = goff[t] = 0;
+      src[t] = 0;
+      hrow[t] = hist0;
+      if (t < ntaps) {
+        const int tt = p.func[0].tap_begin + t;
+        const int di = a.two_d ? (int)p.tap_off[tt][0] - a.c0 : 0;
+        const int dj = (int)p.tap_off[tt][a.two_d ? 1 : 0] - a.c1;
+        const int ldi = sgn * di;
+        coef[t] = coef_dev ? coef_dev[tt] : p.coef[tt];
+        ldj[t] = sgn * dj;
+        goff[t] = di * a.nj + dj;
+        const int ci = ia + di;
+        if (ci >= 0 && ci < a.ni) {
+          if (ldi < 0 || (ldi == 0 && ldj[t] < 0)) {
+            const int r2 = lane + ldi;
+            src[t] = r2 >= 0 ? 2 : 3;
+            hrow[t] = hist0 + (unsigned)((r2 >= 0 ? r2 : 0) * kHistW * 4);
+          } else {
+            src[t] = 1;
+          }
+        }
+      }
+    }
+    int avail = band == 0 ? a.nj : 0;
+    const int nsteps = a.nj + 31 * a.a0;
+    const int64_t row_base = (int64_t)ia * a.nj;
+    const unsigned hown = hist0 + (unsigned)(lane * kHistW * 4);
+    for (int s = 0; s < nsteps; ++s) {
+      if (band > 0) {
+        const int need = min(s + a.r_above + 1, a.nj);
+        if (need > avail) {
+          if (lane == 0) {
+            int v = progress[band - 1];
+            while (v < need) v = progress[band - 1];
+            __threadfence();
+            avail = v;
+          }
+          avail = __shfl_sync(0xffffffffu, avail, 0);
+        }
+      }
+      const int jl = s - a.a0 * lane;
+      if (row_ok && jl >= 0 && jl < a.nj) {
+        const int ja = a.reverse ? a.nj - 1 - jl : jl;
+        const int64_t cell = row_base + ja;
+        TC v[kFastTaps];
+#pragma unroll
+        for (int t = 0; t < kFastTaps; ++t) {           // all loads first: they are independent
+          v[t] = TC(0);
+          if (t < ntaps) {
+            const int cl = jl + ldj[t];                 // logical column of the tap
+            const bool inside = cl >= 0 && cl < a.nj;
+            if (inside && src[t] == 2) {
+              int raw;
+              asm volatile("ld.shared.b32 %0, [%1];" : "=r"(raw) : "r"(hrow[t] + (unsigned)((cl & (kHistW - 1)) * 4)));
+              v[t] = (TC) reinterpret_cast<const TIN&>(raw);
+            } else if (inside && src[t] == 3) {
+              v[t] = (TC)__ldcg(out + cell + goff[t]);
+            } else if (inside && src[t] == 1) {
+              v[t] = (TC)in[cell + goff[t]];
+              // touch the line 16 columns further along the sweep
+              const int cp = cl + 16;
+              if (cp < a.nj) asm volatile("prefetch.global.L1 [%0];" ::"l"(in + cell + goff[t] + sgn * 16));
+            }
+          }
+        }
+        TC acc = bias;
+#pragma unroll
+        for (int t = 0; t < kFastTaps; ++t)
+          if (t < ntaps) acc = mad_wrap(coef[t], v[t], acc);
+        if (p.func[0].post_div != 0.f) acc = (TC)((float)acc / p.func[0].post_div);
+        const TIN stored = (TIN)acc;
+        asm volatile("st.shared.b32 [%0], %1;" ::"r"(hown + (unsigned)((jl & (kHistW - 1)) * 4)),
+                     "r"(reinterpret_cast<const int&>(stored))
+                     : "memory");
+        out[cell] = stored;
+      }
+      const int j31 = s - 31 * a.a0;
+      const bool pub = j31 >= 0 && (((j31 & a.pub_mask) == a.pub_mask) || j31 == a.nj - 1);
+      __syncwarp();
+      if (pub && lane == 31) {
+        __threadfence();
+        progress[band] = j31 + 1;
+      }
+    }
+  }
+}
+
 template <typename TIN, typename TC>
 int try_wave_rows(const KxGeom& g, const KxProgram& prog, const WaveArgs& plan, const void* in, const void* coef_dev,
                   void* state, void* out, int reverse, cudaStream_t s) {
@@ -414,8 +533,14 @@ int try_wave_rows(const KxGeom& g, const KxProgram& prog, const WaveArgs& plan, 
   int64_t blocks = (a.nbands + 3) / 4;
   const int64_t cap = (int64_t)sm_count() * 8;
   if (blocks > cap) blocks = cap;                              // persistent: warps keep taking tickets
-  scan_wavefront_rows_kernel<TIN, TC><<<(unsigned)blocks, 128, 0, s>>>(a, dp, (const TIN*)in, (TIN*)out,
-                                                                      (const TC*)coef_dev);
+  const bool fast = prog.n_funcs == 1 && prog.func[0].kind == KX_AFFINE &&
+                    prog.func[0].tap_end - prog.func[0].tap_begin <= kFastTaps && !getenv("KX_WAVE_GENERIC");
+  if (fast)
+    scan_wavefront_rows_affine_kernel<TIN, TC><<<(unsigned)blocks, 128, 0, s>>>(a, dp, (const TIN*)in, (TIN*)out,
+                                                                               (const TC*)coef_dev);
+  else
+    scan_wavefront_rows_kernel<TIN, TC><<<(unsigned)blocks, 128, 0, s>>>(a, dp, (const TIN*)in, (TIN*)out,
+                                                                        (const TC*)coef_dev);
   return after_launch("scan_wavefront_rows_kernel");
 }
 
