@@ -73,3 +73,15 @@ if want("vjp"):
         gy = torch.randn(y.shape, device=dev, generator=g)
         med, _ = timeit(lambda: torch.autograd.grad(y, x, gy, retain_graph=True), 6)
         rep(f"C2 VJP wrt x, padding={pad}", n * n * 8, med, n * n)
+
+if want("mesh"):
+    # multi-function kmap mesh (F[slice] = fn): interior Laplacian + Dirichlet edges + a source block
+    n = 8192
+    x = torch.randn((n, n), device=dev, generator=g)
+    F = kex.kmap(kernel_size=(3, 3), padding="same", relative=True)
+    F[:, :] = lambda v: v[0, 0]
+    F[1:-1, 1:-1] = lambda v: v[1, 0] + v[0, -1] - 4 * v[0, 0] + v[0, 1] + v[-1, 0]
+    F[n // 4: n // 2, n // 4: n // 2] = lambda v: 0.5 * v[0, 0] + 1.0
+    y = F(x)
+    med, _ = timeit(lambda: F(x), 6)
+    rep("kmap mesh, 3 region functions, 8192^2", x.numel() * 8, med, y.numel())

@@ -76,6 +76,8 @@ void fill_map_args(MapArgs& a, const KxGeom& g, const KxProgram& p, const void* 
 int dispatch_map(const MapArgs& a, const KxProgram& prog, cudaStream_t s) {
   int rc = try_stencil2d(a, prog, s);
   if (rc != KX_ERR_UNSUPPORTED) return rc;
+  rc = try_stencil2d_mesh(a, prog, s);
+  if (rc != KX_ERR_UNSUPPORTED) return rc;
   rc = try_conv2d(a, prog, s);
   if (rc != KX_ERR_UNSUPPORTED) return rc;
   rc = try_stencil3d(a, prog, s);

@@ -114,6 +114,7 @@ int launch_generic_scan(const KxGeom& g, const KxProgram& prog, const void* in, 
 // fast paths; each returns KX_ERR_UNSUPPORTED (without touching the error string)
 // when its template does not cover the request so the caller can fall through
 int try_stencil2d(const MapArgs& a, const KxProgram& prog, cudaStream_t s);
+int try_stencil2d_mesh(const MapArgs& a, const KxProgram& prog, cudaStream_t s);
 int try_stencil3d(const MapArgs& a, const KxProgram& prog, cudaStream_t s);
 int try_stencil3d_star(const MapArgs& a, const KxProgram& prog, int64_t batch, cudaStream_t s);
 int try_patch(const MapArgs& a, const KxProgram& prog, cudaStream_t s);

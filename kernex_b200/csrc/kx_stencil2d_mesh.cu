@@ -1,0 +1,317 @@
+// Fast path: MULTI-FUNCTION kmap meshes (`F[slice] = fn` region assignment, kernel_interface.py:85-90)
+// whose functions are all AFFINE, over the last two axes, stride 1: interior stencil + boundary
+// conditions + source blocks in ONE pass.  The reference evaluates every function for every window
+// under vmap and selects with lax.switch (kernex/_src/map.py:115-118); the generic kernel here
+// re-derives the region of every window from the key table (0.04 of the HBM roofline).
+//
+// Same row-marching skeleton as kx_stencil2d.cu (a thread owns 4 output columns, keeps the last KY
+// input rows in a register queue, 128-bit loads).  Region selection follows select_func
+// (kernex/_src/utils.py:338-382: keys scanned from the LAST inserted, first match wins, no match =
+// function 0) but is factored so that the row loop only does bit operations:
+//   * column part of every key, per owned column: a 32-bit mask, computed once per thread;
+//   * row part of every key (plus the leading batch axes), per row of the band: a 32-bit mask in
+//     shared memory, computed once per block;
+//   * per output: m = row_mask & col_mask, function = m ? func_of_key[31 - clz(m)] : 0.
+// When the thread's 4 columns agree (everywhere except at vertical region boundaries) only that
+// function is evaluated, with its coefficients as constant-bank FFMA operands; otherwise every
+// function is evaluated and selected per column.  Accumulation order: bias, then the window in
+// row-major order (as kx_stencil2d.cu).
+#include "kx_internal.cuh"
+
+namespace kx {
+
+namespace {
+
+constexpr int kMT = 128;        // threads per block
+constexpr int kMCols = 4;
+constexpr int kMaxNF = 4;       // functions per mesh on this path
+constexpr int kMaxTH = 32;      // rows per band
+
+template <typename T>
+struct MeshArgs {
+  const T* in;
+  T* out;
+  int64_t in_batch, out_batch;
+  int hin, win, hout, wout;
+  int ly, lx, th;
+  int n_funcs, n_keys;
+  int ay, ax, ndim;                      // axes of the 2-D window inside the key items
+  int64_t lead_shape[KX_MAX_DIMS];       // leading (batch) axes, for keys that constrain them
+  uint32_t mask[kMaxNF];                 // tap mask per function
+  T bias[kMaxNF];
+  T coef[kMaxNF][9];
+  unsigned char key_func[KX_MAX_KEYS];
+  KxKey key[KX_MAX_KEYS];
+};
+
+__device__ __forceinline__ bool item_match(const KxKeyItem& it, int64_t c) {
+  if (it.kind == KX_KEY_EQ) return c == it.a;
+  if (it.kind == KX_KEY_RANGE) return (it.a <= c) && (c < it.b);
+  if (it.kind == KX_KEY_RANGE_STEP) return (it.a <= c) && (c < it.b) && (c % it.step == 0);
+  return true;
+}
+
+template <typename T>
+__device__ __forceinline__ void ld4(const T* p, T (&d)[4]) {
+  const int4 raw = __ldg(reinterpret_cast<const int4*>(p));
+  d[0] = reinterpret_cast<const T&>(raw.x);
+  d[1] = reinterpret_cast<const T&>(raw.y);
+  d[2] = reinterpret_cast<const T&>(raw.z);
+  d[3] = reinterpret_cast<const T&>(raw.w);
+}
+
+// value of function F at column i from the register queue rows q[u .. u+KY-1]
+template <typename T, int KY, int KX, int SHIFT, int NE, int F>
+__device__ __forceinline__ T eval_one(const MeshArgs<T>& a, const T (*q)[NE], int u, int i) {
+  T acc = a.bias[F];
+#pragma unroll
+  for (int ky = 0; ky < KY; ++ky)
+#pragma unroll
+    for (int kx = 0; kx < KX; ++kx)
+      if (a.mask[F] & (1u << (ky * KX + kx))) acc = mad_wrap(a.coef[F][ky * KX + kx], q[u + ky][SHIFT + kx + i], acc);
+  return acc;
+}
+
+template <typename T, int KY, int KX, int SHIFT, int NE, int NF>
+__device__ __forceinline__ T eval_sel(const MeshArgs<T>& a, const T (*q)[NE], int u, int i, int f) {
+  T v = eval_one<T, KY, KX, SHIFT, NE, 0>(a, q, u, i);
+  if (NF > 1 && f == 1) v = eval_one<T, KY, KX, SHIFT, NE, 1>(a, q, u, i);
+  if (NF > 2 && f == 2) v = eval_one<T, KY, KX, SHIFT, NE, 2>(a, q, u, i);
+  if (NF > 3 && f == 3) v = eval_one<T, KY, KX, SHIFT, NE, 3>(a, q, u, i);
+  return v;
+}
+
+// VW = 4: rows 16-byte aligned (SHIFT = (-lx) mod 4); VW = 1: scalar loads (SHIFT = 0)
+template <typename T, int KY, int KX, int SHIFT, int VW, int NF>
+__global__ void __launch_bounds__(kMT)
+stencil2d_mesh_kernel(const __grid_constant__ MeshArgs<T> a) {
+  constexpr int NV = (SHIFT + KX + kMCols - 1 + VW - 1) / VW;
+  constexpr int NE = NV * VW;
+  constexpr int U = 2;                       // rows fetched back to back
+  __shared__ uint32_t row_mask[kMaxTH];
+  const int tid = threadIdx.x;
+  const int j0 = (blockIdx.x * kMT + tid) * kMCols;
+  const int r0 = blockIdx.y * a.th, r1 = min(r0 + a.th, a.hout);
+  const T* __restrict__ in = a.in + (int64_t)blockIdx.z * a.in_batch;
+  T* __restrict__ out = a.out + (int64_t)blockIdx.z * a.out_batch;
+  const int cy = (KY - 1) / 2, cx = (KX - 1) / 2;
+
+  // ---- row part of the keys (and the leading axes), once per block ----
+  if (tid < a.th) {
+    const int64_t rc = (int64_t)(r0 + tid) - a.ly + cy;     // window-centre row in array coordinates
+    int64_t lead[KX_MAX_DIMS] = {0, 0, 0, 0};
+    int64_t b = blockIdx.z;
+    for (int d = a.ndim - 3; d >= 0; --d) {
+      lead[d] = b % a.lead_shape[d];
+      b /= a.lead_shape[d];
+    }
+    uint32_t m = 0;
+    for (int k = 0; k < a.n_keys; ++k) {
+      const KxKey& key = a.key[k];
+      bool ok = true;
+      for (int d = 0; d < key.n_items; ++d) {
+        if (d == a.ax) continue;
+        ok = ok && item_match(key.item[d], d == a.ay ? rc : lead[d]);
+      }
+      if (ok) m |= 1u << k;
+    }
+    row_mask[tid] = m;
+  }
+  // ---- column part of the keys, once per thread ----
+  uint32_t col_mask[kMCols];
+#pragma unroll
+  for (int i = 0; i < kMCols; ++i) {
+    const int64_t cc = (int64_t)(j0 + i) - a.lx + cx;
+    uint32_t m = 0;
+    for (int k = 0; k < a.n_keys; ++k) {
+      const KxKey& key = a.key[k];
+      if (a.ax >= key.n_items || item_match(key.item[a.ax], cc)) m |= 1u << k;
+    }
+    col_mask[i] = m;
+  }
+  __syncthreads();
+  if (j0 >= a.wout) return;
+  const int xa = j0 - a.lx - SHIFT;
+  const int n_valid = min(kMCols, a.wout - j0);
+
+  auto load_row = [&](int iy, T(&dst)[NE]) {
+    const bool row_ok = (iy >= 0) && (iy < a.hin);
+    const T* rp = in + (int64_t)iy * a.win;
+    if (VW == 4) {
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        const int c = xa + 4 * v;
+        T t4[4] = {T(0), T(0), T(0), T(0)};
+        if (row_ok && c >= 0 && c + 3 < a.win) ld4(rp + c, t4);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) dst[4 * v + e] = t4[e];
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < NE; ++e) {
+        const int c = xa + e;
+        dst[e] = (row_ok && c >= 0 && c < a.win) ? __ldg(rp + c) : T(0);
+      }
+    }
+  };
+
+  T q[KY - 1 + U][NE];
+#pragma unroll
+  for (int ky = 0; ky < KY - 1; ++ky) load_row(r0 - a.ly + ky, q[ky]);
+
+  for (int r = r0; r < r1; r += U) {
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (r + u < r1) load_row(r + u - a.ly + KY - 1, q[KY - 1 + u]);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (r + u < r1) {
+        const uint32_t rm = row_mask[r + u - r0];
+        int f[kMCols];
+#pragma unroll
+        for (int i = 0; i < kMCols; ++i) {
+          const uint32_t m = rm & col_mask[i];
+          f[i] = m ? (int)a.key_func[31 - __clz(m)] : 0;
+        }
+        T acc[kMCols];
+        if (f[0] == f[1] && f[1] == f[2] && f[2] == f[3]) {
+          // one function for the whole thread row: evaluate only it (uniform inside regions)
+          const int fs = f[0];
+          if (NF > 3 && fs == 3) {
+#pragma unroll
+            for (int i = 0; i < kMCols; ++i) acc[i] = eval_one<T, KY, KX, SHIFT, NE, 3>(a, q, u, i);
+          } else if (NF > 2 && fs == 2) {
+#pragma unroll
+            for (int i = 0; i < kMCols; ++i) acc[i] = eval_one<T, KY, KX, SHIFT, NE, 2>(a, q, u, i);
+          } else if (NF > 1 && fs == 1) {
+#pragma unroll
+            for (int i = 0; i < kMCols; ++i) acc[i] = eval_one<T, KY, KX, SHIFT, NE, 1>(a, q, u, i);
+          } else {
+#pragma unroll
+            for (int i = 0; i < kMCols; ++i) acc[i] = eval_one<T, KY, KX, SHIFT, NE, 0>(a, q, u, i);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < kMCols; ++i) acc[i] = eval_sel<T, KY, KX, SHIFT, NE, NF>(a, q, u, i, f[i]);
+        }
+        T* o = out + (int64_t)(r + u) * a.wout + j0;
+        const uintptr_t addr = reinterpret_cast<uintptr_t>(o);
+        if (n_valid == 4 && (addr & 15) == 0) {
+          int4 raw;
+          raw.x = reinterpret_cast<const int&>(acc[0]);
+          raw.y = reinterpret_cast<const int&>(acc[1]);
+          raw.z = reinterpret_cast<const int&>(acc[2]);
+          raw.w = reinterpret_cast<const int&>(acc[3]);
+          __stcs(reinterpret_cast<int4*>(o), raw);
+        } else {
+#pragma unroll
+          for (int i = 0; i < kMCols; ++i)
+            if (i < n_valid) o[i] = acc[i];
+        }
+      }
+    }
+#pragma unroll
+    for (int ky = 0; ky < KY - 1; ++ky) {
+#pragma unroll
+      for (int e = 0; e < NE; ++e) q[ky][e] = q[U + ky][e];
+    }
+  }
+}
+
+template <typename T, int KY, int KX, int NF>
+int launch_mesh_nf(const MeshArgs<T>& a, dim3 grid, bool vec, cudaStream_t s) {
+  const int shift = vec ? (((-a.lx) % 4) + 4) % 4 : 0;
+  if (!vec) stencil2d_mesh_kernel<T, KY, KX, 0, 1, NF><<<grid, kMT, 0, s>>>(a);
+  else if (shift == 0) stencil2d_mesh_kernel<T, KY, KX, 0, 4, NF><<<grid, kMT, 0, s>>>(a);
+  else if (shift == 1) stencil2d_mesh_kernel<T, KY, KX, 1, 4, NF><<<grid, kMT, 0, s>>>(a);
+  else if (shift == 2) stencil2d_mesh_kernel<T, KY, KX, 2, 4, NF><<<grid, kMT, 0, s>>>(a);
+  else stencil2d_mesh_kernel<T, KY, KX, 3, 4, NF><<<grid, kMT, 0, s>>>(a);
+  return after_launch("stencil2d_mesh_kernel");
+}
+
+template <typename T, int KY, int KX>
+int launch_mesh(const MeshArgs<T>& a, dim3 grid, bool vec, cudaStream_t s) {
+  if (a.n_funcs <= 2) return launch_mesh_nf<T, KY, KX, 2>(a, grid, vec, s);
+  if (a.n_funcs == 3) return launch_mesh_nf<T, KY, KX, 3>(a, grid, vec, s);
+  return launch_mesh_nf<T, KY, KX, 4>(a, grid, vec, s);
+}
+
+template <typename T>
+int run_mesh(const MapArgs& m, const KxProgram& p, cudaStream_t s) {
+  const KxGeom& g = m.g;
+  const int nd = g.ndim, ax = nd - 1, ay = nd - 2;
+  const int KY = ay >= 0 ? g.ksize[ay] : 1, KX = g.ksize[ax];
+  static thread_local MeshArgs<T> a;
+  memset(&a, 0, sizeof(a));
+  int64_t lead = 1;
+  for (int d = 0; d < nd - 2; ++d) {
+    if (g.ksize[d] != 1 || g.stride[d] != 1 || g.lo[d] != 0 || g.hi[d] != 0) return KX_ERR_UNSUPPORTED;
+    a.lead_shape[d] = g.in_shape[d];
+    lead *= g.in_shape[d];
+  }
+  const int64_t batch = m.batch * lead;
+  if (batch > 65535 || m.batch != 1) return KX_ERR_UNSUPPORTED;
+  for (int f = 0; f < p.n_funcs; ++f) {
+    const KxFunc& fn = p.func[f];
+    a.bias[f] = (T)fn.bias;
+    for (int t = fn.tap_begin; t < fn.tap_end; ++t) {
+      for (int d = 0; d < nd - 2; ++d)
+        if (p.tap_off[t][d] != 0) return KX_ERR_UNSUPPORTED;
+      const int slot = (ay >= 0 ? p.tap_off[t][ay] : 0) * KX + p.tap_off[t][ax];
+      if (a.mask[f] & (1u << slot)) return KX_ERR_UNSUPPORTED;   // duplicate tap: generic kernel
+      a.mask[f] |= 1u << slot;
+      a.coef[f][slot] = (T)p.coef[t];
+    }
+  }
+  a.n_funcs = p.n_funcs;
+  a.n_keys = p.n_keys;
+  for (int k = 0; k < p.n_keys; ++k) {
+    a.key[k] = p.key[k];
+    a.key_func[k] = (unsigned char)p.key[k].func;
+  }
+  a.ay = ay;
+  a.ax = ax;
+  a.ndim = nd;
+  a.in = (const T*)m.in;
+  a.out = (T*)m.out;
+  a.hin = ay >= 0 ? (int)g.in_shape[ay] : 1;
+  a.win = (int)g.in_shape[ax];
+  a.hout = ay >= 0 ? (int)g.out_shape[ay] : 1;
+  a.wout = (int)g.out_shape[ax];
+  a.ly = ay >= 0 ? g.lo[ay] : 0;
+  a.lx = g.lo[ax];
+  a.in_batch = (int64_t)a.hin * a.win;
+  a.out_batch = (int64_t)a.hout * a.wout;
+  a.th = a.hout >= 512 ? 32 : (a.hout >= 64 ? 16 : 8);
+  while ((a.hout + a.th - 1) / a.th > 65535) a.th *= 2;
+  if (a.th > kMaxTH) return KX_ERR_UNSUPPORTED;
+  const bool vec = (a.win % 4 == 0) && ((reinterpret_cast<uintptr_t>(m.in) & 15) == 0) && (a.in_batch % 4 == 0);
+  dim3 grid((a.wout + kMT * kMCols - 1) / (kMT * kMCols), (a.hout + a.th - 1) / a.th, (unsigned)batch);
+  if (KY == 3 && KX == 3) return launch_mesh<T, 3, 3>(a, grid, vec, s);
+  if (KY == 1 && KX == 3) return launch_mesh<T, 1, 3>(a, grid, vec, s);
+  if (KY == 1 && KX == 1) return launch_mesh<T, 1, 1>(a, grid, vec, s);
+  return KX_ERR_UNSUPPORTED;
+}
+
+}  // namespace
+
+int try_stencil2d_mesh(const MapArgs& m, const KxProgram& p, cudaStream_t s) {
+  const KxGeom& g = m.g;
+  if (p.n_funcs < 2 || p.n_funcs > kMaxNF || m.fn_elems != 1 || m.coef_dev || m.use_box) return KX_ERR_UNSUPPORTED;
+  if (getenv("KX_NO_MESH")) return KX_ERR_UNSUPPORTED;   // cross-check switch: generic kernel
+  if (g.in_dtype != g.out_dtype) return KX_ERR_UNSUPPORTED;
+  bool all_int = true;
+  for (int f = 0; f < p.n_funcs; ++f) {
+    if (p.func[f].kind != KX_AFFINE || p.func[f].post_div != 0.0) return KX_ERR_UNSUPPORTED;
+    if (!p.func[f].coef_is_int) all_int = false;
+  }
+  const int nd = g.ndim;
+  if (g.stride[nd - 1] != 1 || (nd >= 2 && g.stride[nd - 2] != 1)) return KX_ERR_UNSUPPORTED;
+  for (int d = 0; d < nd; ++d)
+    if (g.in_shape[d] > 0x3fffffff || g.out_shape[d] > 0x3fffffff) return KX_ERR_UNSUPPORTED;
+  if (g.in_dtype == KX_F32) return run_mesh<float>(m, p, s);
+  if (g.in_dtype == KX_I32 && all_int) return run_mesh<int32_t>(m, p, s);
+  return KX_ERR_UNSUPPORTED;
+}
+
+}  // namespace kx

@@ -64,6 +64,7 @@ class KernelInterface:
             raise TypeError(f"Input not callable. Found {type(func)}")
         # dict order = order of each function object's FIRST assignment (:90)
         self.container[func] = [*self.container.get(func, []), index]
+        self.__dict__.pop("_mesh_ops", None)   # resolved engine closures are per region table
 
     # -- dispatch ---------------------------------------------------------- #
 
@@ -90,11 +91,16 @@ class KernelInterface:
 
     def _wrap_mesh(self, array, *a, **k):
         shape = tuple(array.shape)
-        ksize, strides, border = self._resolved(shape)
-        normalized = normalize_slices(self.container, shape)
-        resolved = {self._named(func, ksize): keys for func, keys in normalized.items()}
-        op = self._engine()(resolved, shape, ksize, strides, border, self.relative,
-                            self.transform_kind, self.transform_kwargs)
+        ops = self.__dict__.setdefault("_mesh_ops", {})   # shape -> engine closure (dropped by __setitem__)
+        op = ops.get(shape)
+        if op is None:
+            ksize, strides, border = self._resolved(shape)
+            normalized = normalize_slices(self.container, shape)
+            resolved = {self._named(func, ksize): keys for func, keys in normalized.items()}
+            op = self._engine()(resolved, shape, ksize, strides, border, self.relative,
+                                self.transform_kind, self.transform_kwargs)
+            if len(ops) < 64:
+                ops[shape] = op
         return op(array, *a, **k)
 
     def _wrap_decorator(self, func):

@@ -1,0 +1,121 @@
+"""GPU parity of the multi-function kmap mesh kernel (kx_stencil2d_mesh.cu: `F[slice] = fn` region
+assignment with affine functions) against the literal oracle (region selection of
+kernex/_src/utils.py:338-382) on small meshes, and against the generic kernel on large ones."""
+from __future__ import annotations
+
+import itertools
+
+import numpy as np
+import pytest
+
+from oracle import kx_oracle as ko
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+INF = float("inf")
+
+
+@pytest.fixture(scope="module")
+def kex():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import kernex_b200
+    return kernex_b200
+
+
+def _last_kernel():
+    from kernex_b200 import _lib
+    return _lib.last_kernel()
+
+
+def _fn(taps, coefs, bias, integer):
+    def fn(x):
+        acc = int(bias) if integer else float(bias)
+        for tp, c in zip(taps, coefs):
+            acc = acc + (int(c) if integer else float(c)) * x[tp]
+        return acc
+    return fn
+
+
+def _random_key_item(rng, n):
+    kind = int(rng.integers(0, 5))
+    if kind == 0:
+        return int(rng.integers(0, n))
+    if kind == 1:
+        a = int(rng.integers(0, n))
+        return (a, int(rng.integers(a, n + 1)))
+    if kind == 2:
+        a = int(rng.integers(0, n))
+        return (a, int(rng.integers(a, n + 1)), int(rng.integers(1, 4)))
+    if kind == 3:
+        return (-INF, INF)
+    return (int(rng.integers(0, n)), INF)
+
+
+@pytest.mark.parametrize("seed", range(30))
+def test_random_meshes_match_literal_oracle(kex, seed):
+    rng = np.random.default_rng(12000 + seed)
+    nd = 1 if seed % 5 == 4 else 2
+    ksize = (3,) if nd == 1 else [(3, 3), (1, 3), (1, 1)][seed % 3]
+    shape = (int(rng.integers(20, 200)),) if nd == 1 else (int(rng.integers(8, 40)), 4 * int(rng.integers(3, 40)) + (seed % 2))
+    border = tuple((int(rng.integers(0, 3)), int(rng.integers(0, 3))) for _ in range(nd)) if seed % 3 else \
+        tuple(((k - 1) // 2, k // 2) for k in ksize)
+    if any(n + lo + hi < k for n, k, (lo, hi) in zip(shape, ksize, border)):
+        pytest.skip("empty output")
+    integer = seed % 2 == 0
+    nf = 2 + seed % 3
+    all_taps = list(itertools.product(*[range(k) for k in ksize]))
+    fmap = {}
+    for q in range(nf):
+        taps = [all_taps[i] for i in rng.choice(len(all_taps), min(len(all_taps), int(rng.integers(1, 5))), replace=False)]
+        if integer:
+            f = _fn(taps, rng.integers(-3, 4, len(taps)), int(rng.integers(-2, 3)), True)
+        else:
+            f = _fn(taps, rng.standard_normal(len(taps)), float(rng.standard_normal()), False)
+        keys = [[]] if q == 0 else [[_random_key_item(rng, shape[d]) for d in range(int(rng.integers(1, nd + 1)))]
+                                    for _ in range(int(rng.integers(1, 3)))]
+        fmap[f] = keys
+    x = rng.integers(-9, 10, shape).astype(np.int32) if integer else rng.standard_normal(shape).astype(np.float32)
+    want = ko.kernel_map(fmap, shape, ksize, (1,) * nd, border, False)(x)
+    got = kex.kernel_map(fmap, shape, ksize, (1,) * nd, border, False)(x)
+    assert _last_kernel() == "stencil2d_mesh_kernel"
+    assert got.shape == want.shape and got.dtype == want.dtype
+    if integer:
+        np.testing.assert_array_equal(got, want)
+    else:
+        np.testing.assert_allclose(got, want, rtol=1e-5, atol=1e-5)
+
+
+def test_interface_mesh_large_matches_generic_kernel(kex, monkeypatch):
+    """Interior Laplacian + identity edges + a source block on 2000 x 4100 (several bands and column
+    blocks, region boundaries inside thread quads), and a batched mesh whose keys constrain the batch axis."""
+    rng = np.random.default_rng(5)
+    n0, n1 = 2000, 4100
+    x = torch.from_numpy(rng.standard_normal((n0, n1)).astype(np.float32)).cuda()
+    F = kex.kmap(kernel_size=(3, 3), padding="same", relative=True)
+    F[:, :] = lambda v: v[0, 0]
+    F[1:-1, 1:-1] = lambda v: v[1, 0] + v[0, -1] - 4 * v[0, 0] + v[0, 1] + v[-1, 0]
+    F[501:777, 1001:2003] = lambda v: 0.5 * v[0, 0] + 1.0
+    F[::7, 3::5] = lambda v: v[0, 1] - v[0, -1]
+    got = F(x)
+    assert _last_kernel() == "stencil2d_mesh_kernel"
+    monkeypatch.setenv("KX_NO_MESH", "1")
+    want = F(x)
+    assert _last_kernel() == "generic_map_kernel"
+    monkeypatch.delenv("KX_NO_MESH")
+    # same taps and coefficients; the generic kernel accumulates in expression order, this one in window order
+    torch.testing.assert_close(got, want, rtol=1e-5, atol=1e-5)
+    # independent check of the three rectangular regions
+    xh = x.cpu().numpy()
+    g = got.cpu().numpy()
+    np.testing.assert_array_equal(g[0, 1::5][:3], xh[0, 1::5][:3])                     # identity edge
+    lap = xh[2:, 1:-1] + xh[1:-1, :-2] - 4 * xh[1:-1, 1:-1] + xh[1:-1, 2:] + xh[:-2, 1:-1]
+    np.testing.assert_allclose(g[1:-1, 1:-1][3, 4], lap[3, 4], rtol=1e-5, atol=1e-5)  # row 4: not a ::7 row, col 5
+    # batched: keys on the leading axis
+    xb = torch.from_numpy(rng.integers(-5, 6, (3, 40, 64)).astype(np.int32)).cuda()
+    f0, f1 = (lambda v: v[0, 1, 1]), (lambda v: 2 * v[0, 1, 1] - v[0, 1, 0])
+    keys = {f0: [[]], f1: [[1, (5, 30), (8, 50, 3)]]}
+    gb = kex.kernel_map(keys, (3, 40, 64), (1, 3, 3), (1, 1, 1), ((0, 0), (1, 1), (1, 1)), False)(xb)
+    assert _last_kernel() == "stencil2d_mesh_kernel"
+    wb = ko.kernel_map(keys, (3, 40, 64), (1, 3, 3), (1, 1, 1), ((0, 0), (1, 1), (1, 1)), False)(xb.cpu().numpy())
+    np.testing.assert_array_equal(gb.cpu().numpy(), wb)
