@@ -318,6 +318,20 @@ def run_ours(args):
 
     # ---- parity spot check against the oracle (not timed) ---------------------------
     parity = None
+    if world > 1:
+        # every rank checks the first and last 64 output rows of its slab (they involve the exchanged halo rows)
+        from oracle import kx_oracle as ko
+        L, ok = slab.layout, True
+        for out0 in (0, slab.out.shape[0] - 64):
+            in0 = out0 + (1 if L.first else 0) + L.halo_top - 1   # ext row of the first window row of output row out0
+            band = slab.ext[in0:in0 + 66].cpu().numpy()
+            want = ko.affine_map(band, (3, 3), (1, 1), ((0, 0), (0, 0)), TAPS, COEFS)
+            scale = ko.affine_map(np.abs(band), (3, 3), (1, 1), ((0, 0), (0, 0)), TAPS, np.abs(COEFS))
+            err = np.abs(slab.out[out0:out0 + 64].cpu().numpy().astype(np.float64) - want)
+            ok = ok and bool(np.all(err <= 1e-5 * scale + 1e-30))
+        flag = torch.tensor([1 if ok else 0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        parity = bool(flag.item())
     if world == 1:
         from oracle import kx_oracle as ko
         y = holder["y"]

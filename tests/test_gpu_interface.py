@@ -189,3 +189,30 @@ def test_reverse_scan_matches_oracle(kex):
         got = kex.kscan(kernel_size=(3, 3), padding="same", relative=True, scan_kwargs=kw)(f)(x)
         want = ko.kernel_scan({f: ()}, x.shape, (3, 3), (1, 1), ((1, 1), (1, 1)), True, "scan", kw)(x)
         np.testing.assert_array_equal(got, want)
+
+
+# ---- README.md:270-297 (example 5, Gaussian blur): host-computed weights, 'same' padding ----------------
+@pytest.mark.parametrize("ksize", [3, 5, 7])
+def test_readme_gaussian_blur(kex, ksize):
+    rng = np.random.default_rng(50 + ksize)
+    image = rng.standard_normal((61, 84)).astype(np.float32)
+    sigma = 1.5
+    xx, yy = np.meshgrid(np.linspace(-1, 1, ksize), np.linspace(-1, 1, ksize))
+    w = np.exp(-0.5 * (xx ** 2 + yy ** 2) / sigma ** 2)
+    w = (w / w.sum()).astype(np.float32)
+
+    @kex.kmap(kernel_size=(ksize, ksize), padding="same")
+    def conv(x):
+        return np.sum(x * w)
+
+    got = conv(image)
+    pad = ksize // 2
+    padded = np.pad(image.astype(np.float64), pad)
+    want = np.zeros_like(image, dtype=np.float64)
+    for a in range(ksize):
+        for b in range(ksize):
+            want += float(w[a, b]) * padded[a:a + image.shape[0], b:b + image.shape[1]]
+    np.testing.assert_allclose(got, want, rtol=1e-5, atol=1e-5)
+    taps = [(a, b) for a in range(ksize) for b in range(ksize)]
+    oracle = ko.affine_map(image, (ksize, ksize), (1, 1), ((pad, pad), (pad, pad)), taps, [float(w[t]) for t in taps])
+    np.testing.assert_allclose(got, oracle, rtol=1e-5, atol=1e-5)
