@@ -158,6 +158,9 @@ stencil2d_mesh_kernel(const __grid_constant__ MeshArgs<T> a) {
   T q[KY - 1 + U][NE];
 #pragma unroll
   for (int ky = 0; ky < KY - 1; ++ky) load_row(r0 - a.ly + ky, q[ky]);
+  int f[kMCols] = {0, 0, 0, 0};       // function of each owned column in the current row
+  uint32_t rm_prev = 0;               // row mask the selection was computed for
+  bool have_sel = false;
 
   for (int r = r0; r < r1; r += U) {
 #pragma unroll
@@ -167,11 +170,14 @@ stencil2d_mesh_kernel(const __grid_constant__ MeshArgs<T> a) {
     for (int u = 0; u < U; ++u) {
       if (r + u < r1) {
         const uint32_t rm = row_mask[r + u - r0];
-        int f[kMCols];
+        if (!have_sel || rm != rm_prev) {   // block-uniform: the selection only changes at a row boundary of some region
+          rm_prev = rm;
+          have_sel = true;
 #pragma unroll
-        for (int i = 0; i < kMCols; ++i) {
-          const uint32_t m = rm & col_mask[i];
-          f[i] = m ? (int)a.key_func[31 - __clz(m)] : 0;
+          for (int i = 0; i < kMCols; ++i) {
+            const uint32_t m = rm & col_mask[i];
+            f[i] = m ? (int)a.key_func[31 - __clz(m)] : 0;
+          }
         }
         T acc[kMCols];
         if (f[0] == f[1] && f[1] == f[2] && f[2] == f[3]) {
