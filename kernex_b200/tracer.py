@@ -412,6 +412,17 @@ class SymArray:
     __bool__ = _unsupported("bool()")
 
     # -- reductions -- #
+    @staticmethod
+    def _only_defaults(what, kw, ignore=()):
+        """Keyword arguments of a NumPy reduction that would change the VALUE (``where``, ``initial``,
+        ``keepdims``, ``weights`` ...) are refused unless they hold their neutral default; ``dtype`` / ``out``
+        = None are harmless.  Swallowing them silently would compute something else than the user wrote."""
+        for k, v in kw.items():
+            if k in ignore or v is None or (k == "keepdims" and v is False) or (k == "where" and v is True) \
+                    or v is getattr(np, "_NoValue", object()):
+                continue
+            raise UnsupportedStencilError(f"{what}(..., {k}={v!r}) on the window is not supported")
+
     def _reduce_axes(self, axis):
         if axis is None:
             return None
@@ -419,6 +430,7 @@ class SymArray:
         return tuple(a % self.data.ndim for a in axes)
 
     def sum(self, axis=None, **kw):
+        self._only_defaults("sum", kw)
         axes = self._reduce_axes(axis)
         if axes is None or len(axes) == self.data.ndim:
             acc = Affine.const(0)
@@ -437,6 +449,7 @@ class SymArray:
         return SymArray(out)._unwrap()
 
     def mean(self, axis=None, **kw):
+        self._only_defaults("mean", kw)
         axes = self._reduce_axes(axis)
         n = self.data.size if axes is None else int(np.prod([self.data.shape[a] for a in axes]))
         return self.sum(axis=axis) / float(n)
@@ -452,39 +465,56 @@ class SymArray:
         return Reduce(op, [next(iter(v.terms)) for v in flat])
 
     def max(self, axis=None, **kw):
+        self._only_defaults("max", kw)
         return self._minmax("max", axis)
 
     def min(self, axis=None, **kw):
+        self._only_defaults("min", kw)
         return self._minmax("min", axis)
 
 
 @_implements(np.sum)
 def _np_sum(a, axis=None, **kw):
-    return SymArray(_obj(a)).sum(axis=axis)
+    return SymArray(_obj(a)).sum(axis=axis, **kw)
 
 
-@_implements(np.mean, np.average)
+@_implements(np.mean)
 def _np_mean(a, axis=None, **kw):
-    return SymArray(_obj(a)).mean(axis=axis)
+    return SymArray(_obj(a)).mean(axis=axis, **kw)
+
+
+@_implements(np.average)
+def _np_average(a, axis=None, weights=None, **kw):
+    arr = SymArray(_obj(a))
+    if weights is None:
+        return arr.mean(axis=axis, **kw)
+    SymArray._only_defaults("average", kw)
+    w = np.asarray(weights)
+    if w.dtype == object or w.shape != arr.data.shape:
+        raise UnsupportedStencilError("np.average needs host weights of the window's shape")
+    # sum(x * w) / sum(w), as NumPy computes it
+    return _dispatch_ufunc(np.multiply, "__call__", (arr, w), {}).sum(axis=axis) / w.sum(axis=axis)
 
 
 @_implements(np.max, np.amax)
 def _np_max(a, axis=None, **kw):
-    return SymArray(_obj(a)).max(axis=axis)
+    return SymArray(_obj(a)).max(axis=axis, **kw)
 
 
 @_implements(np.min, np.amin)
 def _np_min(a, axis=None, **kw):
-    return SymArray(_obj(a)).min(axis=axis)
+    return SymArray(_obj(a)).min(axis=axis, **kw)
 
 
 @_implements(np.reshape)
 def _np_reshape(a, shape, **kw):
+    SymArray._only_defaults("reshape", kw, ignore=("order",) if kw.get("order") in (None, "C") else ())
     return SymArray(_obj(a)).reshape(shape)
 
 
 @_implements(np.ravel)
 def _np_ravel(a, **kw):
+    SymArray._only_defaults("ravel", kw, ignore=("order",) if kw.get("order") in (None, "C") else ())
     return SymArray(_obj(a)).ravel()
 
 
@@ -510,16 +540,19 @@ def _np_transpose(a, axes=None):
 
 @_implements(np.stack)
 def _np_stack(arrays, axis=0, **kw):
+    SymArray._only_defaults("stack", kw)
     return SymArray(np.stack([_obj(a) for a in arrays], axis=axis))
 
 
 @_implements(np.concatenate)
 def _np_concatenate(arrays, axis=0, **kw):
+    SymArray._only_defaults("concatenate", kw)
     return SymArray(np.concatenate([np.atleast_1d(_obj(a)) for a in arrays], axis=axis))
 
 
 @_implements(np.dot, np.vdot, np.inner)
 def _np_dot(a, b, **kw):
+    SymArray._only_defaults("dot", kw)
     a, b = _obj(a), _obj(b)
     if a.ndim != 1 or b.ndim != 1:
         raise UnsupportedStencilError("np.dot on the window is only supported for 1-D operands")
