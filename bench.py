@@ -135,27 +135,6 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm), "window": window}
 
 
-def bind_to_gpu_numa_node(index):
-    """Pin this rank to the CPUs NVML reports as local to its GPU BEFORE any pinned buffer is allocated,
-    so the staging memory is first-touched on the GPU's own NUMA node.  With 8 ranks whose pinned buffers
-    all live on one socket, half of the PCIe traffic crosses the inter-socket link (measured: e2e
-    16.6 GLUP/s on 8 GPUs unbound).  Returns the number of CPUs bound to, or None."""
-    try:
-        import pynvml
-        pynvml.nvmlInit()
-        h = pynvml.nvmlDeviceGetHandleByIndex(index)
-        ncpu = os.cpu_count() or 1
-        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
-        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
-        cpus &= set(os.sched_getaffinity(0))
-        if cpus:
-            os.sched_setaffinity(0, cpus)
-            return len(cpus)
-    except Exception:
-        pass
-    return None
-
-
 def host_threads():
     """All host threads this process may use (torchrun exports OMP_NUM_THREADS=1: ignore it)."""
     try:
@@ -258,10 +237,12 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    numa_cpus = bind_to_gpu_numa_node(local) if world > 1 else None
+    # NCCL prints its version banner on stdout when the first communicator is created: everything this process
+    # writes goes to stderr until rank 0 prints its ONE JSON line
+    sys.stdout.flush()
+    stdout_fd = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
-        # keep NCCL's version banner / logs off stdout: rank 0 prints ONE JSON line there
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     _lib.load()  # no extension -> fail loudly, there is no fallback
 
@@ -383,8 +364,7 @@ def run_ours(args):
     e2e = {"value": world * (N - 2) * (N - 2) / dt / 1e9, "unit": UNIT, "h2d_bytes_per_step": int(x_host.nbytes) * world,
            "d2h_bytes_per_step": int(y_host.nbytes) * world, "steps": e2e_steps, "ms_per_step": dt * 1e3,
            "api": "kernex_b200.kmap(kernel_size=(3,3), padding='valid', relative=True)(laplacian)(numpy_array), "
-                  "one (16384, 16384) pinned host grid per rank; wall clock, max over ranks",
-           "rank_cpu_binding": numa_cpus}
+                  "one (16384, 16384) pinned host grid per rank; wall clock, max over ranks"}
     if world == 1:
         # ---- CPU baseline on the host cores (rank 0, N = 1 only) ---------------------------
         arms = CpuArms(x_host)
@@ -412,7 +392,10 @@ def run_ours(args):
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
             "clocks": clocks.summary(), "parity_check": parity,
         }
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.dup2(stdout_fd, 1)
+        print(json.dumps(line), flush=True)
+        os.dup2(2, 1)   # anything printed during teardown stays off stdout as well
     if world > 1:
         dist.destroy_process_group()
 

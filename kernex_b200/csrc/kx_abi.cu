@@ -138,6 +138,7 @@ int kx_map(const KxGeom* geom, const KxProgram* prog, const void* in, const void
   if (rc) return rc;
   if (batch < 1) return fail(KX_ERR_INVALID, "batch=%lld", (long long)batch);
   if (!in || !out) return fail(KX_ERR_INVALID, "null device pointer");
+  DeviceGuard guard(out);
   MapArgs a;
   fill_map_args(a, *geom, *prog, in, coef_dev, coef_batch_stride, out, batch);
   if (a.n_win == 0) return KX_OK;
@@ -154,6 +155,7 @@ int kx_map_offset(const KxGeom* geom, const KxProgram* prog, const void* in, con
   for (int f = 0; f < prog->n_funcs; ++f)
     if (prog->func[f].kind == KX_GATHER && prog->func[f].tap_end - prog->func[f].tap_begin != 1)
       return fail(KX_ERR_INVALID, "offset map output must be scalar");
+  DeviceGuard guard(out);
   cudaStream_t s = (cudaStream_t)stream;
   const int64_t in_elems = prod(geom->in_shape, geom->ndim);
   if (in_elems <= 0) return KX_OK;
@@ -205,6 +207,7 @@ int kx_map_vjp_input(const KxGeom* geom, const KxProgram* prog, const void* g, c
   if (prog->n_funcs != 1 || prog->func[0].kind != KX_AFFINE || geom->in_dtype != KX_F32 || geom->out_dtype != KX_F32)
     return fail(KX_ERR_UNSUPPORTED, "VJP is implemented for single-function float32 AFFINE programs");
   if (!g || !dx) return fail(KX_ERR_INVALID, "null device pointer");
+  DeviceGuard guard(dx);
   static thread_local KxGeom gt;
   static thread_local KxProgram pt;
   const int first = prog->func[0].tap_begin;
@@ -230,6 +233,7 @@ int kx_map_vjp_coef(const KxGeom* geom, const KxProgram* prog, const void* x, co
   if (prog->n_funcs != 1 || prog->func[0].kind != KX_AFFINE || geom->in_dtype != KX_F32 || geom->out_dtype != KX_F32)
     return fail(KX_ERR_UNSUPPORTED, "VJP is implemented for single-function float32 AFFINE programs");
   if (!x || !g || !scratch || !dcoef) return fail(KX_ERR_INVALID, "null device pointer");
+  DeviceGuard guard(dcoef);
   rc = try_conv_wgrad(*geom, *prog, x, g, scratch, dcoef, (cudaStream_t)stream);
   if (rc != KX_ERR_UNSUPPORTED) return rc;
   return launch_generic_vjp_coef(*geom, *prog, x, g, scratch, dcoef, (cudaStream_t)stream);
@@ -249,6 +253,7 @@ int kx_scan(const KxGeom* geom, const KxProgram* prog, const void* in, const voi
     if (prog->func[f].kind == KX_GATHER && prog->func[f].tap_end - prog->func[f].tap_begin != 1)
       return fail(KX_ERR_INVALID, "scan operation output must be scalar");
   if (!in || !out || !state) return fail(KX_ERR_INVALID, "null device pointer");
+  DeviceGuard guard(out);
   cudaStream_t s = (cudaStream_t)stream;
   rc = try_scan_rowmarch(*geom, *prog, in, coef_dev, out, reverse, s);
   if (rc != KX_ERR_UNSUPPORTED) return rc;
@@ -267,6 +272,7 @@ int kx_scan_rowmarch_shard(const KxGeom* geom, const KxProgram* prog, int64_t co
   if (geom->ndim != 2 || col_base + geom->in_shape[1] > global_nx + (int64_t)geom->in_shape[0] * 4 || global_nx < 1)
     return fail(KX_ERR_INVALID, "shard [%lld, %lld) does not belong to a scan of width %lld", (long long)col_base,
                 (long long)(col_base + (geom->ndim == 2 ? geom->in_shape[1] : 0)), (long long)global_nx);
+  DeviceGuard guard(out);
   rc = scan_rowmarch_shard(*geom, *prog, nullptr, out, 0, col_base, global_nx, (cudaStream_t)stream, 0, -1);
   if (rc == KX_ERR_UNSUPPORTED)
     return fail(KX_ERR_UNSUPPORTED,
@@ -285,6 +291,7 @@ int kx_scan_rowmarch_shard_rows(const KxGeom* geom, const KxProgram* prog, int64
   if (geom->ndim != 2 || global_nx < 1 || row_begin < 0 || row_end > geom->in_shape[0] || row_begin > row_end)
     return fail(KX_ERR_INVALID, "rows [%d, %d) of a %lld-row shard", row_begin, row_end,
                 (long long)(geom->ndim == 2 ? geom->in_shape[0] : 0));
+  DeviceGuard guard(out);
   rc = scan_rowmarch_shard(*geom, *prog, nullptr, out, 0, col_base, global_nx, (cudaStream_t)stream, row_begin, row_end);
   if (rc == KX_ERR_UNSUPPORTED)
     return fail(KX_ERR_UNSUPPORTED,

@@ -55,6 +55,27 @@ inline int after_launch(const char* name) {
   return KX_OK;
 }
 
+// The launchers enqueue on the caller's stream; CUDA launches go to the calling thread's CURRENT device, so
+// a caller that hands over buffers of another GPU (several GPUs in one process) would fault.  Every entry point
+// switches to the device that owns the buffer for the duration of the call and restores the previous one.
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(const void* device_ptr) {
+    cudaPointerAttributes at;
+    int cur = -1;
+    if (device_ptr && cudaPointerGetAttributes(&at, device_ptr) == cudaSuccess && at.type == cudaMemoryTypeDevice &&
+        cudaGetDevice(&cur) == cudaSuccess && cur != at.device) {
+      if (cudaSetDevice(at.device) == cudaSuccess) prev = cur;
+    }
+    cudaGetLastError();  // a host / unregistered pointer is the caller's problem, reported by the launch itself
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+  DeviceGuard(const DeviceGuard&) = delete;
+  DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+
 inline int sm_count() {
   static int n = 0;
   if (n == 0) {

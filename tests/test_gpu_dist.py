@@ -65,3 +65,19 @@ def test_slab_stencil_multi_gpu_bit_identical():
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
     assert "MISMATCH" not in res.stdout
+
+
+@pytest.mark.skipif(not torch.cuda.is_available() or torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
+def test_tensor_on_a_non_current_device(kex):
+    """Several GPUs in ONE process: the library switches to the device that owns the buffers for the call."""
+    assert torch.cuda.current_device() == 0
+    rng = np.random.default_rng(3)
+    xh = rng.standard_normal((300, 516)).astype(np.float32)
+    x1 = torch.from_numpy(xh).to("cuda:1")
+    f = kex.kmap(kernel_size=(3, 3), padding="same", relative=True)(lap)
+    y1 = f(x1)
+    assert y1.device == x1.device and torch.cuda.current_device() == 0
+    y0 = f(torch.from_numpy(xh).to("cuda:0"))
+    assert torch.equal(y1.cpu(), y0.cpu())
+    s1 = kex.kscan(kernel_size=(3, 3), padding="same", relative=True)(lambda u: 0.25 * (u[0, -1] + u[-1, 0] + u[0, 1] + u[1, 0]))
+    assert torch.equal(s1(x1).cpu(), s1(torch.from_numpy(xh).to("cuda:0")).cpu())
