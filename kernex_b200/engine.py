@@ -501,7 +501,11 @@ def kernel_map(func_map: dict, shape, kernel_size, strides, border, relative: bo
     border = tuple(tuple(b) for b in border)
     _validate(shape, kernel_size, strides, border)
 
+    folded = _fold_leading_axes(func_map, shape, kernel_size, strides, border, relative)
+
     def call(array, *a, **k):
+        if folded is not None:
+            return folded(array, *a, **k)
         piped = _try_host_pipeline(func_map, shape, kernel_size, strides, border, relative, array, a, k)
         if piped is not None:
             return piped
@@ -509,6 +513,41 @@ def kernel_map(func_map: dict, shape, kernel_size, strides, border, relative: bo
         return arr.give_back(out)
 
     return call
+
+
+def _fold_leading_axes(func_map, shape, kernel_size, strides, border, relative):
+    """Arrays of rank > KX_MAX_DIMS: leading axes with a 1-wide window (pure batch axes, e.g. (N, C, D, H, W)
+    with kernel (1, 1, 3, 3, 3)) are merged into ONE batch axis on the host; the kernels fold that axis into
+    their batch grid dimension.  Only single-function maps (region keys could constrain the merged axes)."""
+    nd = len(shape)
+    if nd <= _lib.KX_MAX_DIMS:
+        return None
+    n_fold = nd - _lib.KX_MAX_DIMS + 1
+    pure = all(kernel_size[d] == 1 and strides[d] == 1 and tuple(border[d]) == (0, 0) for d in range(n_fold))
+    if not pure or any(v != () for v in func_map.values()):
+        raise UnsupportedStencilError(
+            f"arrays of rank > {_lib.KX_MAX_DIMS} need leading axes with a 1-wide window (pure batch axes) and a single function")
+    lead = int(np.prod(shape[:n_fold]))
+    shape2 = (lead,) + tuple(shape[n_fold:])
+    fmap2 = {}
+    for f in func_map:
+        def lifted(w, *a, _f=f, _n=n_fold, **k):
+            return _f(w.reshape((1,) * _n + tuple(w.shape[1:])), *a, **k)
+        fmap2[lifted] = ()
+    inner = kernel_map(fmap2, shape2, (1,) + tuple(kernel_size[n_fold:]), (1,) + tuple(strides[n_fold:]),
+                       ((0, 0),) + tuple(border[n_fold:]), relative)
+    return _FoldedCall(inner, shape, shape2, n_fold)
+
+
+class _FoldedCall:
+    def __init__(self, inner, shape, shape2, n_fold):
+        self.inner, self.shape, self.shape2, self.n_fold = inner, tuple(shape), tuple(shape2), n_fold
+
+    def __call__(self, array, *a, **k):
+        if tuple(array.shape) != self.shape:
+            raise ValueError(f"array shape {tuple(array.shape)} != declared shape {self.shape}")
+        out = self.inner(array.reshape(self.shape2), *a, **k)
+        return out.reshape(self.shape[:self.n_fold] + tuple(out.shape[1:]))
 
 
 def _try_host_pipeline(func_map, shape, kernel_size, strides, border, relative, array, a, k):

@@ -216,3 +216,22 @@ def test_readme_gaussian_blur(kex, ksize):
     taps = [(a, b) for a in range(ksize) for b in range(ksize)]
     oracle = ko.affine_map(image, (ksize, ksize), (1, 1), ((pad, pad), (pad, pad)), taps, [float(w[t]) for t in taps])
     np.testing.assert_allclose(got, oracle, rtol=1e-5, atol=1e-5)
+
+
+def test_rank5_array_with_batch_axes(kex):
+    """(N, C, D, H, W) with kernel (1, 1, 3, 3, 3): the two leading 1-wide axes are merged into one batch axis."""
+    rng = np.random.default_rng(77)
+    x = rng.standard_normal((2, 3, 6, 10, 16)).astype(np.float32)
+    f = lambda v: (v[0, 0, 1, 0, 0] + v[0, 0, -1, 0, 0] + v[0, 0, 0, 1, 0] + v[0, 0, 0, -1, 0] + v[0, 0, 0, 0, 1]
+                   + v[0, 0, 0, 0, -1] - 6 * v[0, 0, 0, 0, 0])
+    got = kex.kmap(kernel_size=(1, 1, 3, 3, 3), padding=(0, 0, "same", "same", "same"), relative=True)(f)(x)
+    assert got.shape == x.shape
+    taps = [(2, 1, 1), (0, 1, 1), (1, 2, 1), (1, 0, 1), (1, 1, 2), (1, 1, 0), (1, 1, 1)]
+    for n in range(2):
+        for c in range(3):
+            want = ko.affine_map(x[n, c], (3, 3, 3), (1, 1, 1), ((1, 1),) * 3, taps, [1, 1, 1, 1, 1, 1, -6])
+            np.testing.assert_allclose(got[n, c], want, rtol=1e-5, atol=1e-5)
+    p = kex.kmap(kernel_size=(1, 1, 1, 2, 2), strides=(1, 1, 1, 2, 2))(lambda v: np.max(v))(x)   # pooling over (H, W)
+    np.testing.assert_array_equal(p, x.reshape(2, 3, 6, 5, 2, 8, 2).max(axis=(4, 6)))
+    with pytest.raises(kex.UnsupportedStencilError):
+        kex.kmap(kernel_size=(2, 1, 3, 3, 3), padding="same")(lambda v: np.sum(v))(x)              # 4 windowed axes + 1
