@@ -12,10 +12,12 @@
 //   * row part of every key (plus the leading batch axes), per row of the band: a 32-bit mask in
 //     shared memory, computed once per block;
 //   * per output: m = row_mask & col_mask, function = m ? func_of_key[31 - clz(m)] : 0.
-// When the thread's 4 columns agree (everywhere except at vertical region boundaries) only that
-// function is evaluated, with its coefficients as constant-bank FFMA operands; otherwise every
-// function is evaluated and selected per column.  Accumulation order: bias, then the window in
-// row-major order (as kx_stencil2d.cu).
+// A thread keeps the coefficients (bias, KY*KX taps, tap mask) of ONE function in registers: the one its 4
+// columns agree on, reloaded from the parameter bank only when the selection changes (at region boundaries).
+// Inside a region the row loop is therefore the plain stencil loop with register coefficients, whatever the
+// number of functions; a thread whose columns disagree (vertical region boundary) evaluates each column with
+// that column's own coefficients.  Accumulation order: bias, then the window in row-major order (as
+// kx_stencil2d.cu).
 #include "kx_internal.cuh"
 
 namespace kx {
@@ -24,7 +26,7 @@ namespace {
 
 constexpr int kMT = 128;        // threads per block
 constexpr int kMCols = 4;
-constexpr int kMaxNF = 4;       // functions per mesh on this path
+constexpr int kMaxNF = KX_MAX_FUNCS;   // functions per mesh on this path
 constexpr int kMaxTH = 32;      // rows per band
 
 template <typename T>
@@ -60,29 +62,8 @@ __device__ __forceinline__ void ld4(const T* p, T (&d)[4]) {
   d[3] = reinterpret_cast<const T&>(raw.w);
 }
 
-// value of function F at column i from the register queue rows q[u .. u+KY-1]
-template <typename T, int KY, int KX, int SHIFT, int NE, int F>
-__device__ __forceinline__ T eval_one(const MeshArgs<T>& a, const T (*q)[NE], int u, int i) {
-  T acc = a.bias[F];
-#pragma unroll
-  for (int ky = 0; ky < KY; ++ky)
-#pragma unroll
-    for (int kx = 0; kx < KX; ++kx)
-      if (a.mask[F] & (1u << (ky * KX + kx))) acc = mad_wrap(a.coef[F][ky * KX + kx], q[u + ky][SHIFT + kx + i], acc);
-  return acc;
-}
-
-template <typename T, int KY, int KX, int SHIFT, int NE, int NF>
-__device__ __forceinline__ T eval_sel(const MeshArgs<T>& a, const T (*q)[NE], int u, int i, int f) {
-  T v = eval_one<T, KY, KX, SHIFT, NE, 0>(a, q, u, i);
-  if (NF > 1 && f == 1) v = eval_one<T, KY, KX, SHIFT, NE, 1>(a, q, u, i);
-  if (NF > 2 && f == 2) v = eval_one<T, KY, KX, SHIFT, NE, 2>(a, q, u, i);
-  if (NF > 3 && f == 3) v = eval_one<T, KY, KX, SHIFT, NE, 3>(a, q, u, i);
-  return v;
-}
-
 // VW = 4: rows 16-byte aligned (SHIFT = (-lx) mod 4); VW = 1: scalar loads (SHIFT = 0)
-template <typename T, int KY, int KX, int SHIFT, int VW, int NF>
+template <typename T, int KY, int KX, int SHIFT, int VW>
 __global__ void __launch_bounds__(kMT)
 stencil2d_mesh_kernel(const __grid_constant__ MeshArgs<T> a) {
   constexpr int NV = (SHIFT + KX + kMCols - 1 + VW - 1) / VW;
@@ -159,6 +140,11 @@ stencil2d_mesh_kernel(const __grid_constant__ MeshArgs<T> a) {
 #pragma unroll
   for (int ky = 0; ky < KY - 1; ++ky) load_row(r0 - a.ly + ky, q[ky]);
   int f[kMCols] = {0, 0, 0, 0};       // function of each owned column in the current row
+  int cur_f = -1;                     // function whose coefficients sit in cb / cc / cm
+  T cb = T(0), cc[KY * KX];
+  uint32_t cm = 0;
+#pragma unroll
+  for (int t = 0; t < KY * KX; ++t) cc[t] = T(0);
   uint32_t rm_prev = 0;               // row mask the selection was computed for
   bool have_sel = false;
 
@@ -181,24 +167,37 @@ stencil2d_mesh_kernel(const __grid_constant__ MeshArgs<T> a) {
         }
         T acc[kMCols];
         if (f[0] == f[1] && f[1] == f[2] && f[2] == f[3]) {
-          // one function for the whole thread row: evaluate only it (uniform inside regions)
-          const int fs = f[0];
-          if (NF > 3 && fs == 3) {
+          if (f[0] != cur_f) {   // entering another region: this thread's coefficient registers follow
+            cur_f = f[0];
+            cb = a.bias[cur_f];
+            cm = a.mask[cur_f];
 #pragma unroll
-            for (int i = 0; i < kMCols; ++i) acc[i] = eval_one<T, KY, KX, SHIFT, NE, 3>(a, q, u, i);
-          } else if (NF > 2 && fs == 2) {
-#pragma unroll
-            for (int i = 0; i < kMCols; ++i) acc[i] = eval_one<T, KY, KX, SHIFT, NE, 2>(a, q, u, i);
-          } else if (NF > 1 && fs == 1) {
-#pragma unroll
-            for (int i = 0; i < kMCols; ++i) acc[i] = eval_one<T, KY, KX, SHIFT, NE, 1>(a, q, u, i);
-          } else {
-#pragma unroll
-            for (int i = 0; i < kMCols; ++i) acc[i] = eval_one<T, KY, KX, SHIFT, NE, 0>(a, q, u, i);
+            for (int t = 0; t < KY * KX; ++t) cc[t] = a.coef[cur_f][t];
           }
-        } else {
 #pragma unroll
-          for (int i = 0; i < kMCols; ++i) acc[i] = eval_sel<T, KY, KX, SHIFT, NE, NF>(a, q, u, i, f[i]);
+          for (int i = 0; i < kMCols; ++i) acc[i] = cb;
+#pragma unroll
+          for (int ky = 0; ky < KY; ++ky)
+#pragma unroll
+            for (int kx = 0; kx < KX; ++kx)
+              if (cm & (1u << (ky * KX + kx))) {
+#pragma unroll
+                for (int i = 0; i < kMCols; ++i) acc[i] = mad_wrap(cc[ky * KX + kx], q[u + ky][SHIFT + kx + i], acc[i]);
+              }
+        } else {
+          // vertical region boundary inside the thread's 4 columns: every column with its own function
+#pragma unroll
+          for (int i = 0; i < kMCols; ++i) {
+            const int fi = f[i];
+            const uint32_t m = a.mask[fi];
+            T v = a.bias[fi];
+#pragma unroll
+            for (int ky = 0; ky < KY; ++ky)
+#pragma unroll
+              for (int kx = 0; kx < KX; ++kx)
+                if (m & (1u << (ky * KX + kx))) v = mad_wrap(a.coef[fi][ky * KX + kx], q[u + ky][SHIFT + kx + i], v);
+            acc[i] = v;
+          }
         }
         T* o = out + (int64_t)(r + u) * a.wout + j0;
         const uintptr_t addr = reinterpret_cast<uintptr_t>(o);
@@ -224,22 +223,15 @@ stencil2d_mesh_kernel(const __grid_constant__ MeshArgs<T> a) {
   }
 }
 
-template <typename T, int KY, int KX, int NF>
-int launch_mesh_nf(const MeshArgs<T>& a, dim3 grid, bool vec, cudaStream_t s) {
-  const int shift = vec ? (((-a.lx) % 4) + 4) % 4 : 0;
-  if (!vec) stencil2d_mesh_kernel<T, KY, KX, 0, 1, NF><<<grid, kMT, 0, s>>>(a);
-  else if (shift == 0) stencil2d_mesh_kernel<T, KY, KX, 0, 4, NF><<<grid, kMT, 0, s>>>(a);
-  else if (shift == 1) stencil2d_mesh_kernel<T, KY, KX, 1, 4, NF><<<grid, kMT, 0, s>>>(a);
-  else if (shift == 2) stencil2d_mesh_kernel<T, KY, KX, 2, 4, NF><<<grid, kMT, 0, s>>>(a);
-  else stencil2d_mesh_kernel<T, KY, KX, 3, 4, NF><<<grid, kMT, 0, s>>>(a);
-  return after_launch("stencil2d_mesh_kernel");
-}
-
 template <typename T, int KY, int KX>
 int launch_mesh(const MeshArgs<T>& a, dim3 grid, bool vec, cudaStream_t s) {
-  if (a.n_funcs <= 2) return launch_mesh_nf<T, KY, KX, 2>(a, grid, vec, s);
-  if (a.n_funcs == 3) return launch_mesh_nf<T, KY, KX, 3>(a, grid, vec, s);
-  return launch_mesh_nf<T, KY, KX, 4>(a, grid, vec, s);
+  const int shift = vec ? (((-a.lx) % 4) + 4) % 4 : 0;
+  if (!vec) stencil2d_mesh_kernel<T, KY, KX, 0, 1><<<grid, kMT, 0, s>>>(a);
+  else if (shift == 0) stencil2d_mesh_kernel<T, KY, KX, 0, 4><<<grid, kMT, 0, s>>>(a);
+  else if (shift == 1) stencil2d_mesh_kernel<T, KY, KX, 1, 4><<<grid, kMT, 0, s>>>(a);
+  else if (shift == 2) stencil2d_mesh_kernel<T, KY, KX, 2, 4><<<grid, kMT, 0, s>>>(a);
+  else stencil2d_mesh_kernel<T, KY, KX, 3, 4><<<grid, kMT, 0, s>>>(a);
+  return after_launch("stencil2d_mesh_kernel");
 }
 
 template <typename T>
