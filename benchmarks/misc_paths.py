@@ -85,3 +85,7 @@ if want("mesh"):
     y = F(x)
     med, _ = timeit(lambda: F(x), 6)
     rep("kmap mesh, 3 region functions, 8192^2", x.numel() * 8, med, y.numel())
+    f1 = kex.kmap(kernel_size=(3, 3), padding="same", relative=True)(lambda v: v[1, 0] + v[0, -1] - 4 * v[0, 0] + v[0, 1] + v[-1, 0])
+    y = f1(x)
+    med, _ = timeit(lambda: f1(x), 6)
+    rep("single-function Laplacian 'same' on the same 8192^2 grid (calibration)", x.numel() * 8, med, y.numel())

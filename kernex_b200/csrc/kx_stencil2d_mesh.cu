@@ -46,10 +46,16 @@ struct MeshArgs {
   KxKey key[KX_MAX_KEYS];
 };
 
-__device__ __forceinline__ bool item_match(const KxKeyItem& it, int64_t c) {
-  if (it.kind == KX_KEY_EQ) return c == it.a;
+// the coordinates fit 31 bits (checked by the launcher); slices arrive as (start, end, step) with step 1 in the
+// common case, so the division is skipped for it (a 64-bit modulo costs ~100 instructions per key and column)
+__device__ __forceinline__ bool item_match(const KxKeyItem& it, int c) {
+  if (it.kind == KX_KEY_EQ) return (int64_t)c == it.a;
   if (it.kind == KX_KEY_RANGE) return (it.a <= c) && (c < it.b);
-  if (it.kind == KX_KEY_RANGE_STEP) return (it.a <= c) && (c < it.b) && (c % it.step == 0);
+  if (it.kind == KX_KEY_RANGE_STEP) {
+    if (!((it.a <= c) && (c < it.b))) return false;
+    if (it.step == 1 || it.step == -1) return true;
+    return c % it.step == 0;   // C remainder: exact test for negative coordinates too
+  }
   return true;
 }
 
@@ -79,11 +85,11 @@ stencil2d_mesh_kernel(const __grid_constant__ MeshArgs<T> a) {
 
   // ---- row part of the keys (and the leading axes), once per block ----
   if (tid < a.th) {
-    const int64_t rc = (int64_t)(r0 + tid) - a.ly + cy;     // window-centre row in array coordinates
-    int64_t lead[KX_MAX_DIMS] = {0, 0, 0, 0};
+    const int rc = (r0 + tid) - a.ly + cy;                  // window-centre row in array coordinates
+    int lead[KX_MAX_DIMS] = {0, 0, 0, 0};
     int64_t b = blockIdx.z;
     for (int d = a.ndim - 3; d >= 0; --d) {
-      lead[d] = b % a.lead_shape[d];
+      lead[d] = (int)(b % a.lead_shape[d]);
       b /= a.lead_shape[d];
     }
     uint32_t m = 0;
@@ -102,11 +108,11 @@ stencil2d_mesh_kernel(const __grid_constant__ MeshArgs<T> a) {
   uint32_t col_mask[kMCols];
 #pragma unroll
   for (int i = 0; i < kMCols; ++i) {
-    const int64_t cc = (int64_t)(j0 + i) - a.lx + cx;
+    const int ccol = (j0 + i) - a.lx + cx;
     uint32_t m = 0;
     for (int k = 0; k < a.n_keys; ++k) {
       const KxKey& key = a.key[k];
-      if (a.ax >= key.n_items || item_match(key.item[a.ax], cc)) m |= 1u << k;
+      if (a.ax >= key.n_items || item_match(key.item[a.ax], ccol)) m |= 1u << k;
     }
     col_mask[i] = m;
   }
