@@ -89,3 +89,18 @@ if want("mesh"):
     y = f1(x)
     med, _ = timeit(lambda: f1(x), 6)
     rep("single-function Laplacian 'same' on the same 8192^2 grid (calibration)", x.numel() * 8, med, y.numel())
+
+if want("dense3d"):
+    n = 1024
+    x = torch.randn((n, n, n), device=dev, generator=g)
+    w = np.random.default_rng(1).standard_normal((3, 3, 3)).astype(np.float32)
+    f = kex.kmap(kernel_size=(3, 3, 3), padding="same")(lambda v: np.sum(v * w))
+    y = f(x)
+    med, _ = timeit(lambda: f(x), 4)
+    rep("dense 27-point 3-D stencil (host weights) 'same' on 1024^3", x.numel() * 8, med, y.numel())
+    f2 = kex.kmap(kernel_size=(3, 3, 3), strides=(2, 2, 2))(lambda v: np.max(v))
+    y = f2(x)
+    med, _ = timeit(lambda: f2(x), 3)
+    rep("3-D maxpool 3x3x3 s2 on 1024^3", x.numel() * 4 + y.numel() * 4, med, y.numel())
+    del x, y
+    torch.cuda.empty_cache()
