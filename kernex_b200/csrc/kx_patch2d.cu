@@ -31,6 +31,7 @@ struct P2Args {
   int64_t in_batch, out_batch;
   int hin, win, hout, wout;
   int ly, lx, th;
+  int aligned;         // input rows 16-byte aligned: the warp-independent kernel applies
 };
 
 template <int KY, int KX, bool ROLLED>
@@ -130,8 +131,134 @@ patch2d_kernel(const __grid_constant__ P2Args a) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Warp-independent variant for 16-byte aligned input rows (KX <= 3): no block barriers at all.
+// A warp owns 128 consecutive windows of a row and marches down the band.  Input: every lane
+// loads only the aligned vector of its own 4 columns per new row (prefetched one row ahead), the x
+// halo comes from the neighbouring lanes by shuffle (edge lanes: scalar loads); the last KY rows
+// live in registers.  Output: the lane's 4 * KY*KX words go to a warp-private staging buffer
+// (conflict-free 128-bit stores; double buffered, so ONE __syncwarp per row) and the warp writes
+// its 128 * KY*KX contiguous words with fully coalesced 128-bit streaming stores.
+template <int KY, int KX, bool ROLLED, int LX>
+__global__ void __launch_bounds__(kPT)
+patch2d_warp_kernel(const __grid_constant__ P2Args a) {
+  constexpr int NT = KY * KX;
+  constexpr int NC = KX + kWPT - 1;                 // input columns a lane needs per row (<= 6)
+  constexpr int RX = KX - 1 - LX;                   // columns needed right of the lane's vector
+  __shared__ __align__(16) uint32_t stage[kPT / 32][2][128 * NT];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int x0 = (blockIdx.x * (kPT / 32) + warp) * 128;     // first window of the warp
+  const int j0 = x0 + 4 * lane;                               // first window (= aligned input column) of the lane
+  const int r0 = blockIdx.y * a.th, r1 = min(r0 + a.th, a.hout);
+  const uint32_t* __restrict__ in = a.in + (int64_t)blockIdx.z * a.in_batch;
+  uint32_t* __restrict__ out = a.out + (int64_t)blockIdx.z * a.out_batch;
+  if (x0 >= a.wout) return;                                    // whole warp outside (warp-uniform)
+  const int nwin = min(128, a.wout - x0);
+  const int count = nwin * NT;                                 // output words of the warp per row
+  const bool first = lane == 0, last = lane == 31;
+
+  // input columns j0-LX .. j0-LX+NC-1 of row iy, as raw 32-bit words (zero outside the array)
+  struct Raw {
+    uint32_t v[4], el[LX > 0 ? LX : 1], er[RX > 0 ? RX : 1];
+  };
+  auto fetch = [&](int iy, Raw& r) {
+    const bool row_ok = (iy >= 0) && (iy < a.hin);
+    const uint32_t* rp = in + (int64_t)iy * a.win;
+    if (row_ok && j0 + 3 < a.win) {
+      const uint4 q = __ldg(reinterpret_cast<const uint4*>(rp + j0));
+      r.v[0] = q.x; r.v[1] = q.y; r.v[2] = q.z; r.v[3] = q.w;
+    } else {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) r.v[e] = (row_ok && j0 + e < a.win) ? __ldg(rp + j0 + e) : 0u;
+    }
+#pragma unroll
+    for (int k = 0; k < LX; ++k) {
+      const int c = j0 - LX + k;
+      r.el[k] = (first && row_ok && c >= 0 && c < a.win) ? __ldg(rp + c) : 0u;
+    }
+#pragma unroll
+    for (int k = 0; k < RX; ++k) {
+      const int c = j0 + 4 + k;
+      r.er[k] = (last && row_ok && c < a.win) ? __ldg(rp + c) : 0u;
+    }
+  };
+  auto assemble = [&](const Raw& r, uint32_t (&e)[NC]) {
+#pragma unroll
+    for (int k = 0; k < LX; ++k) {
+      const uint32_t up = __shfl_up_sync(0xffffffffu, r.v[4 - LX + k], 1);
+      e[k] = first ? r.el[k] : up;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) e[LX + k] = r.v[k];
+#pragma unroll
+    for (int k = 0; k < RX; ++k) {
+      const uint32_t dn = __shfl_down_sync(0xffffffffu, r.v[k], 1);
+      e[LX + 4 + k] = last ? r.er[k] : dn;
+    }
+  };
+
+  uint32_t q[KY][NC];
+#pragma unroll
+  for (int ky = 0; ky < KY - 1; ++ky) {
+    Raw t;
+    fetch(r0 - a.ly + ky, t);
+    assemble(t, q[ky]);
+  }
+  Raw nxt;
+  fetch(r0 - a.ly + KY - 1, nxt);
+  uint32_t* dst = out + ((int64_t)r0 * a.wout + x0) * NT;
+  const int64_t dst_pitch = (int64_t)a.wout * NT;
+  for (int r = r0; r < r1; ++r) {
+    assemble(nxt, q[KY - 1]);
+    if (r + 1 < r1) fetch(r + 1 - a.ly + KY - 1, nxt);          // in flight while this row is built and written
+    uint32_t o[kWPT * NT];
+#pragma unroll
+    for (int w = 0; w < kWPT; ++w)
+#pragma unroll
+      for (int ty = 0; ty < KY; ++ty)
+#pragma unroll
+        for (int tx = 0; tx < KX; ++tx) {
+          const int sy = ROLLED ? (ty + (KY - 1) / 2) % KY : ty;
+          const int sx = ROLLED ? (tx + (KX - 1) / 2) % KX : tx;
+          o[w * NT + ty * KX + tx] = q[sy][w + sx];
+        }
+    uint32_t* sb = stage[warp][(r - r0) & 1];
+    uint32_t* sp = sb + lane * (kWPT * NT);
+#pragma unroll
+    for (int k = 0; k < kWPT * NT / 4; ++k)
+      *reinterpret_cast<uint4*>(sp + 4 * k) = make_uint4(o[4 * k], o[4 * k + 1], o[4 * k + 2], o[4 * k + 3]);
+    __syncwarp();
+    if (count == 128 * NT && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+#pragma unroll
+      for (int k = 0; k < NT; ++k)
+        __stcs(reinterpret_cast<uint4*>(dst) + lane + 32 * k, *reinterpret_cast<const uint4*>(sb + 4 * (lane + 32 * k)));
+    } else {
+      for (int i = lane; i < count; i += 32) dst[i] = sb[i];
+    }
+    dst += dst_pitch;
+#pragma unroll
+    for (int ky = 0; ky < KY - 1; ++ky)
+#pragma unroll
+      for (int e = 0; e < NC; ++e) q[ky][e] = q[ky + 1][e];
+  }
+}
+
+template <int KY, int KX, bool ROLLED>
+int launch_p2_warp(const P2Args& a, int64_t batch, cudaStream_t s) {
+  dim3 grid((a.wout + kTW - 1) / kTW, (a.hout + a.th - 1) / a.th, (unsigned)batch);
+  if (a.lx == 0) patch2d_warp_kernel<KY, KX, ROLLED, 0><<<grid, kPT, 0, s>>>(a);
+  else if (KX >= 2 && a.lx == 1) patch2d_warp_kernel<KY, KX, ROLLED, (KX >= 2 ? 1 : 0)><<<grid, kPT, 0, s>>>(a);
+  else if (KX >= 3 && a.lx == 2) patch2d_warp_kernel<KY, KX, ROLLED, (KX >= 3 ? 2 : 0)><<<grid, kPT, 0, s>>>(a);
+  else return KX_ERR_UNSUPPORTED;
+  return after_launch("patch2d_kernel");
+}
+
 template <int KY, int KX>
 int launch_p2(const P2Args& a, bool rolled, int64_t batch, cudaStream_t s) {
+  if (KX <= 3 && a.aligned && a.lx >= 0 && a.lx <= KX - 1 && !getenv("KX_PATCH_BLOCK")) {
+    const int rc = rolled ? launch_p2_warp<KY, KX, true>(a, batch, s) : launch_p2_warp<KY, KX, false>(a, batch, s);
+    if (rc != KX_ERR_UNSUPPORTED) return rc;
+  }
   dim3 grid((a.wout + kTW - 1) / kTW, (a.hout + a.th - 1) / a.th, (unsigned)batch);
   if (rolled) patch2d_kernel<KY, KX, true><<<grid, kPT, 0, s>>>(a);
   else patch2d_kernel<KY, KX, false><<<grid, kPT, 0, s>>>(a);
@@ -182,6 +309,7 @@ int try_patch2d(const MapArgs& m, const KxProgram& p, cudaStream_t s) {
   a.th = a.hout >= 512 ? 16 : (a.hout >= 64 ? 8 : 4);
   while ((a.hout + a.th - 1) / a.th > 65535) a.th *= 2;
   const bool roll = !plain;
+  a.aligned = (a.win % 4 == 0) && ((reinterpret_cast<uintptr_t>(m.in) & 15) == 0) && (a.in_batch % 4 == 0);
   if (KY == 3 && KX == 3) return launch_p2<3, 3>(a, roll, batch, s);
   if (KY == 1 && KX == 3) return launch_p2<1, 3>(a, roll, batch, s);
   if (KY == 2 && KX == 2) return launch_p2<2, 2>(a, roll, batch, s);
