@@ -256,7 +256,12 @@ int launch_p2_warp(const P2Args& a, int64_t batch, cudaStream_t s) {
 template <int KY, int KX>
 int launch_p2(const P2Args& a, bool rolled, int64_t batch, cudaStream_t s) {
   if (KX <= 3 && a.aligned && a.lx >= 0 && a.lx <= KX - 1 && !getenv("KX_PATCH_BLOCK")) {
-    const int rc = rolled ? launch_p2_warp<KY, KX, true>(a, batch, s) : launch_p2_warp<KY, KX, false>(a, batch, s);
+    // short bands: measured on C3b (8192^2): th = 3..4 164 GLUP/s, 8 160, 16 155, 32 151, 128 141 -- the input is
+    // only 10 % of the traffic, so re-reading two halo rows per band costs less than the coarser write pattern
+    P2Args w = a;
+    if (!getenv("KX_PATCH_TH") && w.hout >= 64) w.th = 4;
+    while ((w.hout + w.th - 1) / w.th > 65535) w.th *= 2;
+    const int rc = rolled ? launch_p2_warp<KY, KX, true>(w, batch, s) : launch_p2_warp<KY, KX, false>(w, batch, s);
     if (rc != KX_ERR_UNSUPPORTED) return rc;
   }
   dim3 grid((a.wout + kTW - 1) / kTW, (a.hout + a.th - 1) / a.th, (unsigned)batch);
@@ -307,6 +312,7 @@ int try_patch2d(const MapArgs& m, const KxProgram& p, cudaStream_t s) {
   a.in_batch = (int64_t)a.hin * a.win;
   a.out_batch = (int64_t)a.hout * a.wout * KY * KX;
   a.th = a.hout >= 512 ? 16 : (a.hout >= 64 ? 8 : 4);
+  if (const char* e = getenv("KX_PATCH_TH")) a.th = atoi(e) > 0 ? atoi(e) : a.th;   // tuning knob
   while ((a.hout + a.th - 1) / a.th > 65535) a.th *= 2;
   const bool roll = !plain;
   a.aligned = (a.win % 4 == 0) && ((reinterpret_cast<uintptr_t>(m.in) & 15) == 0) && (a.in_batch % 4 == 0);

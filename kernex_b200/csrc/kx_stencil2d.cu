@@ -241,7 +241,9 @@ int run(const MapArgs& m, const KxProgram& p, int ay, int ax, int64_t batch, cud
     a.bx0 = (int)m.box_lo[ax];
     a.bx1 = (int)m.box_hi[ax];
   }
-  a.th = a.hout >= 512 ? 32 : (a.hout >= 64 ? 16 : 8);
+  // band height, measured on C2 (16384^2, 3x3): 4 rows 762 GLUP/s, 8 822, 12 824 (VJP 834), 16 802, 32 776, 48 761:
+  // short bands keep the concurrently active blocks on few DRAM pages and their halo re-reads in L2
+  a.th = a.hout >= 512 ? 12 : (a.hout >= 64 ? 16 : 8);
   if (const char* e = getenv("KX_S2_TH")) a.th = atoi(e) > 0 ? atoi(e) : a.th;   // tuning knob
   while ((a.hout + a.th - 1) / a.th > 65535) a.th *= 2;
   const bool dev = m.coef_dev != nullptr;

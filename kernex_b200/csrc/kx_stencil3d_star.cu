@@ -34,7 +34,7 @@ struct StarArgs {
   int64_t in_batch, out_batch;
   int din, hin, win, dout, hout, wout;
   int lz, ly, lx;
-  int nzc;
+  int nzc, zc;           // z chunks per volume, planes per chunk
   uint32_t mask;        // bit t set = tap t present; taps in row-major window order:
   T bias;               // 0:(z-1) 1:(y-1) 2:(x-1) 3:centre 4:(x+1) 5:(y+1) 6:(z+1)
   T c[7];
@@ -96,8 +96,8 @@ stencil3d_star_kernel(const __grid_constant__ StarArgs<T> a) {
 
   const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * 32 + tx;
   const int b = blockIdx.z / a.nzc;
-  const int z0 = (blockIdx.z - b * a.nzc) * kZC;
-  const int z1 = min(z0 + kZC, a.dout);
+  const int z0 = (blockIdx.z - b * a.nzc) * a.zc;
+  const int z1 = min(z0 + a.zc, a.dout);
   const int x0 = blockIdx.x * kTX, y0 = blockIdx.y * kTY;
   const T* __restrict__ in = a.in + (int64_t)b * a.in_batch;
   T* __restrict__ out = a.out + (int64_t)b * a.out_batch;
@@ -246,7 +246,9 @@ int run_star(const MapArgs& m, const KxProgram& p, int64_t batch, cudaStream_t s
   a.in_batch = (int64_t)a.din * a.hin * a.win;
   a.out_batch = (int64_t)a.dout * a.hout * a.wout;
   a.bias = (T)f.bias;
-  a.nzc = (a.dout + kZC - 1) / kZC;
+  a.zc = kZC;
+  if (const char* e = getenv("KX_STAR_ZC")) a.zc = atoi(e) > 0 ? atoi(e) : a.zc;   // tuning knob
+  a.nzc = (a.dout + a.zc - 1) / a.zc;
   const int tiles_x = (a.wout + kTX - 1) / kTX, tiles_y = (a.hout + kTY - 1) / kTY;
   if ((int64_t)a.nzc * batch > 65535 || tiles_y > 65535) return KX_ERR_UNSUPPORTED;
   dim3 grid(tiles_x, tiles_y, (unsigned)(a.nzc * batch)), block(32, kTYB);
