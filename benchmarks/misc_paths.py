@@ -98,6 +98,11 @@ if want("dense3d"):
     y = f(x)
     med, _ = timeit(lambda: f(x), 4)
     rep("dense 27-point 3-D stencil (host weights) 'same' on 1024^3", x.numel() * 8, med, y.numel())
+    xb = torch.randn((256, 2048, 2048), device=dev, generator=g)
+    yb = f(xb)
+    med, _ = timeit(lambda: f(xb), 4)
+    rep("dense 27-point 3-D stencil (host weights) 'same' on 256x2048^2", xb.numel() * 8, med, yb.numel())
+    del xb, yb
     f2 = kex.kmap(kernel_size=(3, 3, 3), strides=(2, 2, 2))(lambda v: np.max(v))
     y = f2(x)
     med, _ = timeit(lambda: f2(x), 3)

@@ -15,6 +15,7 @@
 //                        accumulates C*KY*KX partial sums in registers, blocks reduce through
 //                        shuffles + shared memory into partial[block][tap]; a second kernel sums
 //                        the partials in a fixed order (deterministic, no atomics).
+#include <algorithm>
 #include <type_traits>
 
 #include "kx_internal.cuh"
@@ -736,7 +737,109 @@ int run_fwd(const MapArgs& m, const KxProgram& p, const ConvGeom& cg, cudaStream
   return KX_ERR_UNSUPPORTED;
 }
 
+// ---- dense 3x3x3 stencils over a volume ------------------------------------------------
+// out[z, y, x] = sum_kz sum_ky sum_kx w[kz,ky,kx] * in[z+kz-lz, y+ky-ly, x+kx-lx] is the conv above with the
+// three input PLANES z-lz .. z-lz+2 as channels and one launch batch item per output plane (batch items
+// overlap: in_batch = one plane).  Consecutive output planes run back to back, so two of the three planes
+// an output plane reads are still in the 126 MB L2 from its predecessor: DRAM traffic stays 8 B per
+// lattice update, the 27 FMAs per output run as packed FFMA2.  Output planes next to a padded z face see
+// only one or two real planes: they are separate launches of the C = 1 / C = 2 instantiations on the
+// matching slice of the coefficient table (zero planes contribute nothing).
+template <typename T>
+int run_dense3d(const MapArgs& m, const KxProgram& p, int64_t batch, cudaStream_t s) {
+  const KxGeom& g = m.g;
+  const KxFunc& f = p.func[0];
+  const int nd = g.ndim, az = nd - 3, ay = nd - 2, ax = nd - 1;
+  if (f.tap_end - f.tap_begin != 27) return KX_ERR_UNSUPPORTED;
+  T coef[27];
+  uint32_t seen = 0;
+  bool fwd_order = true, rev_order = true;
+  for (int t = f.tap_begin; t < f.tap_end; ++t) {
+    const int slot = (p.tap_off[t][az] * 3 + p.tap_off[t][ay]) * 3 + p.tap_off[t][ax];
+    if (slot < 0 || slot >= 27 || (seen & (1u << slot))) return KX_ERR_UNSUPPORTED;
+    seen |= 1u << slot;
+    coef[slot] = (T)p.coef[t];
+    if (slot != t - f.tap_begin) fwd_order = false;
+    if (slot != 26 - (t - f.tap_begin)) rev_order = false;
+  }
+  if (m.coef_dev && !(fwd_order || rev_order)) return KX_ERR_UNSUPPORTED;
+  const int din = (int)g.in_shape[az], dout = (int)g.out_shape[az], lz = g.lo[az];
+  // interior planes [i0, i1) see three real input planes; the (at most four) others at least one
+  const int i0 = std::min(dout, std::max(0, lz)), i1 = std::max(i0, std::min(dout, din - 2 + lz));
+  if (i0 + (dout - i1) > 4) return KX_ERR_UNSUPPORTED;
+  for (int oz = 0; oz < dout; ++oz) {
+    if (oz == i0) oz = i1;
+    if (oz < dout && std::max(0, lz - oz) > std::min(2, din - 1 - oz + lz)) return KX_ERR_UNSUPPORTED;
+  }
+  ConvArgs<T> base;
+  memset(&base, 0, sizeof(base));
+  base.hin = (int)g.in_shape[ay];
+  base.win = (int)g.in_shape[ax];
+  base.hout = (int)g.out_shape[ay];
+  base.wout = (int)g.out_shape[ax];
+  base.ly = g.lo[ay];
+  base.lx = g.lo[ax];
+  base.plane = (int64_t)base.hin * base.win;
+  base.in_batch = base.plane;
+  base.out_batch = (int64_t)base.hout * base.wout;
+  base.th = base.hout >= 512 ? 32 : (base.hout >= 64 ? 16 : 8);
+  while ((base.hout + base.th - 1) / base.th > 65535) base.th *= 2;
+  base.bias = (T)f.bias;
+  const int tiles_x = (base.wout + kTX * kCols - 1) / (kTX * kCols);
+
+  // planes [oz0, oz1) all use window planes kz0 .. kz0 + C - 1
+  auto launch = [&](const T* in, T* out, int oz0, int oz1, int kz0, int C) -> int {
+    ConvArgs<T> a = base;
+    a.in = in + (int64_t)(oz0 - lz + kz0) * base.plane;
+    a.out = out + (int64_t)oz0 * base.out_batch;
+    for (int i = 0; i < C * 9; ++i) a.coef[i] = coef[kz0 * 9 + i];
+    if (m.coef_dev) {
+      a.coef_rev = fwd_order ? 0 : 1;
+      a.coef_dev = (const T*)m.coef_dev + (fwd_order ? kz0 * 9 : (3 - kz0 - C) * 9);
+    }
+    dim3 grid(tiles_x, (base.hout + base.th - 1) / base.th, (unsigned)(oz1 - oz0));
+    switch (C) {
+      case 1: return launch_fwd<T, 1>(a, grid, true, s);
+      case 2: return launch_fwd<T, 2>(a, grid, true, s);
+      default: return launch_fwd<T, 3>(a, grid, true, s);
+    }
+  };
+
+  for (int64_t b = 0; b < batch; ++b) {
+    const T* in = (const T*)m.in + b * (int64_t)din * base.plane;          // leading 1-wide axes are the batch
+    T* out = (T*)m.out + b * (int64_t)dout * base.out_batch;
+    for (int oz = 0; oz < dout; ++oz) {
+      if (oz == i0 && i1 > i0) {
+        for (int z = i0; z < i1; z += 65535) {
+          const int rc = launch(in, out, z, std::min(i1, z + 65535), 0, 3);
+          if (rc != KX_OK) return rc;
+        }
+        oz = i1 - 1;
+        continue;
+      }
+      const int kz0 = std::max(0, lz - oz), kz1 = std::min(2, din - 1 - oz + lz);
+      const int rc = launch(in, out, oz, oz + 1, kz0, kz1 - kz0 + 1);
+      if (rc != KX_OK) return rc;
+    }
+  }
+  return KX_OK;
+}
+
 }  // namespace
+
+// Called by try_stencil3d after the star kernel declined: dense 3x3x3 windows, unit strides, 16-byte aligned rows.
+int try_conv_dense3d(const MapArgs& m, const KxProgram& p, int64_t batch, cudaStream_t s) {
+  const KxGeom& g = m.g;
+  const int nd = g.ndim;
+  if (!conv_rows_enabled() || getenv("KX_NO_DENSE3D")) return KX_ERR_UNSUPPORTED;
+  if (g.ksize[nd - 3] != 3 || g.ksize[nd - 2] != 3 || g.ksize[nd - 1] != 3) return KX_ERR_UNSUPPORTED;
+  if (g.lo[nd - 1] < 0 || g.lo[nd - 1] > 2 || batch < 1 || batch > 8) return KX_ERR_UNSUPPORTED;
+  if (g.in_shape[nd - 1] % 4 != 0 || (reinterpret_cast<uintptr_t>(m.in) & 15) != 0) return KX_ERR_UNSUPPORTED;
+  if (g.out_shape[nd - 3] < 1 || g.out_shape[nd - 2] < 1 || g.out_shape[nd - 1] < 1) return KX_ERR_UNSUPPORTED;
+  if (g.in_dtype == KX_F32) return run_dense3d<float>(m, p, batch, s);
+  if (g.in_dtype == KX_I32 && p.func[0].coef_is_int) return run_dense3d<int32_t>(m, p, batch, s);
+  return KX_ERR_UNSUPPORTED;
+}
 
 int try_conv2d(const MapArgs& m, const KxProgram& p, cudaStream_t s) {
   const KxGeom& g = m.g;

@@ -281,6 +281,11 @@ int try_stencil3d(const MapArgs& m, const KxProgram& p, cudaStream_t s) {
     const int rc = try_stencil3d_star(m, p, batch, s);
     if (rc != KX_ERR_UNSUPPORTED) return rc;
   }
+  {
+    // dense 3x3x3 windows: the conv row-ring kernel with the three z planes as channels (kx_conv2d.cu)
+    const int rc = try_conv_dense3d(m, p, batch, s);
+    if (rc != KX_ERR_UNSUPPORTED) return rc;
+  }
   if (g.in_dtype == KX_F32) return run3<float>(m, p, batch, s);
   if (g.in_dtype == KX_I32 && p.func[0].coef_is_int) return run3<int32_t>(m, p, batch, s);
   return KX_ERR_UNSUPPORTED;

@@ -164,8 +164,73 @@ def test_stencil3d_random_geometry(kex, seed):
         return acc
 
     got = kex.kernel_map({fn: ()}, (d, h, w), ks, (1, 1, 1), border, False)(x)
-    assert _last_kernel() in ("stencil3d_kernel", "stencil3d_star_kernel")
+    assert _last_kernel() in ("stencil3d_kernel", "stencil3d_star_kernel", "conv_fwd_rows_kernel")
     _check_affine(got, x, ks, (1, 1, 1), border, taps, coefs, bias)
+
+
+_DENSE3D = [((9, 37, 132), "same"), ((3, 20, 64), "same"), ((5, 18, 260), "valid"), ((4, 70, 1028), "same"),
+            ((7, 33, 136), ((2, 0), (0, 2), (1, 1))), ((6, 21, 72), ((1, 2), (2, 1), (0, 2))),
+            ((8, 19, 68), ((-1, 1), (1, -1), (2, 0))), ((1, 16, 32), "same"), ((2, 16, 32), ((2, 2), (1, 1), (1, 1))),
+            ((12, 40, 516), ((0, 1), (1, 1), (1, 1)))]
+
+
+@pytest.mark.parametrize("case", range(len(_DENSE3D)))
+@pytest.mark.parametrize("dtype", ["f32", "i32"])
+def test_dense3d_runs_on_the_conv_row_ring(kex, case, dtype):
+    """Dense 27-point windows over a volume: the conv row-ring kernel with the three z planes as channels;
+    output planes at a padded z face use the 1- and 2-plane instantiations (kx_conv2d.cu run_dense3d)."""
+    shape, pad = _DENSE3D[case]
+    rng = np.random.default_rng(7000 + case)
+    ks = (3, 3, 3)
+    border = ko.resolve_padding(pad, ks)
+    taps = list(itertools.product(range(3), range(3), range(3)))
+    if dtype == "f32":
+        x = rng.standard_normal(shape).astype(np.float32)
+        w = rng.standard_normal(ks).astype(np.float32)
+        bias = 0.25
+    else:
+        x = rng.integers(-1000, 1000, shape).astype(np.int32)
+        w = rng.integers(-9, 10, ks).astype(np.int32)
+        w[w == 0] = 3
+        bias = 0
+    coefs = [w[t].item() for t in taps]
+
+    def fn(v):
+        acc = bias
+        for t, cf in zip(taps, coefs):
+            acc = acc + cf * v[t]
+        return acc
+
+    got = kex.kernel_map({fn: ()}, shape, ks, (1, 1, 1), border, False)(x)
+    assert _last_kernel() == "conv_fwd_rows_kernel"
+    _check_affine(got, x, ks, (1, 1, 1), border, taps, coefs, bias)
+    if dtype == "f32" and shape[0] >= 3:   # runtime weights on the device (conv3d-as-kmap) and a leading batch axis
+        conv = kex.kmap(kernel_size=ks, padding=pad)(lambda v, w: np.sum(v * w))
+        got = conv(torch.from_numpy(x).cuda(), torch.from_numpy(w).cuda())
+        assert _last_kernel() == "conv_fwd_rows_kernel"
+        _check_affine(got.cpu().numpy(), x, ks, (1, 1, 1), border, taps, coefs)
+        xb = np.stack([x, x[::-1].copy()])
+        gotb = kex.kmap(kernel_size=(1,) + ks, padding=((0, 0),) + tuple(border))(lambda v: np.sum(v[0] * w))(xb)
+        assert _last_kernel() == "conv_fwd_rows_kernel"
+        for b in range(2):
+            _check_affine(gotb[b], xb[b], ks, (1, 1, 1), border, taps, coefs)
+
+
+def test_dense3d_input_vjp_runs_on_the_conv_row_ring(kex):
+    """dx of a dense 3-D stencil with device weights = the same kernel on the reversed coefficient table."""
+    rng = np.random.default_rng(17)
+    shape, ks = (6, 24, 68), (3, 3, 3)
+    taps = list(itertools.product(range(3), range(3), range(3)))
+    w = rng.standard_normal(ks).astype(np.float32)
+    x = torch.from_numpy(rng.standard_normal(shape).astype(np.float32)).cuda().requires_grad_()
+    wd = torch.from_numpy(w).cuda()
+    y = kex.kmap(kernel_size=ks, padding="same")(lambda v, w: np.sum(v * w))(x, wd)
+    g = rng.standard_normal(shape).astype(np.float32)
+    (dx,) = torch.autograd.grad(y, x, torch.from_numpy(g).cuda())
+    assert _last_kernel() == "conv_fwd_rows_kernel"
+    # transpose of a 'same' 3x3x3 stencil = the stencil with flipped taps
+    flipped = [tuple(2 - i for i in t) for t in taps]
+    _check_affine(dx.cpu().numpy(), g, ks, (1, 1, 1), ((1, 1),) * 3, flipped, [float(w[t]) for t in taps])
 
 
 def test_conv_as_kmap_config3a_shape(kex):
