@@ -18,6 +18,9 @@
 // number of functions; a thread whose columns disagree (vertical region boundary) evaluates each column with
 // that column's own coefficients.  Accumulation order: bias, then the window in row-major order (as
 // kx_stencil2d.cu).
+#include <algorithm>
+#include <climits>
+
 #include "kx_internal.cuh"
 
 namespace kx {
@@ -27,7 +30,13 @@ namespace {
 constexpr int kMT = 128;        // threads per block
 constexpr int kMCols = 4;
 constexpr int kMaxNF = KX_MAX_FUNCS;   // functions per mesh on this path
-constexpr int kMaxTH = 32;      // rows per band
+constexpr int kMaxTH = 128;     // rows per band
+
+// A region key in the form the kernel tests: per axis lo <= c < hi and c % step == 0 in 32-bit arithmetic
+// (int -> [a, a+1), slice -> [start, end) with its step, wildcard / axis not in the key -> everything).
+struct MeshKey {
+  int lo[KX_MAX_DIMS], hi[KX_MAX_DIMS], step[KX_MAX_DIMS];
+};
 
 template <typename T>
 struct MeshArgs {
@@ -43,20 +52,13 @@ struct MeshArgs {
   T bias[kMaxNF];
   T coef[kMaxNF][9];
   unsigned char key_func[KX_MAX_KEYS];
-  KxKey key[KX_MAX_KEYS];
+  MeshKey key[KX_MAX_KEYS];
 };
 
-// the coordinates fit 31 bits (checked by the launcher); slices arrive as (start, end, step) with step 1 in the
-// common case, so the division is skipped for it (a 64-bit modulo costs ~100 instructions per key and column)
-__device__ __forceinline__ bool item_match(const KxKeyItem& it, int c) {
-  if (it.kind == KX_KEY_EQ) return (int64_t)c == it.a;
-  if (it.kind == KX_KEY_RANGE) return (it.a <= c) && (c < it.b);
-  if (it.kind == KX_KEY_RANGE_STEP) {
-    if (!((it.a <= c) && (c < it.b))) return false;
-    if (it.step == 1 || it.step == -1) return true;
-    return c % it.step == 0;   // C remainder: exact test for negative coordinates too
-  }
-  return true;
+// the coordinates fit 31 bits (checked by the launcher); unit steps skip the division
+__device__ __forceinline__ bool item_match(const MeshKey& k, int d, int c) {
+  const int st = k.step[d];
+  return (c >= k.lo[d]) && (c < k.hi[d]) && (st == 1 || c % st == 0);   // C remainder: exact for negative c too
 }
 
 template <typename T>
@@ -69,12 +71,12 @@ __device__ __forceinline__ void ld4(const T* p, T (&d)[4]) {
 }
 
 // VW = 4: rows 16-byte aligned (SHIFT = (-lx) mod 4); VW = 1: scalar loads (SHIFT = 0)
-template <typename T, int KY, int KX, int SHIFT, int VW>
+// U = rows fetched back to back
+template <typename T, int KY, int KX, int SHIFT, int VW, int U>
 __global__ void __launch_bounds__(kMT)
 stencil2d_mesh_kernel(const __grid_constant__ MeshArgs<T> a) {
   constexpr int NV = (SHIFT + KX + kMCols - 1 + VW - 1) / VW;
   constexpr int NE = NV * VW;
-  constexpr int U = 2;                       // rows fetched back to back
   __shared__ uint32_t row_mask[kMaxTH];
   const int tid = threadIdx.x;
   const int j0 = (blockIdx.x * kMT + tid) * kMCols;
@@ -93,12 +95,13 @@ stencil2d_mesh_kernel(const __grid_constant__ MeshArgs<T> a) {
       b /= a.lead_shape[d];
     }
     uint32_t m = 0;
+#pragma unroll 1
     for (int k = 0; k < a.n_keys; ++k) {
-      const KxKey& key = a.key[k];
       bool ok = true;
-      for (int d = 0; d < key.n_items; ++d) {
+#pragma unroll 1
+      for (int d = 0; d < a.ndim; ++d) {
         if (d == a.ax) continue;
-        ok = ok && item_match(key.item[d], d == a.ay ? rc : lead[d]);
+        ok = ok && item_match(a.key[k], d, d == a.ay ? rc : lead[d]);
       }
       if (ok) m |= 1u << k;
     }
@@ -110,10 +113,9 @@ stencil2d_mesh_kernel(const __grid_constant__ MeshArgs<T> a) {
   for (int i = 0; i < kMCols; ++i) {
     const int ccol = (j0 + i) - a.lx + cx;
     uint32_t m = 0;
-    for (int k = 0; k < a.n_keys; ++k) {
-      const KxKey& key = a.key[k];
-      if (a.ax >= key.n_items || item_match(key.item[a.ax], ccol)) m |= 1u << k;
-    }
+#pragma unroll 1
+    for (int k = 0; k < a.n_keys; ++k)
+      if (item_match(a.key[k], a.ax, ccol)) m |= 1u << k;
     col_mask[i] = m;
   }
   __syncthreads();
@@ -229,15 +231,23 @@ stencil2d_mesh_kernel(const __grid_constant__ MeshArgs<T> a) {
   }
 }
 
+template <typename T, int KY, int KX, int U>
+int launch_mesh_v(const MeshArgs<T>& a, dim3 grid, bool vec, cudaStream_t s) {
+  const int shift = vec ? (((-a.lx) % 4) + 4) % 4 : 0;
+  if (!vec) stencil2d_mesh_kernel<T, KY, KX, 0, 1, U><<<grid, kMT, 0, s>>>(a);
+  else if (shift == 0) stencil2d_mesh_kernel<T, KY, KX, 0, 4, U><<<grid, kMT, 0, s>>>(a);
+  else if (shift == 1) stencil2d_mesh_kernel<T, KY, KX, 1, 4, U><<<grid, kMT, 0, s>>>(a);
+  else if (shift == 2) stencil2d_mesh_kernel<T, KY, KX, 2, 4, U><<<grid, kMT, 0, s>>>(a);
+  else stencil2d_mesh_kernel<T, KY, KX, 3, 4, U><<<grid, kMT, 0, s>>>(a);
+  return after_launch("stencil2d_mesh_kernel");
+}
+
+// four rows in flight per thread: 566 GLUP/s on the 3-function 8192^2 mesh, two rows 549 (KX_MESH_U=2 for A/B)
 template <typename T, int KY, int KX>
 int launch_mesh(const MeshArgs<T>& a, dim3 grid, bool vec, cudaStream_t s) {
-  const int shift = vec ? (((-a.lx) % 4) + 4) % 4 : 0;
-  if (!vec) stencil2d_mesh_kernel<T, KY, KX, 0, 1><<<grid, kMT, 0, s>>>(a);
-  else if (shift == 0) stencil2d_mesh_kernel<T, KY, KX, 0, 4><<<grid, kMT, 0, s>>>(a);
-  else if (shift == 1) stencil2d_mesh_kernel<T, KY, KX, 1, 4><<<grid, kMT, 0, s>>>(a);
-  else if (shift == 2) stencil2d_mesh_kernel<T, KY, KX, 2, 4><<<grid, kMT, 0, s>>>(a);
-  else stencil2d_mesh_kernel<T, KY, KX, 3, 4><<<grid, kMT, 0, s>>>(a);
-  return after_launch("stencil2d_mesh_kernel");
+  const char* e = getenv("KX_MESH_U");
+  if (e && atoi(e) == 2) return launch_mesh_v<T, KY, KX, 2>(a, grid, vec, s);
+  return launch_mesh_v<T, KY, KX, 4>(a, grid, vec, s);
 }
 
 template <typename T>
@@ -270,8 +280,28 @@ int run_mesh(const MapArgs& m, const KxProgram& p, cudaStream_t s) {
   a.n_funcs = p.n_funcs;
   a.n_keys = p.n_keys;
   for (int k = 0; k < p.n_keys; ++k) {
-    a.key[k] = p.key[k];
     a.key_func[k] = (unsigned char)p.key[k].func;
+    for (int d = 0; d < KX_MAX_DIMS; ++d) {
+      int64_t lo = INT32_MIN, hi = INT32_MAX, st = 1;
+      if (d < p.key[k].n_items) {
+        const KxKeyItem& it = p.key[k].item[d];
+        if (it.kind == KX_KEY_EQ) {
+          lo = it.a;
+          hi = it.a + 1;
+        } else if (it.kind == KX_KEY_RANGE || it.kind == KX_KEY_RANGE_STEP) {
+          lo = it.a;
+          hi = it.b;
+          if (it.kind == KX_KEY_RANGE_STEP) st = it.step < 0 ? -(int64_t)it.step : it.step;
+          if (st == 0) return KX_ERR_UNSUPPORTED;   // left to the generic kernel
+        }
+      }
+      lo = std::max<int64_t>(lo, INT32_MIN);
+      hi = std::min<int64_t>(hi, INT32_MAX);
+      if (lo >= hi) lo = 1, hi = 0;                 // empty range
+      a.key[k].lo[d] = (int)lo;
+      a.key[k].hi[d] = (int)hi;
+      a.key[k].step[d] = (int)st;
+    }
   }
   a.ay = ay;
   a.ax = ax;
@@ -286,8 +316,8 @@ int run_mesh(const MapArgs& m, const KxProgram& p, cudaStream_t s) {
   a.lx = g.lo[ax];
   a.in_batch = (int64_t)a.hin * a.win;
   a.out_batch = (int64_t)a.hout * a.wout;
-  // band height measured on the 3-function 8192^2 mesh: 8 rows 420 GLUP/s, 12 474, 16 503, 32 513 (region reloads
-  // amortise over the band, unlike the single-function kernel where short bands win)
+  // band height measured on the 3-function 8192^2 mesh (U = 4): 8 rows 484 GLUP/s, 12 531, 16 550, 24 563, 32 566,
+  // 48 529, 64 512, 128 400
   a.th = a.hout >= 512 ? 32 : (a.hout >= 64 ? 16 : 8);
   if (const char* e = getenv("KX_MESH_TH")) a.th = atoi(e) > 0 ? atoi(e) : a.th;
   while ((a.hout + a.th - 1) / a.th > 65535) a.th *= 2;
