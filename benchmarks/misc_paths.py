@@ -32,6 +32,25 @@ if want("pool"):
     del x, y
     torch.cuda.empty_cache()
 
+if want("wide"):
+    # window shapes / reductions the stride-1 row-march kernel learnt in r1c (before: pool2d or the generic kernel)
+    x = torch.randn((16384, 16384), device=dev, generator=g)
+    gw = np.exp(-0.5 * (np.arange(-3, 4)[:, None] ** 2 + np.arange(-3, 4)[None, :] ** 2) / 2.0).astype(np.float32)
+    gw /= gw.sum()
+    cases = [("box blur 5x5 (np.mean) same", (5, 5), lambda v: np.mean(v)),
+             ("Gaussian blur 7x7 (host weights) same", (7, 7), lambda v: np.sum(v * gw)),
+             ("max filter 3x3 same", (3, 3), lambda v: np.max(v)),
+             ("max filter 5x5 same", (5, 5), lambda v: np.max(v)),
+             ("weighted 4x4 window same", (4, 4), lambda v: np.sum(v * gw[:4, :4])),
+             ("moving average k=7 along rows (1,7) same", (1, 7), lambda v: np.sum(v) / 7.0)]
+    for name, ks, fn in cases:
+        f = kex.kmap(kernel_size=ks, padding="same")(fn)
+        y = f(x)
+        med, _ = timeit(lambda: f(x), 4)
+        rep(f"{name} on 16384^2", x.numel() * 8, med, y.numel())
+    del x, y
+    torch.cuda.empty_cache()
+
 if want("depthwise"):
     x = torch.randn((16, 4096, 4096), device=dev, generator=g)
     w = torch.randn((16, 3, 3), device=dev, generator=g)

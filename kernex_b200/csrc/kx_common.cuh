@@ -111,6 +111,22 @@ __device__ __forceinline__ int32_t mad_wrap(int32_t c, int32_t v, int32_t acc) {
 }
 __device__ __forceinline__ float mad_wrap(float c, float v, float acc) { return fmaf(c, v, acc); }
 
+// window max / min: NaN propagates like np.max / jnp.max (a comparison-select would drop a NaN that is not first)
+__device__ __forceinline__ float red_max(float a, float b) {
+  float r;
+  asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ float red_min(float a, float b) {
+  float r;
+  asm("min.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ int32_t red_max(int32_t a, int32_t b) { return a > b ? a : b; }
+__device__ __forceinline__ int32_t red_min(int32_t a, int32_t b) { return a < b ? a : b; }
+__device__ __forceinline__ double red_max(double a, double b) { return (a != a || b != b) ? (a + b) : (a > b ? a : b); }
+__device__ __forceinline__ double red_min(double a, double b) { return (a != a || b != b) ? (a + b) : (a < b ? a : b); }
+
 // Packed fp32 FMA (sm_100 FFMA2): (d0, d1) = (a0 * b0 + d0, a1 * b1 + d1), each half rounded exactly like
 // fmaf.  One issue slot for two FMAs: what the issue-bound kernels (27 FMA per conv output) need.  ptxas
 // broadcasts a scalar operand (a0 == a1) without building a register pair.

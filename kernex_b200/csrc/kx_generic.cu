@@ -39,9 +39,9 @@ __device__ __forceinline__ TC eval_func(const DevProgram<TC>& p, int f, const TI
       const TC c = coef_dev ? coef_dev[t] : p.coef[t];
       acc = mad_wrap(c, v, acc);
     } else if (kind == KX_REDUCE_MAX) {
-      acc = (t == t0) ? v : (v > acc ? v : acc);
+      acc = (t == t0) ? v : red_max(acc, v);
     } else {  // KX_REDUCE_MIN (KX_GATHER is handled by the caller)
-      acc = (t == t0) ? v : (v < acc ? v : acc);
+      acc = (t == t0) ? v : red_min(acc, v);
     }
   }
   if (kind == KX_AFFINE && p.func[f].post_div != 0.f) acc = (TC)((float)acc / p.func[f].post_div);

@@ -62,8 +62,8 @@ struct RowW {
 template <typename T, int OP>
 __device__ __forceinline__ T fold(T acc, T c, T v) {
   if (OP == kOpAffine) return mad_wrap(c, v, acc);
-  if (OP == kOpMax) return v > acc ? v : acc;
-  return v < acc ? v : acc;
+  if (OP == kOpMax) return red_max(acc, v);
+  return red_min(acc, v);
 }
 
 template <typename T, int OP, int KY, int KX, int SY, int SX, int SHIFT>

@@ -97,9 +97,9 @@ __device__ __forceinline__ void wave_window(const WaveArgs& a, const DevProgram<
       const TC c = coef_dev ? coef_dev[t] : p.coef[t];
       acc = mad_wrap(c, v, acc);
     } else if (kind == KX_REDUCE_MAX) {
-      acc = (t == t0) ? v : (v > acc ? v : acc);
+      acc = (t == t0) ? v : red_max(acc, v);
     } else if (kind == KX_REDUCE_MIN) {
-      acc = (t == t0) ? v : (v < acc ? v : acc);
+      acc = (t == t0) ? v : red_min(acc, v);
     } else {  // scalar KX_GATHER: x[tap]
       acc = v;
     }
@@ -344,9 +344,9 @@ scan_wavefront_rows_kernel(const __grid_constant__ WaveRowsArgs a, const __grid_
             const TC c = coef_dev ? coef_dev[t] : p.coef[t];
             acc = mad_wrap(c, v, acc);
           } else if (kind == KX_REDUCE_MAX) {
-            acc = (t == t0) ? v : (v > acc ? v : acc);
+            acc = (t == t0) ? v : red_max(acc, v);
           } else if (kind == KX_REDUCE_MIN) {
-            acc = (t == t0) ? v : (v < acc ? v : acc);
+            acc = (t == t0) ? v : red_min(acc, v);
           } else {
             acc = v;
           }

@@ -1,0 +1,304 @@
+// Fast path: single-function AFFINE stencils over the last two axes, stride 1, f32 / i32.
+// (2-D 5-point Laplacian, 3x3 blur / conv, 1-D windows as H = 1, leading axes with a
+// 1-wide window folded into the batch.)
+//
+// HBM-bound design (8 B per lattice update = read once + write once):
+//   * each thread owns 4 consecutive output columns and MARCHES down the rows of its
+//     block's band, keeping the last KY input rows in a register queue, so every input
+//     row is fetched once per thread column; the x-halo and the row halo between bands
+//     are re-read through L1 / L2, never from DRAM;
+//   * input rows are fetched as 128-bit aligned vectors (ld.global.nc.v4); the window
+//     misalignment ((-lo_x) mod 4) is a template parameter so the realignment is pure
+//     register renaming; U rows are fetched back to back before any arithmetic so each
+//     warp keeps U*NV 512-byte requests in flight;
+//   * zero padding (kernex/_src/utils.py:43-53) is a predicate on whole vectors, never a
+//     materialised pad; negative borders just move the window origin;
+//   * coefficients sit in kernel-parameter constant memory (FFMA constant operands) or,
+//     for device weights, in registers; a tap mask skips taps the user never wrote so
+//     non-finite inputs cannot leak through a 0 * x product.
+//
+// This header holds the kernel template; kx_stencil2d.cu the host-side planning; kx_stencil2d_k<KY>.cu the
+// instantiations of one window height each.
+#pragma once
+
+#include <type_traits>
+
+#include "kx_internal.cuh"
+
+namespace kx {
+namespace s2 {
+
+constexpr int kTX = 128;      // threads per block, each owning 4 output columns
+constexpr int kCols = 4;
+constexpr int kMaxK = 7;
+
+template <typename T>
+struct S2Args {
+  const T* in;
+  T* out;
+  const T* coef_dev;           // optional [KY*KX] device table (dense, row-major)
+  int64_t in_batch, out_batch, coef_batch;
+  int hin, win, hout, wout;
+  int ly, lx;                  // left borders
+  int th;                      // output rows per block
+  uint64_t mask;               // bit ky*KX+kx set = tap present
+  int use_box, by0, by1, bx0, bx1;  // offset maps: outputs outside the box copy the window centre
+  float post_div;              // != 0: result = (bias + sum) / post_div (window mean), f32 only
+  T bias;
+  T coef[kMaxK * kMaxK];
+};
+
+template <typename T>
+struct Vec4 {
+  T v[4];
+};
+
+template <typename T>
+__device__ __forceinline__ Vec4<T> ld_vec4(const T* p) {
+  Vec4<T> r;
+  const int4 raw = __ldg(reinterpret_cast<const int4*>(p));
+  r.v[0] = reinterpret_cast<const T&>(raw.x);
+  r.v[1] = reinterpret_cast<const T&>(raw.y);
+  r.v[2] = reinterpret_cast<const T&>(raw.z);
+  r.v[3] = reinterpret_cast<const T&>(raw.w);
+  return r;
+}
+
+template <typename T>
+__device__ __forceinline__ void st_row4(T* p, const T (&a)[4], int n_valid) {
+  const uintptr_t addr = reinterpret_cast<uintptr_t>(p);
+  if (n_valid == 4 && (addr & 15) == 0) {
+    int4 raw;
+    raw.x = reinterpret_cast<const int&>(a[0]);
+    raw.y = reinterpret_cast<const int&>(a[1]);
+    raw.z = reinterpret_cast<const int&>(a[2]);
+    raw.w = reinterpret_cast<const int&>(a[3]);
+    __stcs(reinterpret_cast<int4*>(p), raw);
+  } else if (n_valid == 4 && (addr & 7) == 0) {
+    int2 lo, hi;
+    lo.x = reinterpret_cast<const int&>(a[0]);
+    lo.y = reinterpret_cast<const int&>(a[1]);
+    hi.x = reinterpret_cast<const int&>(a[2]);
+    hi.y = reinterpret_cast<const int&>(a[3]);
+    __stcs(reinterpret_cast<int2*>(p), lo);
+    __stcs(reinterpret_cast<int2*>(p) + 1, hi);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (i < n_valid) p[i] = a[i];
+  }
+}
+
+// VW = elements per load: 4 when the input rows are 16-byte aligned, 2 when they are 8-byte aligned
+// (even widths such as the 16382-wide cotangent of the C2 backward pass), else 1.
+// SHIFT = (-lx) mod VW: misalignment of the window inside the thread's aligned row buffer.
+// OP = kAffine: bias + sum of coef * tap over the masked window; kMax / kMin: reduction over the WHOLE window;
+// kBox: bias + c * (sum of the WHOLE window), for programs whose taps all carry the same coefficient c (np.sum,
+// np.mean, box blurs) -- summed rows first, then columns (fp32: another order than the row-major FMA chain, inside
+// the stated 1e-5 * sum|c x| tolerance; int32: exact).
+enum S2Op { kAffine = 0, kMax = 1, kMin = 2, kBox = 3 };
+
+// max / min propagate NaN like np.max / jnp.max (max.NaN.f32); kBox adds
+template <typename T, int OP>
+__device__ __forceinline__ T s2_fold(T acc, T v) {
+  if constexpr (OP == kBox) {
+    if constexpr (std::is_same<T, float>::value) return acc + v;
+    else return (T)((uint32_t)acc + (uint32_t)v);
+  } else {
+    return OP == kMax ? red_max(acc, v) : red_min(acc, v);
+  }
+}
+
+template <typename T, int KY, int KX, int SHIFT, int VW, int U, int OP>
+__global__ void __launch_bounds__(kTX)
+stencil2d_kernel(const __grid_constant__ S2Args<T> a) {
+  constexpr int NV = (SHIFT + KX + kCols - 1 + VW - 1) / VW;  // aligned vectors per row per thread
+  constexpr int NE = NV * VW;
+  const int j0 = (blockIdx.x * kTX + threadIdx.x) * kCols;  // first output column
+  if (j0 >= a.wout) return;
+  const int r0 = blockIdx.y * a.th;
+  const int r1 = min(r0 + a.th, a.hout);
+  const T* __restrict__ in = a.in + (int64_t)blockIdx.z * a.in_batch;
+  T* __restrict__ out = a.out + (int64_t)blockIdx.z * a.out_batch;
+  const int xa = j0 - a.lx - SHIFT;  // column of element 0 of the thread's row buffer
+  const int n_valid = min(kCols, a.wout - j0);
+
+  T coef[OP == kAffine ? KY * KX : 1];
+  if (OP != kAffine) {
+    coef[0] = T(0);   // unused
+  } else if (a.coef_dev) {
+    const T* cd = a.coef_dev + (int64_t)blockIdx.z * a.coef_batch;
+#pragma unroll
+    for (int i = 0; i < KY * KX; ++i) coef[i] = cd[i];
+  } else {
+#pragma unroll
+    for (int i = 0; i < KY * KX; ++i) coef[i] = a.coef[i];
+  }
+
+  auto load_row = [&](int iy, T(&dst)[NE]) {
+    const bool row_ok = (iy >= 0) && (iy < a.hin);
+    const T* rp = in + (int64_t)iy * a.win;
+    if (VW == 4) {
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        const int c = xa + 4 * v;
+        if (row_ok && c >= 0 && c + 3 < a.win) {  // win % 4 == 0: a vector is all in or all out
+          const Vec4<T> t = ld_vec4(rp + c);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) dst[4 * v + e] = t.v[e];
+        } else {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) dst[4 * v + e] = T(0);
+        }
+      }
+    } else if (VW == 2) {
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        const int c = xa + 2 * v;
+        if (row_ok && c >= 0 && c + 1 < a.win) {  // win % 2 == 0: a pair is all in or all out
+          const int2 raw = __ldg(reinterpret_cast<const int2*>(rp + c));
+          dst[2 * v] = reinterpret_cast<const T&>(raw.x);
+          dst[2 * v + 1] = reinterpret_cast<const T&>(raw.y);
+        } else {
+          dst[2 * v] = T(0);
+          dst[2 * v + 1] = T(0);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < KX + kCols - 1; ++e) {
+        const int c = xa + e;
+        dst[e] = (row_ok && c >= 0 && c < a.win) ? __ldg(rp + c) : T(0);
+      }
+    }
+  };
+
+  // Separable operators (whole-window max / min, and sums with one common coefficient) queue the HORIZONTAL fold
+  // of every input row (4 values per thread) instead of the row itself: KX-1 + KY-1 operations per output
+  // instead of KY*KX-1, and a queue of 4-wide rows.
+  constexpr bool SEP = OP != kAffine;
+  constexpr int QW = SEP ? kCols : NE;
+  auto fill = [&](int iy, T(&dst)[QW]) {
+    if constexpr (!SEP) {
+      load_row(iy, dst);
+    } else {
+      T row[NE];
+      load_row(iy, row);
+#pragma unroll
+      for (int i = 0; i < kCols; ++i) {
+        T v = row[SHIFT + i];
+#pragma unroll
+        for (int kx = 1; kx < KX; ++kx) v = s2_fold<T, OP>(v, row[SHIFT + kx + i]);
+        dst[i] = v;
+      }
+    }
+  };
+
+  T q[KY - 1 + U][QW];
+#pragma unroll
+  for (int ky = 0; ky < KY - 1; ++ky) fill(r0 - a.ly + ky, q[ky]);
+
+  for (int r = r0; r < r1; r += U) {
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (r + u < r1) fill(r + u - a.ly + KY - 1, q[KY - 1 + u]);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (r + u < r1) {
+        T acc[kCols];
+        if constexpr (!SEP) {
+#pragma unroll
+          for (int i = 0; i < kCols; ++i) acc[i] = a.bias;
+#pragma unroll
+          for (int ky = 0; ky < KY; ++ky) {
+#pragma unroll
+            for (int kx = 0; kx < KX; ++kx) {
+              if (a.mask & (1ull << (ky * KX + kx))) {
+#pragma unroll
+                for (int i = 0; i < kCols; ++i)
+                  acc[i] = mad_wrap(coef[ky * KX + kx], q[u + ky][SHIFT + kx + i], acc[i]);
+              }
+            }
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < kCols; ++i) {
+            T v = q[u][i];
+#pragma unroll
+            for (int ky = 1; ky < KY; ++ky) v = s2_fold<T, OP>(v, q[u + ky][i]);
+            acc[i] = (OP == kBox) ? mad_wrap(a.coef[0], v, a.bias) : v;
+          }
+        }
+        if (std::is_same<T, float>::value && (OP == kAffine || OP == kBox) && a.post_div != 0.f) {
+#pragma unroll
+          for (int i = 0; i < kCols; ++i) acc[i] = (T)((float)acc[i] / a.post_div);   // block-uniform: window mean
+        }
+        if constexpr (!SEP) {
+          if (a.use_box) {  // block-uniform: smap / offset_kernel_map fused into one pass
+            const bool rin = (r + u >= a.by0) && (r + u < a.by1);
+#pragma unroll
+            for (int i = 0; i < kCols; ++i)
+              if (!(rin && j0 + i >= a.bx0 && j0 + i < a.bx1)) acc[i] = q[u + (KY - 1) / 2][SHIFT + (KX - 1) / 2 + i];
+          }
+        }
+        st_row4(out + (int64_t)(r + u) * a.wout + j0, acc, n_valid);
+      }
+    }
+#pragma unroll
+    for (int ky = 0; ky < KY - 1; ++ky) {
+#pragma unroll
+      for (int e = 0; e < QW; ++e) q[ky][e] = q[U + ky][e];
+    }
+  }
+}
+
+template <typename T, int KY, int KX, int OP>
+int launch_kk(const S2Args<T>& a, int batch, int vw, cudaStream_t s) {
+  constexpr int U = (OP == kAffine && KY * KX >= 15) ? 2 : 4;
+  dim3 grid((a.wout + kTX * kCols - 1) / (kTX * kCols), (a.hout + a.th - 1) / a.th, batch);
+  const int shift = vw > 1 ? (((-a.lx) % vw) + vw) % vw : 0;
+  if (vw == 1) stencil2d_kernel<T, KY, KX, 0, 1, U, OP><<<grid, kTX, 0, s>>>(a);
+  else if (vw == 2) {
+    if constexpr (OP == kAffine) {
+      if (shift == 0) stencil2d_kernel<T, KY, KX, 0, 2, U, OP><<<grid, kTX, 0, s>>>(a);
+      else stencil2d_kernel<T, KY, KX, 1, 2, U, OP><<<grid, kTX, 0, s>>>(a);
+    } else {
+      return KX_ERR_UNSUPPORTED;
+    }
+  } else if (shift == 0) stencil2d_kernel<T, KY, KX, 0, 4, U, OP><<<grid, kTX, 0, s>>>(a);
+  else if (shift == 1) stencil2d_kernel<T, KY, KX, 1, 4, U, OP><<<grid, kTX, 0, s>>>(a);
+  else if (shift == 2) stencil2d_kernel<T, KY, KX, 2, 4, U, OP><<<grid, kTX, 0, s>>>(a);
+  else stencil2d_kernel<T, KY, KX, 3, 4, U, OP><<<grid, kTX, 0, s>>>(a);
+  return after_launch("stencil2d_kernel");
+}
+
+// The separable operators come in the 16-byte aligned and the scalar-load variants only.  Box sums are
+// instantiated where they save work (windows of 7 or more elements).
+template <int KY, int KX>
+struct S2HasBox {
+  static constexpr bool value = KY * KX >= 7;
+};
+
+template <typename T, int KY, int KX>
+int launch_op(const S2Args<T>& a, int op, int batch, int vw, cudaStream_t s) {
+  if (op == kAffine) return launch_kk<T, KY, KX, kAffine>(a, batch, vw, s);
+  if (vw == 2) vw = 1;
+  if (op == kMax) return launch_kk<T, KY, KX, kMax>(a, batch, vw, s);
+  if (op == kMin) return launch_kk<T, KY, KX, kMin>(a, batch, vw, s);
+  if constexpr (S2HasBox<KY, KX>::value) {
+    if (op == kBox) return launch_kk<T, KY, KX, kBox>(a, batch, vw, s);
+  }
+  return KX_ERR_UNSUPPORTED;
+}
+
+// One translation unit per window height (kx_stencil2d_k<KY>.cu) so the instantiations compile in parallel.
+#define KX_S2_DECLARE(KY)                                                                                     \
+  int s2_launch_k##KY(const S2Args<float>& a, int kx, int op, int batch, int vw, cudaStream_t s);            \
+  int s2_launch_k##KY(const S2Args<int32_t>& a, int kx, int op, int batch, int vw, cudaStream_t s);
+KX_S2_DECLARE(1) KX_S2_DECLARE(2) KX_S2_DECLARE(3) KX_S2_DECLARE(4) KX_S2_DECLARE(5) KX_S2_DECLARE(7)
+#undef KX_S2_DECLARE
+
+inline bool s2_has_box(int ky, int kx) { return ky * kx >= 7; }
+
+}  // namespace s2
+}  // namespace kx

@@ -74,6 +74,75 @@ def test_stencil2d_random_geometry(kex, seed):
     _check_affine(got, x, (ky, kx), (1, 1), border, taps, coefs, bias)
 
 
+_WIDE = [(1, 4), (4, 4), (3, 5), (5, 3), (2, 5), (4, 1), (1, 7), (7, 1), (7, 7), (5, 2), (4, 3), (2, 4)]
+
+
+@pytest.mark.parametrize("ki", range(len(_WIDE)))
+@pytest.mark.parametrize("variant", ["f32-aligned", "i32-aligned", "f32-ragged", "f32-even"])
+def test_stencil2d_every_window_shape_up_to_5x5_and_7x7(kex, ki, variant):
+    ky, kx = _WIDE[ki]
+    rng = np.random.default_rng(9100 + 10 * ki + len(variant))
+    h = int(rng.integers(ky + 3, 90))
+    w = {"f32-aligned": 260, "i32-aligned": 132, "f32-ragged": 131, "f32-even": 150}[variant]
+    border = ((int(rng.integers(-1, ky)), int(rng.integers(-1, ky))), (int(rng.integers(-1, kx)), int(rng.integers(-1, kx))))
+    taps = [t for t in itertools.product(range(ky), range(kx)) if rng.random() < 0.8] or [(0, 0)]
+    if variant.startswith("i32"):
+        x = rng.integers(-1000, 1000, (h, w)).astype(np.int32)
+        coefs, bias = [int(c) or 2 for c in rng.integers(-9, 10, len(taps))], 3
+    else:
+        x = rng.standard_normal((h, w)).astype(np.float32)
+        coefs, bias = [float(c) for c in rng.standard_normal(len(taps))], -0.25
+
+    def fn(v):
+        acc = bias
+        for t, c in zip(taps, coefs):
+            acc = acc + c * v[t]
+        return acc
+
+    got = kex.kernel_map({fn: ()}, (h, w), (ky, kx), (1, 1), border, False)(x)
+    assert _last_kernel() == "stencil2d_kernel"
+    _check_affine(got, x, (ky, kx), (1, 1), border, taps, coefs, bias)
+
+
+@pytest.mark.parametrize("ksize", [(2, 2), (3, 3), (1, 3), (3, 1), (5, 5), (1, 7), (2, 4), (1, 1)])
+@pytest.mark.parametrize("op", ["max", "min", "mean"])
+@pytest.mark.parametrize("dtype", ["f32", "i32"])
+def test_stencil2d_window_reductions_stride1(kex, ksize, op, dtype):
+    """np.max / np.min / np.mean over stride-1 windows (max / min filters, box blurs): zero padding takes part."""
+    if op == "mean" and dtype == "i32":
+        pytest.skip("the mean of an int32 array is float32: generic kernel")
+    rng = np.random.default_rng(9300 + 7 * ksize[0] + ksize[1])
+    for (h, w), pad in [((45, 260), "same"), ((33, 131), "valid"), ((20, 64), ((1, 0), (2, 1)))]:
+        if ksize[0] > h or ksize[1] > w:
+            continue
+        border = ko.resolve_padding(pad, ksize) if isinstance(pad, str) else tuple(
+            (min(l, k - 1), min(r, k - 1)) for (l, r), k in zip(pad, ksize))
+        x = (rng.standard_normal((h, w)).astype(np.float32) if dtype == "f32"
+             else rng.integers(-1000, 1000, (h, w)).astype(np.int32))
+        fn = {"max": lambda v: np.max(v), "min": lambda v: np.min(v), "mean": lambda v: np.mean(v)}[op]
+        got = kex.kernel_map({fn: ()}, (h, w), ksize, (1, 1), border, False)(x)
+        assert _last_kernel() == "stencil2d_kernel"
+        want = ko.reduce_map(x, ksize, (1, 1), border, op)
+        assert got.shape == want.shape and got.dtype == want.dtype
+        if op == "mean":
+            np.testing.assert_allclose(got, want, rtol=0, atol=1e-5 * float(np.abs(x).max()) * ksize[0] * ksize[1])
+        else:
+            np.testing.assert_array_equal(got, want)
+
+
+def test_window_max_propagates_nan_like_numpy(kex):
+    """np.max / jnp.max return NaN when any window element is NaN, whichever position it has in the window."""
+    rng = np.random.default_rng(5)
+    x = rng.standard_normal((40, 132)).astype(np.float32)
+    x[7, 9] = x[20, 100] = x[39, 131] = np.nan
+    for ksize, strides in [((3, 3), (1, 1)), ((2, 2), (2, 2)), ((3, 5), (1, 1)), ((3, 3), (1, 3))]:
+        for op, fn in [("max", lambda v: np.max(v)), ("min", lambda v: np.min(v))]:
+            got = kex.kernel_map({fn: ()}, x.shape, ksize, strides, ((1, 1), (1, 1)), False)(x)
+            want = ko.reduce_map(x, ksize, strides, ((1, 1), (1, 1)), op)
+            assert np.isnan(want).sum() > 0
+            np.testing.assert_array_equal(got, want)   # NaNs compare equal position-wise here
+
+
 def test_stencil2d_nonfinite_inputs_do_not_leak_through_missing_taps(kex):
     x = np.ones((16, 64), np.float32)
     x[5, 7] = np.inf

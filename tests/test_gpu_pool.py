@@ -37,10 +37,16 @@ FNS = {"max": lambda v: np.max(v), "min": lambda v: np.min(v), "mean": lambda v:
 @pytest.mark.parametrize("gi", range(len(GEOMS)))
 @pytest.mark.parametrize("op", ["max", "min", "mean", "sum"])
 @pytest.mark.parametrize("case", range(4))
-def test_pool2d_matches_oracle(kex, gi, op, case):
+@pytest.mark.parametrize("legacy", [False, True])
+def test_pool2d_matches_oracle(kex, gi, op, case, legacy, monkeypatch):
     ksize, strides = GEOMS[gi]
-    if strides == (1, 1) and op in ("mean", "sum"):
-        pytest.skip("stride-1 affine windows belong to stencil2d")
+    if strides == (1, 1) and op == "sum" and legacy:
+        pytest.skip("stride-1 sums always belonged to stencil2d")
+    if strides != (1, 1) and legacy:
+        pytest.skip("strided windows never run on stencil2d")
+    if legacy:   # stride-1 max / min / mean on the row-ring kernel (their home before stencil2d learnt them)
+        monkeypatch.setenv("KX_S2_LEGACY_SHAPES", "1")
+    expect = "stencil2d_kernel" if strides == (1, 1) and not legacy else "pool2d_kernel"
     rng = np.random.default_rng(7000 + 100 * gi + case)
     h = [70, 33, 129, 200][case]
     w = [516, 132, 1028, 260][(case + gi) % 4]
@@ -53,7 +59,7 @@ def test_pool2d_matches_oracle(kex, gi, op, case):
     else:
         x = rng.standard_normal((h, w)).astype(np.float32)
     got = kex.kernel_map({FNS[op]: ()}, (h, w), ksize, strides, border, False)(x)
-    assert _last_kernel() == "pool2d_kernel"
+    assert _last_kernel() == expect
     want = ko.reduce_map(x, ksize, strides, border, op)
     assert got.shape == want.shape and got.dtype == want.dtype
     if integer or op in ("max", "min"):
