@@ -39,6 +39,7 @@ if want("wide"):
     gw /= gw.sum()
     cases = [("box blur 5x5 (np.mean) same", (5, 5), lambda v: np.mean(v)),
              ("Gaussian blur 7x7 (host weights) same", (7, 7), lambda v: np.sum(v * gw)),
+             ("weighted 3x3 window same", (3, 3), lambda v: np.sum(v * gw[:3, :3])),
              ("max filter 3x3 same", (3, 3), lambda v: np.max(v)),
              ("max filter 5x5 same", (5, 5), lambda v: np.max(v)),
              ("weighted 4x4 window same", (4, 4), lambda v: np.sum(v * gw[:4, :4])),

@@ -85,7 +85,7 @@ int run(const MapArgs& m, const KxProgram& p, int ay, int ax, int64_t batch, cud
     for (int i = 1; i < KY * KX; ++i) same = same && (dense[i] == dense[0]);
     if (same) op = kBox;
   }
-  a.post_div = (float)f.post_div;
+  a.post_mul = f.post_div != 0.0 ? (float)(1.0 / f.post_div) : 0.f;
   return launch_t<T>(a, KY, KX, op, (int)batch, vw, s);
 }
 
