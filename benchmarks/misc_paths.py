@@ -37,8 +37,17 @@ if want("wide"):
     x = torch.randn((16384, 16384), device=dev, generator=g)
     gw = np.exp(-0.5 * (np.arange(-3, 4)[:, None] ** 2 + np.arange(-3, 4)[None, :] ** 2) / 2.0).astype(np.float32)
     gw /= gw.sum()
+    def gauss(k):
+        gg = np.exp(-0.5 * np.linspace(-(k - 1) / 2, (k - 1) / 2, k) ** 2 / 2.0)
+        ww = np.outer(gg, gg)
+        return (ww / ww.sum()).astype(np.float32)
+    g11, g15 = gauss(11), gauss(15)
+    rw = np.random.default_rng(3).standard_normal((7, 7)).astype(np.float32)
     cases = [("box blur 5x5 (np.mean) same", (5, 5), lambda v: np.mean(v)),
-             ("Gaussian blur 7x7 (host weights) same", (7, 7), lambda v: np.sum(v * gw)),
+             ("Gaussian blur 7x7 (README.md:277-294, outer-product weights) same", (7, 7), lambda v: np.sum(v * gw)),
+             ("Gaussian blur 11x11 same", (11, 11), lambda v: np.sum(v * g11)),
+             ("Gaussian blur 15x15 same", (15, 15), lambda v: np.sum(v * g15)),
+             ("dense 7x7 window (random weights) same", (7, 7), lambda v: np.sum(v * rw)),
              ("weighted 3x3 window same", (3, 3), lambda v: np.sum(v * gw[:3, :3])),
              ("max filter 3x3 same", (3, 3), lambda v: np.max(v)),
              ("max filter 5x5 same", (5, 5), lambda v: np.max(v)),

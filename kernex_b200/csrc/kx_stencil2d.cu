@@ -1,4 +1,6 @@
 // Host-side planning of the stencil2d fast path (kernel: kx_stencil2d_impl.cuh, instantiations: kx_stencil2d_k*.cu).
+#include <cmath>
+
 #include "kx_stencil2d_impl.cuh"
 
 namespace kx {
@@ -16,6 +18,10 @@ int launch_t(const S2Args<T>& a, int ky, int kx, int op, int batch, int vw, cuda
     case 4: return s2_launch_k4(a, kx, op, batch, vw, s);
     case 5: return s2_launch_k5(a, kx, op, batch, vw, s);
     case 7: return s2_launch_k7(a, kx, op, batch, vw, s);
+    case 9: return s2_launch_k9(a, kx, op, batch, vw, s);
+    case 11: return s2_launch_k11(a, kx, op, batch, vw, s);
+    case 13: return s2_launch_k13(a, kx, op, batch, vw, s);
+    case 15: return s2_launch_k15(a, kx, op, batch, vw, s);
   }
   return KX_ERR_UNSUPPORTED;
 }
@@ -56,35 +62,63 @@ int run(const MapArgs& m, const KxProgram& p, int ay, int ax, int64_t batch, cud
   // device tables are indexed by tap slot; the kernel wants a dense KY*KX table: only
   // usable directly when the program lists every window element in row-major order
   bool dense_order = (f.tap_end - f.tap_begin) == KY * KX;
+  bool seen[kMaxK * kMaxK] = {false};
+  int n_seen = 0;
   for (int t = f.tap_begin; t < f.tap_end; ++t) {
     const int oy = ay >= 0 ? p.tap_off[t][ay] : 0, ox = p.tap_off[t][ax];
     const int slot = oy * KX + ox;
-    if (a.mask & (1ull << slot)) return KX_ERR_UNSUPPORTED;  // duplicate tap: leave it to the generic kernel
-    a.mask |= 1ull << slot;
+    if (seen[slot]) return KX_ERR_UNSUPPORTED;  // duplicate tap: leave it to the generic kernel
+    seen[slot] = true;
+    ++n_seen;
+    if (slot < 64) a.mask |= 1ull << slot;
     dense[slot] = (T)p.coef[t];
     if (slot != t - f.tap_begin) dense_order = false;
   }
+  const bool full = n_seen == KY * KX;
   if (dev) {
     if (!dense_order) return KX_ERR_UNSUPPORTED;
     a.coef_dev = (const T*)m.coef_dev;
     a.coef_batch = m.coef_batch_stride;
   }
-  for (int i = 0; i < KY * KX; ++i) a.coef[i] = dense[i];
+  for (int i = 0; i < KY * KX; ++i) a.coef[i] = dense[i];   // (kSep overwrites its two vectors below)
   const uintptr_t base = reinterpret_cast<uintptr_t>(m.in);
   int vw = 1;
   if (a.win % 4 == 0 && (base & 15) == 0 && a.in_batch % 4 == 0) vw = 4;
   else if (a.win % 2 == 0 && (base & 7) == 0 && a.in_batch % 2 == 0) vw = 2;
   int op = kAffine;
-  const uint64_t full = (1ull << (KY * KX)) - 1;   // KY * KX <= 49
   if (f.kind != KX_AFFINE) {
     // whole-window reductions only (np.max(x) / np.min(x)); subsets stay on the generic kernel
-    if (dev || a.mask != full || m.use_box) return KX_ERR_UNSUPPORTED;
+    if (dev || !full || m.use_box) return KX_ERR_UNSUPPORTED;
     op = f.kind == KX_REDUCE_MAX ? kMax : kMin;
-  } else if (!dev && !m.use_box && a.mask == full && s2_has_box(KY, KX) && !getenv("KX_S2_NO_BOX")) {
+  } else if (!dev && !m.use_box && full && !getenv("KX_S2_NO_SEP")) {
     bool same = true;   // np.sum / np.mean / box blurs: one common coefficient -> separable row / column sums
     for (int i = 1; i < KY * KX; ++i) same = same && (dense[i] == dense[0]);
-    if (same) op = kBox;
+    if (same && s2_has_box(KY, KX)) op = kBox;
+    else if (std::is_same<T, float>::value && s2_has_sep(KY, KX)) {
+      // outer-product tables (Gaussian blur = outer(w, w) / sum, README.md:281-284): w[ky][kx] = cy[ky] * cx[kx] with
+      // cy = column / pivot and cx = row through the largest entry, accepted when every entry is reproduced to
+      // 4e-7 relative (fp32 rounding of the user's own products); the result then differs from the dense form
+      // by <= ~5e-7 * sum|c x|, well inside the stated 1e-5 tolerance
+      int pi = 0;
+      for (int i = 1; i < KY * KX; ++i)
+        if (fabs((double)dense[i]) > fabs((double)dense[pi])) pi = i;
+      const int py = pi / KX, px = pi % KX;
+      const double piv = (double)dense[pi];
+      bool sep = piv != 0.0;
+      for (int ky = 0; ky < KY && sep; ++ky)
+        for (int kx = 0; kx < KX && sep; ++kx) {
+          const double w = (double)dense[ky * KX + kx];
+          const double r = (double)dense[ky * KX + px] / piv * (double)dense[py * KX + kx];
+          sep = fabs(w - r) <= 4e-7 * fabs(w) + 1e-37;
+        }
+      if (sep) {
+        op = kSep;
+        for (int ky = 0; ky < KY; ++ky) a.coef[ky] = (T)((double)dense[ky * KX + px] / piv);
+        for (int kx = 0; kx < KX; ++kx) a.coef[kMaxK + kx] = dense[py * KX + kx];
+      }
+    }
   }
+  if (op == kAffine && (KY > 7 || KX > 7)) return KX_ERR_UNSUPPORTED;   // dense form: windows up to 7x7
   a.post_mul = f.post_div != 0.0 ? (float)(1.0 / f.post_div) : 0.f;
   return launch_t<T>(a, KY, KX, op, (int)batch, vw, s);
 }

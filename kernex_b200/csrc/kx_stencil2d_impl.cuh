@@ -30,7 +30,7 @@ namespace s2 {
 
 constexpr int kTX = 128;      // threads per block, each owning 4 output columns
 constexpr int kCols = 4;
-constexpr int kMaxK = 7;
+constexpr int kMaxK = 15;
 
 template <typename T>
 struct S2Args {
@@ -41,11 +41,11 @@ struct S2Args {
   int hin, win, hout, wout;
   int ly, lx;                  // left borders
   int th;                      // output rows per block
-  uint64_t mask;               // bit ky*KX+kx set = tap present
+  uint64_t mask;               // bit ky*KX+kx set = tap present (kAffine: windows of at most 7x7)
   int use_box, by0, by1, bx0, bx1;  // offset maps: outputs outside the box copy the window centre
   float post_mul;              // != 0: result = (bias + sum) * post_mul, post_mul = 1 / n (window mean), f32 only
   T bias;
-  T coef[kMaxK * kMaxK];
+  T coef[kMaxK * kMaxK];       // kAffine: dense KY*KX table; kBox: coef[0]; kSep: coef[ky] and coef[kMaxK + kx]
 };
 
 template <typename T>
@@ -95,8 +95,11 @@ __device__ __forceinline__ void st_row4(T* p, const T (&a)[4], int n_valid) {
 // OP = kAffine: bias + sum of coef * tap over the masked window; kMax / kMin: reduction over the WHOLE window;
 // kBox: bias + c * (sum of the WHOLE window), for programs whose taps all carry the same coefficient c (np.sum,
 // np.mean, box blurs) -- summed rows first, then columns (fp32: another order than the row-major FMA chain, inside
-// the stated 1e-5 * sum|c x| tolerance; int32: exact).
-enum S2Op { kAffine = 0, kMax = 1, kMin = 2, kBox = 3 };
+// the stated 1e-5 * sum|c x| tolerance; int32: exact);
+// kSep: bias + sum_ky cy[ky] * (sum_kx cx[kx] * tap), for fp32 coefficient tables that are an outer product
+// cy (x) cx to within fp32 rounding (Gaussian blurs, README.md:277-294; Sobel-like filters): KY + KX FMAs per output
+// instead of KY * KX, which keeps windows up to 15x15 on the HBM roofline instead of the FMA pipe.
+enum S2Op { kAffine = 0, kMax = 1, kMin = 2, kBox = 3, kSep = 4 };
 
 // max / min propagate NaN like np.max / jnp.max (max.NaN.f32); kBox adds
 template <typename T, int OP>
@@ -181,9 +184,16 @@ stencil2d_kernel(const __grid_constant__ S2Args<T> a) {
   auto hfold = [&](const T(&row)[NE], T(&dst)[QW]) {   // SEP only: horizontal fold of one input row
 #pragma unroll
     for (int i = 0; i < kCols; ++i) {
-      T v = row[SHIFT + i];
+      T v;
+      if constexpr (OP == kSep) {
+        v = a.coef[kMaxK] * row[SHIFT + i];
 #pragma unroll
-      for (int kx = 1; kx < KX; ++kx) v = s2_fold<T, OP>(v, row[SHIFT + kx + i]);
+        for (int kx = 1; kx < KX; ++kx) v = mad_wrap(a.coef[kMaxK + kx], row[SHIFT + kx + i], v);
+      } else {
+        v = row[SHIFT + i];
+#pragma unroll
+        for (int kx = 1; kx < KX; ++kx) v = s2_fold<T, OP>(v, row[SHIFT + kx + i]);
+      }
       dst[i < QW ? i : 0] = v;
     }
   };
@@ -235,13 +245,20 @@ stencil2d_kernel(const __grid_constant__ S2Args<T> a) {
         } else {
 #pragma unroll
           for (int i = 0; i < kCols; ++i) {
-            T v = q[u][i];
+            if constexpr (OP == kSep) {
+              T v = a.bias;
 #pragma unroll
-            for (int ky = 1; ky < KY; ++ky) v = s2_fold<T, OP>(v, q[u + ky][i]);
-            acc[i] = (OP == kBox) ? mad_wrap(a.coef[0], v, a.bias) : v;
+              for (int ky = 0; ky < KY; ++ky) v = mad_wrap(a.coef[ky], q[u + ky][i], v);
+              acc[i] = v;
+            } else {
+              T v = q[u][i];
+#pragma unroll
+              for (int ky = 1; ky < KY; ++ky) v = s2_fold<T, OP>(v, q[u + ky][i]);
+              acc[i] = (OP == kBox) ? mad_wrap(a.coef[0], v, a.bias) : v;
+            }
           }
         }
-        if (std::is_same<T, float>::value && (OP == kAffine || OP == kBox) && a.post_mul != 0.f) {
+        if (std::is_same<T, float>::value && (OP == kAffine || OP == kBox || OP == kSep) && a.post_mul != 0.f) {
           // block-uniform: window mean.  One multiply by the host-rounded reciprocal (<= 1.5 ulp from the true
           // quotient, exact for power-of-two windows) instead of ~10 instructions of IEEE division per output:
           // the 5x5 box blur went from 0.74 to 0.9x of peak
@@ -269,7 +286,7 @@ stencil2d_kernel(const __grid_constant__ S2Args<T> a) {
 
 template <typename T, int KY, int KX, int OP>
 int launch_kk(const S2Args<T>& a, int batch, int vw, cudaStream_t s) {
-  constexpr int U = (OP == kAffine && KY * KX >= 15) ? 2 : 4;
+  constexpr int U = ((OP == kAffine && KY * KX >= 15) || (OP != kAffine && KX >= 7)) ? 2 : 4;
   dim3 grid((a.wout + kTX * kCols - 1) / (kTX * kCols), (a.hout + a.th - 1) / a.th, batch);
   const int shift = vw > 1 ? (((-a.lx) % vw) + vw) % vw : 0;
   if (vw == 1) stencil2d_kernel<T, KY, KX, 0, 1, U, OP><<<grid, kTX, 0, s>>>(a);
@@ -287,21 +304,30 @@ int launch_kk(const S2Args<T>& a, int batch, int vw, cudaStream_t s) {
   return after_launch("stencil2d_kernel");
 }
 
-// The separable operators come in the 16-byte aligned and the scalar-load variants only.  Box sums are
-// instantiated where they save work (windows of 7 or more elements).
+// The separable operators come in the 16-byte aligned and the scalar-load variants only.  Box sums and outer-product
+// tables are instantiated where they save work; windows larger than 7x7 exist in separable form only.
 template <int KY, int KX>
-struct S2HasBox {
-  static constexpr bool value = KY * KX >= 7;
+struct S2Has {
+  static constexpr bool affine = KY <= 7 && KX <= 7;
+  static constexpr bool box = KY >= 2 && KY * KX >= 7;
+  static constexpr bool sep = KY >= 2 && KX >= 2 && KY * KX >= 15;
 };
+inline bool s2_has_box(int ky, int kx) { return ky >= 2 && ky * kx >= 7; }   // 1-row windows gain nothing
+inline bool s2_has_sep(int ky, int kx) { return ky >= 2 && kx >= 2 && ky * kx >= 15; }
 
 template <typename T, int KY, int KX>
 int launch_op(const S2Args<T>& a, int op, int batch, int vw, cudaStream_t s) {
-  if (op == kAffine) return launch_kk<T, KY, KX, kAffine>(a, batch, vw, s);
+  if constexpr (S2Has<KY, KX>::affine) {
+    if (op == kAffine) return launch_kk<T, KY, KX, kAffine>(a, batch, vw, s);
+  }
   if (vw == 2) vw = 1;
   if (op == kMax) return launch_kk<T, KY, KX, kMax>(a, batch, vw, s);
   if (op == kMin) return launch_kk<T, KY, KX, kMin>(a, batch, vw, s);
-  if constexpr (S2HasBox<KY, KX>::value) {
+  if constexpr (S2Has<KY, KX>::box) {
     if (op == kBox) return launch_kk<T, KY, KX, kBox>(a, batch, vw, s);
+  }
+  if constexpr (S2Has<KY, KX>::sep && std::is_same<T, float>::value) {
+    if (op == kSep) return launch_kk<T, KY, KX, kSep>(a, batch, vw, s);
   }
   return KX_ERR_UNSUPPORTED;
 }
@@ -311,9 +337,9 @@ int launch_op(const S2Args<T>& a, int op, int batch, int vw, cudaStream_t s) {
   int s2_launch_k##KY(const S2Args<float>& a, int kx, int op, int batch, int vw, cudaStream_t s);            \
   int s2_launch_k##KY(const S2Args<int32_t>& a, int kx, int op, int batch, int vw, cudaStream_t s);
 KX_S2_DECLARE(1) KX_S2_DECLARE(2) KX_S2_DECLARE(3) KX_S2_DECLARE(4) KX_S2_DECLARE(5) KX_S2_DECLARE(7)
+KX_S2_DECLARE(9) KX_S2_DECLARE(11) KX_S2_DECLARE(13) KX_S2_DECLARE(15)
 #undef KX_S2_DECLARE
 
-inline bool s2_has_box(int ky, int kx) { return ky >= 2 && ky * kx >= 7; }   // 1-row windows gain nothing
 
 }  // namespace s2
 }  // namespace kx

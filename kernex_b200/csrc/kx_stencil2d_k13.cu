@@ -1,0 +1,15 @@
+// stencil2d_kernel instantiations for 13x13 windows: separable forms only (see kx_stencil2d_impl.cuh).
+#include "kx_stencil2d_impl.cuh"
+
+namespace kx {
+namespace s2 {
+
+int s2_launch_k13(const S2Args<float>& a, int kx, int op, int batch, int vw, cudaStream_t s) {
+  return kx == 13 ? launch_op<float, 13, 13>(a, op, batch, vw, s) : KX_ERR_UNSUPPORTED;
+}
+int s2_launch_k13(const S2Args<int32_t>& a, int kx, int op, int batch, int vw, cudaStream_t s) {
+  return kx == 13 ? launch_op<int32_t, 13, 13>(a, op, batch, vw, s) : KX_ERR_UNSUPPORTED;
+}
+
+}  // namespace s2
+}  // namespace kx

@@ -130,6 +130,61 @@ def test_stencil2d_window_reductions_stride1(kex, ksize, op, dtype):
             np.testing.assert_array_equal(got, want)
 
 
+def _gauss(ky, kx, rng):
+    gy = np.exp(-0.5 * np.linspace(-(ky - 1) / 2, (ky - 1) / 2, ky) ** 2 / 1.7).astype(np.float32)
+    gx = np.exp(-0.5 * np.linspace(-(kx - 1) / 2, (kx - 1) / 2, kx) ** 2 / 0.9).astype(np.float32)
+    w = np.outer(gy, gx).astype(np.float32)
+    return (w / w.sum()).astype(np.float32)
+
+
+@pytest.mark.parametrize("ksize", [(4, 4), (5, 5), (3, 5), (5, 3), (7, 7), (9, 9), (11, 11), (13, 13), (15, 15)])
+@pytest.mark.parametrize("kind", ["gauss", "signed", "mean", "max", "sum-i32"])
+def test_stencil2d_separable_windows_up_to_15x15(kex, ksize, kind):
+    """README.md:277-294 Gaussian blur (w = outer(g, g) / sum, any kernel size) and other outer-product tables run as
+    KY + KX FMAs per output; box sums / means and max / min as row-then-column folds; vs the dense oracle."""
+    ky, kx = ksize
+    rng = np.random.default_rng(9500 + 16 * ky + kx)
+    taps = list(itertools.product(range(ky), range(kx)))
+    for (h, w_), pad in [((40, 260), "same"), ((37, 131), "valid"), ((48, 72), tuple(((k - 1) // 2, 0) for k in ksize))]:
+        border = ko.resolve_padding(pad, ksize) if isinstance(pad, str) else pad
+        if kind == "sum-i32":
+            x = rng.integers(-1000, 1000, (h, w_)).astype(np.int32)
+            got = kex.kernel_map({(lambda v: np.sum(v)): ()}, (h, w_), ksize, (1, 1), border, False)(x)
+            assert _last_kernel() == ("stencil2d_kernel")
+            np.testing.assert_array_equal(got, ko.reduce_map(x, ksize, (1, 1), border, "sum"))
+            continue
+        x = rng.standard_normal((h, w_)).astype(np.float32)
+        if kind in ("mean", "max"):
+            fn = (lambda v: np.mean(v)) if kind == "mean" else (lambda v: np.max(v))
+            got = kex.kernel_map({fn: ()}, (h, w_), ksize, (1, 1), border, False)(x)
+            assert _last_kernel() == "stencil2d_kernel"
+            want = ko.reduce_map(x, ksize, (1, 1), border, kind)
+            if kind == "max":
+                np.testing.assert_array_equal(got, want)
+            else:
+                np.testing.assert_allclose(got, want, rtol=0, atol=1e-5 * float(np.abs(x).max()))
+            continue
+        wt = _gauss(ky, kx, rng)
+        if kind == "signed":   # derivative-of-Gaussian style: sign changes in one factor (zero entries would be
+            wt = np.outer(wt[:, kx // 2], np.linspace(-1, 1.37, kx)).astype(np.float32)   # dropped by the tracer)
+        got = kex.kernel_map({(lambda v: np.sum(v * wt)): ()}, (h, w_), ksize, (1, 1), border, False)(x)
+        assert _last_kernel() == "stencil2d_kernel"
+        _check_affine(got, x, ksize, (1, 1), border, taps, [float(wt[t]) for t in taps])
+
+
+def test_stencil2d_dense_tables_are_not_mistaken_for_outer_products(kex):
+    """A table one entry away from an outer product must take the dense kernel (<= 7x7) or the generic one."""
+    rng = np.random.default_rng(77)
+    x = rng.standard_normal((40, 132)).astype(np.float32)
+    for k in (5, 7, 9):
+        wt = _gauss(k, k, rng)
+        wt[1, 2] *= np.float32(1.001)
+        taps = list(itertools.product(range(k), range(k)))
+        got = kex.kernel_map({(lambda v: np.sum(v * wt)): ()}, x.shape, (k, k), (1, 1), ((1, 1), (2, 2)), False)(x)
+        assert _last_kernel() == ("stencil2d_kernel" if k <= 7 else "generic_map_kernel")
+        _check_affine(got, x, (k, k), (1, 1), ((1, 1), (2, 2)), taps, [float(wt[t]) for t in taps])
+
+
 def test_window_max_propagates_nan_like_numpy(kex):
     """np.max / jnp.max return NaN when any window element is NaN, whichever position it has in the window."""
     rng = np.random.default_rng(5)
