@@ -61,6 +61,19 @@ if want("wide"):
     del x, y
     torch.cuda.empty_cache()
 
+if want("fir"):
+    # 1-D arrays: FIR filters / moving averages of up to 15 taps are one-row windows of the row-march kernel
+    x = torch.randn((1 << 27,), device=dev, generator=g)
+    w15 = np.random.default_rng(5).standard_normal(15).astype(np.float32)
+    for name, k, fn in [("15-tap FIR filter", 15, lambda v: np.sum(v * w15)), ("moving average k=9", 9, lambda v: np.mean(v)),
+                        ("running max k=11", 11, lambda v: np.max(v))]:
+        f = kex.kmap(kernel_size=(k,), padding="same")(fn)
+        y = f(x)
+        med, _ = timeit(lambda: f(x), 4)
+        rep(f"{name} on a 1-D array of 2^27 fp32", x.numel() * 8, med, y.numel())
+    del x, y
+    torch.cuda.empty_cache()
+
 if want("depthwise"):
     x = torch.randn((16, 4096, 4096), device=dev, generator=g)
     w = torch.randn((16, 3, 3), device=dev, generator=g)

@@ -118,7 +118,7 @@ int run(const MapArgs& m, const KxProgram& p, int ay, int ax, int64_t batch, cud
       }
     }
   }
-  if (op == kAffine && (KY > 7 || KX > 7)) return KX_ERR_UNSUPPORTED;   // dense form: windows up to 7x7
+  if (op == kAffine && !s2_has_affine(KY, KX)) return KX_ERR_UNSUPPORTED;   // dense form: windows up to 7x7, 1 x 15
   a.post_mul = f.post_div != 0.0 ? (float)(1.0 / f.post_div) : 0.f;
   return launch_t<T>(a, KY, KX, op, (int)batch, vw, s);
 }

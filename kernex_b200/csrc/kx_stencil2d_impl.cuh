@@ -286,7 +286,7 @@ stencil2d_kernel(const __grid_constant__ S2Args<T> a) {
 
 template <typename T, int KY, int KX, int OP>
 int launch_kk(const S2Args<T>& a, int batch, int vw, cudaStream_t s) {
-  constexpr int U = ((OP == kAffine && KY * KX >= 15) || (OP != kAffine && KX >= 7)) ? 2 : 4;
+  constexpr int U = ((OP == kAffine && (KY * KX >= 15 || KX >= 9)) || (OP != kAffine && KX >= 7)) ? 2 : 4;
   dim3 grid((a.wout + kTX * kCols - 1) / (kTX * kCols), (a.hout + a.th - 1) / a.th, batch);
   const int shift = vw > 1 ? (((-a.lx) % vw) + vw) % vw : 0;
   if (vw == 1) stencil2d_kernel<T, KY, KX, 0, 1, U, OP><<<grid, kTX, 0, s>>>(a);
@@ -308,11 +308,12 @@ int launch_kk(const S2Args<T>& a, int batch, int vw, cudaStream_t s) {
 // tables are instantiated where they save work; windows larger than 7x7 exist in separable form only.
 template <int KY, int KX>
 struct S2Has {
-  static constexpr bool affine = KY <= 7 && KX <= 7;
+  static constexpr bool affine = (KY <= 7 && KX <= 7) || (KY == 1 && KX <= kMaxK);   // 1-row FIR filters up to 15 taps
   static constexpr bool box = KY >= 2 && KY * KX >= 7;
   static constexpr bool sep = KY >= 2 && KX >= 2 && KY * KX >= 15;
 };
 inline bool s2_has_box(int ky, int kx) { return ky >= 2 && ky * kx >= 7; }   // 1-row windows gain nothing
+inline bool s2_has_affine(int ky, int kx) { return (ky <= 7 && kx <= 7) || (ky == 1 && kx <= kMaxK); }
 inline bool s2_has_sep(int ky, int kx) { return ky >= 2 && kx >= 2 && ky * kx >= 15; }
 
 template <typename T, int KY, int KX>

@@ -13,7 +13,13 @@ int launch_row(const S2Args<T>& a, int kx, int op, int batch, int vw, cudaStream
     case 3: return launch_op<T, 1, 3>(a, op, batch, vw, s);
     case 4: return launch_op<T, 1, 4>(a, op, batch, vw, s);
     case 5: return launch_op<T, 1, 5>(a, op, batch, vw, s);
+    case 6: return launch_op<T, 1, 6>(a, op, batch, vw, s);
     case 7: return launch_op<T, 1, 7>(a, op, batch, vw, s);
+    case 8: return launch_op<T, 1, 8>(a, op, batch, vw, s);
+    case 9: return launch_op<T, 1, 9>(a, op, batch, vw, s);
+    case 11: return launch_op<T, 1, 11>(a, op, batch, vw, s);
+    case 13: return launch_op<T, 1, 13>(a, op, batch, vw, s);
+    case 15: return launch_op<T, 1, 15>(a, op, batch, vw, s);
   }
   return KX_ERR_UNSUPPORTED;
 }

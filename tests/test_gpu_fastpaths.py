@@ -74,7 +74,8 @@ def test_stencil2d_random_geometry(kex, seed):
     _check_affine(got, x, (ky, kx), (1, 1), border, taps, coefs, bias)
 
 
-_WIDE = [(1, 4), (4, 4), (3, 5), (5, 3), (2, 5), (4, 1), (1, 7), (7, 1), (7, 7), (5, 2), (4, 3), (2, 4)]
+_WIDE = [(1, 4), (4, 4), (3, 5), (5, 3), (2, 5), (4, 1), (1, 7), (7, 1), (7, 7), (5, 2), (4, 3), (2, 4),
+         (1, 6), (1, 8), (1, 9), (1, 11), (1, 13), (1, 15)]
 
 
 @pytest.mark.parametrize("ki", range(len(_WIDE)))
@@ -183,6 +184,25 @@ def test_stencil2d_dense_tables_are_not_mistaken_for_outer_products(kex):
         got = kex.kernel_map({(lambda v: np.sum(v * wt)): ()}, x.shape, (k, k), (1, 1), ((1, 1), (2, 2)), False)(x)
         assert _last_kernel() == ("stencil2d_kernel" if k <= 7 else "generic_map_kernel")
         _check_affine(got, x, (k, k), (1, 1), ((1, 1), (2, 2)), taps, [float(wt[t]) for t in taps])
+
+
+@pytest.mark.parametrize("k", [6, 9, 11, 15])
+def test_fir_filter_on_a_1d_array(kex, k):
+    """1-D arrays are one-row windows: FIR filters / moving averages of up to 15 taps on the row-march kernel."""
+    rng = np.random.default_rng(9700 + k)
+    x = rng.standard_normal(100003).astype(np.float32)
+    w = rng.standard_normal(k).astype(np.float32)
+    taps = [(t,) for t in range(k)]
+    got = kex.kmap(kernel_size=(k,), padding="same")(lambda v: np.sum(v * w))(x)
+    assert _last_kernel() == "stencil2d_kernel"
+    _check_affine(got, x, (k,), (1,), ko.resolve_padding("same", (k,)), taps, [float(c) for c in w])
+    xi = rng.integers(-1000, 1000, 4096).astype(np.int32)
+    goti = kex.kmap(kernel_size=(k,), padding="valid")(lambda v: np.sum(v))(xi)
+    assert _last_kernel() == "stencil2d_kernel"
+    np.testing.assert_array_equal(goti, ko.reduce_map(xi, (k,), (1,), ((0, 0),), "sum"))
+    gotm = kex.kmap(kernel_size=(k,), padding="same")(lambda v: np.max(v))(xi)
+    assert _last_kernel() == "stencil2d_kernel"
+    np.testing.assert_array_equal(gotm, ko.reduce_map(xi, (k,), (1,), ko.resolve_padding("same", (k,)), "max"))
 
 
 def test_window_max_propagates_nan_like_numpy(kex):
