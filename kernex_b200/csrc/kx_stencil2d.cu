@@ -70,7 +70,8 @@ int run(const MapArgs& m, const KxProgram& p, int ay, int ax, int64_t batch, cud
     if (seen[slot]) return KX_ERR_UNSUPPORTED;  // duplicate tap: leave it to the generic kernel
     seen[slot] = true;
     ++n_seen;
-    if (slot < 64) a.mask |= 1ull << slot;
+    if (slot < 32) a.mask |= 1u << slot;
+    else if (slot < 64) a.mask_hi |= 1u << (slot - 32);
     dense[slot] = (T)p.coef[t];
     if (slot != t - f.tap_begin) dense_order = false;
   }

@@ -41,7 +41,7 @@ struct S2Args {
   int hin, win, hout, wout;
   int ly, lx;                  // left borders
   int th;                      // output rows per block
-  uint64_t mask;               // bit ky*KX+kx set = tap present (kAffine: windows of at most 7x7)
+  uint32_t mask, mask_hi;      // bit ky*KX+kx set = tap present (kAffine: at most 49 taps; two words keep the tests 32-bit)
   int use_box, by0, by1, bx0, bx1;  // offset maps: outputs outside the box copy the window centre
   float post_mul;              // != 0: result = (bias + sum) * post_mul, post_mul = 1 / n (window mean), f32 only
   T bias;
@@ -235,7 +235,7 @@ stencil2d_kernel(const __grid_constant__ S2Args<T> a) {
           for (int ky = 0; ky < KY; ++ky) {
 #pragma unroll
             for (int kx = 0; kx < KX; ++kx) {
-              if (a.mask & (1ull << (ky * KX + kx))) {
+              if ((ky * KX + kx < 32) ? (a.mask & (1u << ((ky * KX + kx) & 31))) : (a.mask_hi & (1u << ((ky * KX + kx) & 31)))) {
 #pragma unroll
                 for (int i = 0; i < kCols; ++i)
                   acc[i] = mad_wrap(coef[ky * KX + kx], q[u + ky][SHIFT + kx + i], acc[i]);
