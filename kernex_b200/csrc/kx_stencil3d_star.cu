@@ -84,15 +84,19 @@ __device__ __forceinline__ void store4(T* o, const T (&acc)[4], int n_valid) {
   }
 }
 
-template <typename T, int SHIFT, bool FULL>
+// PAIR (opt-in, KX_STAR_PAIR=1): a 4-stage ring and ONE block barrier per TWO planes -- the r1b ncu capture has 30 % of
+// the stall samples on the per-plane barrier.  Written at the end of round 1 without GPU time left: NOT yet run on
+// hardware, off by default.
+template <typename T, int SHIFT, bool FULL, bool PAIR>
 __global__ void __launch_bounds__(kThreads3)
 stencil3d_star_kernel(const __grid_constant__ StarArgs<T> a) {
+  constexpr int STG = PAIR ? 4 : kStages;
   constexpr int NV = (SHIFT + 6 + 3) / 4;          // aligned 4-vectors covering the 6 needed columns
   constexpr int SW = kTX + 4 * NV;                  // tile width (columns), multiple of 4
   constexpr int SR = kTY + 2;
   constexpr int CH = SW / 4;
   constexpr int NCH = (SR * CH + kThreads3 - 1) / kThreads3;   // 16-byte chunks per thread per plane
-  __shared__ __align__(16) T smem[kStages * SR * SW];
+  __shared__ __align__(16) T smem[STG * SR * SW];
 
   const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * 32 + tx;
   const int b = blockIdx.z / a.nzc;
@@ -127,7 +131,7 @@ stencil3d_star_kernel(const __grid_constant__ StarArgs<T> a) {
     const int gz = gz0 + pl;
     const bool z_ok = (gz >= 0) && (gz < a.din);
     const T* src = in + (int64_t)gz * plane_elems;
-    const unsigned dst = smem_base + (unsigned)((pl % kStages) * SR * SW * sizeof(T));
+    const unsigned dst = smem_base + (unsigned)((pl % STG) * SR * SW * sizeof(T));
 #pragma unroll
     for (int k = 0; k < NCH; ++k) {
       if (dst_off[k] != 0xffffffffu) {
@@ -153,7 +157,7 @@ stencil3d_star_kernel(const __grid_constant__ StarArgs<T> a) {
 
   // rows iy .. iy+RY+1 of a plane tile: the 6 window columns SHIFT+jx .. SHIFT+jx+5 of each
   auto read_plane = [&](int pl, T (&dst)[kRY + 2][6]) {
-    const T* t = smem + (pl % kStages) * SR * SW + iy * SW + jx;
+    const T* t = smem + (pl % STG) * SR * SW + iy * SW + jx;
 #pragma unroll
     for (int r = 0; r < kRY + 2; ++r) {
       T w[4 * NV];
@@ -206,12 +210,56 @@ stencil3d_star_kernel(const __grid_constant__ StarArgs<T> a) {
     }
   };
 
-  int pl = 0;
-  for (; pl + 1 < nplanes; pl += 2) {   // unrolled by two: the plane buffers swap roles by name
-    step(pl, bufB, bufA);
-    step(pl + 1, bufA, bufB);
+  if constexpr (!PAIR) {
+    int pl = 0;
+    for (; pl + 1 < nplanes; pl += 2) {   // unrolled by two: the plane buffers swap roles by name
+      step(pl, bufB, bufA);
+      step(pl + 1, bufA, bufB);
+    }
+    if (pl < nplanes) step(pl, bufB, bufA);
+  } else {
+    // the math of one ring step without its synchronisation
+    auto math = [&](int pl, T (&mid)[kRY + 2][6], T (&up)[kRY + 2][6]) {
+      read_plane(pl, up);
+      if (pl >= 2) {
+#pragma unroll
+        for (int r = 0; r < kRY; ++r) {
+          T acc[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            T v = a.bias;
+            if (FULL || (a.mask & 1u)) v = mad_wrap(a.c[0], below[r][i], v);
+            if (FULL || (a.mask & 2u)) v = mad_wrap(a.c[1], mid[r][i + 1], v);
+            if (FULL || (a.mask & 4u)) v = mad_wrap(a.c[2], mid[r + 1][i], v);
+            if (FULL || (a.mask & 8u)) v = mad_wrap(a.c[3], mid[r + 1][i + 1], v);
+            if (FULL || (a.mask & 16u)) v = mad_wrap(a.c[4], mid[r + 1][i + 2], v);
+            if (FULL || (a.mask & 32u)) v = mad_wrap(a.c[5], mid[r + 2][i + 1], v);
+            if (FULL || (a.mask & 64u)) v = mad_wrap(a.c[6], up[r + 1][i + 1], v);
+            acc[i] = v;
+          }
+          if (col_ok && (y0 + iy + r < a.hout)) store4(orow + (int64_t)r * a.wout, acc, n_valid);
+        }
+        orow += out_plane;
+      }
+#pragma unroll
+      for (int r = 0; r < kRY; ++r) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) below[r][i] = mid[r + 1][i + 1];
+      }
+    };
+    // prologue above issued planes 0 and 1 (kStages - 1 = 2 groups).  Per pair: both planes of the pair have
+    // landed (wait_group 0), one barrier, the next pair goes into the two stages read by the previous pair, math.
+    for (int pl = 0; pl < nplanes; pl += 2) {
+      cp_wait<0>();
+      __syncthreads();
+      if (pl + 2 < nplanes) issue(pl + 2);
+      cp_commit();
+      if (pl + 3 < nplanes) issue(pl + 3);
+      cp_commit();
+      math(pl, bufB, bufA);
+      if (pl + 1 < nplanes) math(pl + 1, bufA, bufB);
+    }
   }
-  if (pl < nplanes) step(pl, bufB, bufA);
 }
 
 template <typename T>
@@ -254,9 +302,11 @@ int run_star(const MapArgs& m, const KxProgram& p, int64_t batch, cudaStream_t s
   dim3 grid(tiles_x, tiles_y, (unsigned)(a.nzc * batch)), block(32, kTYB);
   const int shift = (((-a.lx) % 4) + 4) % 4;
   const bool full = a.mask == 0x7fu;
-#define KX_STAR(S)                                                              \
-  if (full) stencil3d_star_kernel<T, S, true><<<grid, block, 0, s>>>(a);        \
-  else stencil3d_star_kernel<T, S, false><<<grid, block, 0, s>>>(a);
+  const bool pair = getenv("KX_STAR_PAIR") != nullptr;   // opt-in variant, see the kernel
+#define KX_STAR(S)                                                                        \
+  if (full && pair) stencil3d_star_kernel<T, S, true, true><<<grid, block, 0, s>>>(a);    \
+  else if (full) stencil3d_star_kernel<T, S, true, false><<<grid, block, 0, s>>>(a);      \
+  else stencil3d_star_kernel<T, S, false, false><<<grid, block, 0, s>>>(a);
   switch (shift) {
     case 0: KX_STAR(0) break;
     case 1: KX_STAR(1) break;

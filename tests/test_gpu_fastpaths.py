@@ -486,3 +486,20 @@ def test_conv_rows_batched_and_host_weights(kex):
     taps = list(itertools.product(range(C), range(3), range(3)))
     for b in range(B):
         _check_affine(got[b].cpu().numpy(), x[b], (C, 3, 3), (1, 1, 1), border[1:], taps, [float(w[t]) for t in taps])
+
+
+@pytest.mark.skipif(not __import__("os").environ.get("KX_TEST_EXPERIMENTAL"),
+                    reason="opt-in kernel variants written without GPU time left (set KX_TEST_EXPERIMENTAL=1)")
+def test_star_kernel_pair_variant_is_bit_identical(kex, monkeypatch):
+    """KX_STAR_PAIR=1: one block barrier per two planes (kx_stencil3d_star.cu).  Must equal the default kernel bit for bit."""
+    rng = np.random.default_rng(31)
+    lap = kex.kmap(kernel_size=(3, 3, 3), padding="same", relative=True)(
+        lambda v: v[1, 0, 0] + v[-1, 0, 0] + v[0, 1, 0] + v[0, -1, 0] + v[0, 0, 1] + v[0, 0, -1] - 6 * v[0, 0, 0])
+    for shape in [(70, 40, 260), (33, 17, 132), (5, 64, 128), (2, 20, 64)]:
+        x = torch.from_numpy(rng.standard_normal(shape).astype(np.float32)).cuda()
+        want = lap(x).clone()
+        assert _last_kernel() == "stencil3d_star_kernel"
+        monkeypatch.setenv("KX_STAR_PAIR", "1")
+        got = lap(x)
+        monkeypatch.delenv("KX_STAR_PAIR")
+        assert torch.equal(got, want)
