@@ -281,6 +281,11 @@ int try_stencil3d(const MapArgs& m, const KxProgram& p, cudaStream_t s) {
     const int rc = try_stencil3d_star(m, p, batch, s);
     if (rc != KX_ERR_UNSUPPORTED) return rc;
   }
+  if (batch <= 65535) {
+    // opt-in (KX_DENSE3D_PLANES=1): plane-stationary dense 3x3x3 kernel (kx_stencil3d_dense.cu), not yet the default
+    const int rc = try_stencil3d_dense(m, p, batch, s);
+    if (rc != KX_ERR_UNSUPPORTED) return rc;
+  }
   {
     // dense 3x3x3 windows: the conv row-ring kernel with the three z planes as channels (kx_conv2d.cu)
     const int rc = try_conv_dense3d(m, p, batch, s);

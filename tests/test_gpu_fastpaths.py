@@ -503,3 +503,33 @@ def test_star_kernel_pair_variant_is_bit_identical(kex, monkeypatch):
         got = lap(x)
         monkeypatch.delenv("KX_STAR_PAIR")
         assert torch.equal(got, want)
+
+
+@pytest.mark.skipif(not __import__("os").environ.get("KX_TEST_EXPERIMENTAL"),
+                    reason="opt-in kernel variants written without GPU time left (set KX_TEST_EXPERIMENTAL=1)")
+@pytest.mark.parametrize("case", range(len(_DENSE3D)))
+@pytest.mark.parametrize("dtype", ["f32", "i32"])
+def test_plane_stationary_dense3d_kernel(kex, case, dtype, monkeypatch):
+    """KX_DENSE3D_PLANES=1: stencil3d_dense_kernel (kx_stencil3d_dense.cu) against the oracle on the dense-3-D cases."""
+    shape, pad = _DENSE3D[case]
+    rng = np.random.default_rng(7100 + case)
+    ks = (3, 3, 3)
+    border = ko.resolve_padding(pad, ks)
+    taps = list(itertools.product(range(3), range(3), range(3)))
+    if dtype == "f32":
+        x = rng.standard_normal(shape).astype(np.float32)
+        coefs, bias = [float(c) for c in rng.standard_normal(27)], 0.25
+    else:
+        x = rng.integers(-1000, 1000, shape).astype(np.int32)
+        coefs, bias = [int(c) or 3 for c in rng.integers(-9, 10, 27)], 2
+
+    def fn(v):
+        acc = bias
+        for t, cf in zip(taps, coefs):
+            acc = acc + cf * v[t]
+        return acc
+
+    monkeypatch.setenv("KX_DENSE3D_PLANES", "1")
+    got = kex.kernel_map({fn: ()}, shape, ks, (1, 1, 1), border, False)(x)
+    assert _last_kernel() == "stencil3d_dense_kernel"
+    _check_affine(got, x, ks, (1, 1, 1), border, taps, coefs, bias)
