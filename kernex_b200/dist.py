@@ -24,7 +24,7 @@ from dataclasses import dataclass
 import torch
 import torch.distributed as dist
 
-__all__ = ["SlabLayout", "exchange_halos", "exchange_halo_grads", "SlabStencil", "ColumnShardedScan",
+__all__ = ["SlabLayout", "halo_pull_plan", "exchange_halos", "exchange_halo_grads", "SlabStencil", "ColumnShardedScan",
            "column_shard_plan", "column_exchange_plan"]
 
 
@@ -95,6 +95,22 @@ class SlabLayout:
         return slice(self.halo_top, self.halo_top + self.rows)
 
 
+def halo_pull_plan(rank: int, world: int, rows: int, k0: int, border0=(0, 0)):
+    """One-sided form of :func:`exchange_halos`: ``[(my_ext_rows, peer_rank, peer_ext_rows), ...]`` -- which rows of
+    which neighbour's ``ext`` buffer fill my halos (pure geometry; the buffers all start at row 0 of their allocation)."""
+    L = SlabLayout(rank, world, rows, k0, border0)
+    plan = []
+    if not L.first and L.halo_top:       # the last send_down own rows of rank-1
+        up = SlabLayout(rank - 1, world, rows, k0, border0)
+        a = up.halo_top + rows - up.send_down
+        plan.append((slice(0, L.halo_top), rank - 1, slice(a, a + up.send_down)))
+    if not L.last and L.halo_bot:        # the first send_up own rows of rank+1
+        dn = SlabLayout(rank + 1, world, rows, k0, border0)
+        b = L.halo_top + rows
+        plan.append((slice(b, b + L.halo_bot), rank + 1, slice(dn.halo_top, dn.halo_top + dn.send_up)))
+    return plan
+
+
 def exchange_halos(ext: torch.Tensor, layout: SlabLayout, group=None):
     """Post the halo traffic of one step; returns the list of outstanding requests."""
     ops = []
@@ -140,10 +156,19 @@ class SlabStencil:
     """A kmap applied to a row-slab-decomposed global array on CUDA."""
 
     def __init__(self, func, kernel_size, relative, rows_per_rank, width=None, device=None, padding="valid",
-                 trailing_shape=None, group=None, args=()):
+                 trailing_shape=None, group=None, args=(), transport=None):
+        import os
+
         from .engine import PreparedMap
         from .resolve import resolve_padding
 
+        # "nccl" (default): isend / irecv of the halo rows.  "p2p" (opt-in, KX_DIST_TRANSPORT=p2p; written at the end
+        # of round 1 without GPU time left, not yet run on hardware): the slab lives in torch symmetric memory and every
+        # rank PULLS its halo rows out of the neighbours' buffers over NVLink peer mappings, fenced by two device-side
+        # barriers -- no NCCL kernel, no rendezvous between the ranks' host threads.
+        self.transport = transport or os.environ.get("KX_DIST_TRANSPORT", "nccl")
+        if self.transport not in ("nccl", "p2p"):
+            raise ValueError(f"transport must be 'nccl' or 'p2p', got {self.transport!r}")
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
@@ -153,7 +178,11 @@ class SlabStencil:
         border = resolve_padding(padding, kernel_size)
         self.layout = SlabLayout(self.rank, self.world, rows_per_rank, kernel_size[0], border[0])
         L = self.layout
-        self.ext = torch.zeros((L.ext_rows,) + trailing, dtype=torch.float32, device=self.device)
+        self._hdl = None
+        if self.transport == "p2p" and self.world > 1:
+            self._init_peer_memory(kernel_size[0], rows_per_rank, trailing)
+        else:
+            self.ext = torch.zeros((L.ext_rows,) + trailing, dtype=torch.float32, device=self.device)
         strides = (1,) * len(kernel_size)
         self.maps = []
         out_trailing = None
@@ -167,6 +196,31 @@ class SlabStencil:
         self.local_windows = int(self.out.numel())
         self.side = torch.cuda.Stream(device=self.device)
 
+    def _init_peer_memory(self, k0, rows, trailing):
+        """Allocate the slab in symmetric memory (same size on every rank) and map the neighbours' buffers."""
+        import torch.distributed._symmetric_memory as symm
+
+        L = self.layout
+        rows_max = rows + (k0 - 1) // 2 + k0 // 2          # the interior ranks' ext_rows: identical everywhere
+        shape = (rows_max,) + trailing
+        self._sym = symm.empty(*shape, dtype=torch.float32, device=self.device)
+        self._sym.zero_()
+        self._hdl = symm.rendezvous(self._sym, self.group if self.group is not None else dist.group.WORLD)
+        self.ext = self._sym[:L.ext_rows]
+        self._pulls = []                                     # (my ext rows, neighbour's view of the rows I need)
+        for mine, peer_rank, theirs in halo_pull_plan(self.rank, self.world, rows, k0, (L.lo, L.hi)):
+            peer = self._hdl.get_buffer(peer_rank, shape, torch.float32)
+            self._pulls.append((mine, peer[theirs]))
+
+    def _pull_halos(self):
+        """One-sided halo exchange on the current stream: barrier (every rank's own rows are final), peer reads over
+        NVLink, barrier (every rank has read, own rows may change again)."""
+        self._hdl.barrier(channel=0)
+        for mine, theirs in self._pulls:
+            if theirs.numel():
+                self.ext[mine].copy_(theirs)
+        self._hdl.barrier(channel=1)
+
     def fill_random(self, generator=None):
         self.ext[self.layout.own].normal_(generator=generator)
 
@@ -179,7 +233,10 @@ class SlabStencil:
         if self.world > 1:
             self.side.wait_stream(main)  # own rows written by earlier work on `main` must be visible
             with torch.cuda.stream(self.side):
-                reqs = exchange_halos(self.ext, self.layout, self.group)
+                if self._hdl is not None:
+                    self._pull_halos()
+                else:
+                    reqs = exchange_halos(self.ext, self.layout, self.group)
         for p, pm in self.maps:          # interior first: overlaps the exchange
             if not p.needs_halo:
                 pm(self.ext[p.in0:p.in1], out=self.out[p.out0:p.out1])

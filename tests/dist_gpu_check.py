@@ -42,6 +42,18 @@ def main():
         for _ in range(2):  # a second step must give the same answer (halos re-exchanged)
             out = slab.step()
         torch.cuda.synchronize()
+        if os.environ.get("KX_TEST_EXPERIMENTAL"):   # opt-in: halo rows pulled from peer memory instead of NCCL send/recv
+            p2p = SlabStencil(fn, kernel_size=ksize, relative=True, rows_per_rank=rows, trailing_shape=trailing,
+                              device=dev, padding=padding, transport="p2p")
+            p2p.set_local(slab.ext[slab.layout.own])
+            for _ in range(2):
+                out2 = p2p.step()
+            torch.cuda.synchronize()
+            same2 = torch.tensor([1 if torch.equal(out2, out) else 0], device=dev)
+            dist.all_reduce(same2, op=dist.ReduceOp.MIN)
+            ok = ok and bool(same2.item())
+            if rank == 0:
+                print(f"  p2p transport: {'bit-identical' if same2.item() else 'MISMATCH'}", flush=True)
         own = slab.ext[slab.layout.own].contiguous()
         parts = [torch.empty_like(own) for _ in range(world)]
         dist.all_gather(parts, own)
