@@ -70,7 +70,8 @@ if want("fir"):
         f = kex.kmap(kernel_size=(k,), padding="same")(fn)
         y = f(x)
         med, _ = timeit(lambda: f(x), 4)
-        rep(f"{name} on a 1-D array of 2^27 fp32", x.numel() * 8, med, y.numel())
+        rep(f"{name} on a 1-D array of 2^27 fp32" + (" (KX_FOLD_1D)" if os.environ.get("KX_FOLD_1D") else ""),
+            x.numel() * 8, med, y.numel())
     del x, y
     torch.cuda.empty_cache()
 

@@ -502,10 +502,13 @@ def kernel_map(func_map: dict, shape, kernel_size, strides, border, relative: bo
     _validate(shape, kernel_size, strides, border)
 
     folded = _fold_leading_axes(func_map, shape, kernel_size, strides, border, relative)
+    fold1d = _fold_1d(func_map, shape, kernel_size, strides, border, relative)
 
     def call(array, *a, **k):
         if folded is not None:
             return folded(array, *a, **k)
+        if fold1d is not None and fold1d.applies(array, a, k):
+            return fold1d(array, *a, **k)
         piped = _try_host_pipeline(func_map, shape, kernel_size, strides, border, relative, array, a, k)
         if piped is not None:
             return piped
@@ -537,6 +540,48 @@ def _fold_leading_axes(func_map, shape, kernel_size, strides, border, relative):
     inner = kernel_map(fmap2, shape2, (1,) + tuple(kernel_size[n_fold:]), (1,) + tuple(strides[n_fold:]),
                        ((0, 0),) + tuple(border[n_fold:]), relative)
     return _FoldedCall(inner, shape, shape2, n_fold)
+
+
+def _fold_1d(func_map, shape, kernel_size, strides, border, relative):
+    """Opt-in (``KX_FOLD_1D=1``): large 1-D arrays run as 2-D row problems plus a seam fix-up (``fold1d.py``)."""
+    import os
+
+    from .fold1d import plan_fold
+    if not os.environ.get("KX_FOLD_1D") or len(shape) != 1 or len(func_map) != 1 or any(v != () for v in func_map.values()):
+        return None
+    (n,), (k,), (st,), ((lo, hi),) = shape, kernel_size, strides, border
+    w = plan_fold(int(n), int(k), int(lo), int(hi), int(st))
+    if w is None:
+        return None
+    (f,) = func_map
+
+    def lifted(win, *a, _f=f, **kw):        # the (1, k) window of the folded array is the user's 1-D window
+        return _f(win.reshape((k,)), *a, **kw)
+
+    main = kernel_map({lifted: ()}, (n // w, w), (1, k), (1, 1), ((0, 0), (lo, k - 1 - lo)), relative)
+    seam = kernel_map({lifted: ()}, (n // w - 1, 2 * (k - 1)), (1, k), (1, 1), ((0, 0), (0, 0)), relative) if k > 1 else None
+    return _Fold1dCall(main, seam, int(n), int(k), int(lo), int(hi), w)
+
+
+class _Fold1dCall:
+    def __init__(self, main, seam, n, k, lo, hi, w):
+        self.main, self.seam, self.n, self.k, self.lo, self.hi, self.w = main, seam, n, k, lo, hi, w
+
+    def applies(self, array, a, kw):
+        """Device-resident contiguous tensors outside autograd (the seam write-back is an in-place strided copy)."""
+        if not isinstance(array, torch.Tensor) or not array.is_cuda or not array.is_contiguous():
+            return False
+        if tuple(array.shape) != (self.n,):
+            return False
+        if torch.is_grad_enabled() and (array.requires_grad or any(
+                isinstance(v, torch.Tensor) and v.requires_grad for v in list(a) + list(kw.values()))):
+            return False
+        return True
+
+    def __call__(self, array, *a, **kw):
+        from .fold1d import folded_map_1d
+        return folded_map_1d(array, self.k, self.lo, self.hi, self.w,
+                             lambda t: self.main(t, *a, **kw), lambda t: self.seam(t, *a, **kw))
 
 
 class _FoldedCall:

@@ -533,3 +533,21 @@ def test_plane_stationary_dense3d_kernel(kex, case, dtype, monkeypatch):
     got = kex.kernel_map({fn: ()}, shape, ks, (1, 1, 1), border, False)(x)
     assert _last_kernel() == "stencil3d_dense_kernel"
     _check_affine(got, x, ks, (1, 1, 1), border, taps, coefs, bias)
+
+
+@pytest.mark.skipif(not __import__("os").environ.get("KX_TEST_EXPERIMENTAL"),
+                    reason="opt-in paths written without GPU time left (set KX_TEST_EXPERIMENTAL=1)")
+@pytest.mark.parametrize("k,pad", [(3, "same"), (3, "valid"), (15, "same"), (6, ((2, 1),)), (9, "valid")])
+def test_folded_1d_map_equals_the_one_row_launch(kex, k, pad, monkeypatch):
+    """KX_FOLD_1D=1 (kernex_b200/fold1d.py): a large 1-D array as rows + seam fix-up must equal the plain launch bit for bit."""
+    rng = np.random.default_rng(9900 + k)
+    x = torch.from_numpy(rng.standard_normal(1 << 22).astype(np.float32)).cuda()
+    w = rng.standard_normal(k).astype(np.float32)
+    want = kex.kmap(kernel_size=(k,), padding=pad)(lambda v: np.sum(v * w))(x)
+    monkeypatch.setenv("KX_FOLD_1D", "1")
+    got = kex.kmap(kernel_size=(k,), padding=pad)(lambda v: np.sum(v * w))(x)
+    assert got.shape == want.shape and torch.equal(got, want)
+    xi = torch.from_numpy(rng.integers(-1000, 1000, 1 << 22).astype(np.int32)).cuda()
+    goti = kex.kmap(kernel_size=(k,), padding=pad)(lambda v: np.max(v))(xi)
+    monkeypatch.delenv("KX_FOLD_1D")
+    assert torch.equal(goti, kex.kmap(kernel_size=(k,), padding=pad)(lambda v: np.max(v))(xi))
