@@ -143,6 +143,8 @@ generic_vjp_input_kernel(const __grid_constant__ KxGeom g, const __grid_constant
       }
       if (ok) acc = fmaf(coef_dev ? coef_dev[t] : p.coef[t], gout[off], acc);
     }
+    // forward = (bias + sum) / post_div  =>  the cotangent carries the same final division
+    if (p.func[0].post_div != 0.f) acc = (TC)((float)acc / p.func[0].post_div);
     dx[i] = acc;
   }
 }
@@ -185,13 +187,14 @@ generic_vjp_coef_stage1(const __grid_constant__ KxGeom g, const __grid_constant_
 }
 
 // stage 2: fixed-order sum of the per-block partials (deterministic)
-__global__ void generic_vjp_coef_stage2(const float* __restrict__ partial, float* __restrict__ dcoef, int nblocks) {
+__global__ void generic_vjp_coef_stage2(const float* __restrict__ partial, float* __restrict__ dcoef, int nblocks,
+                                        float post_div) {
   const int t = blockIdx.x;
   float acc = 0.f;
   for (int i = threadIdx.x; i < nblocks; i += 32) acc += partial[(int64_t)t * nblocks + i];
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-  if (threadIdx.x == 0) dcoef[t] = acc;
+  if (threadIdx.x == 0) dcoef[t] = post_div != 0.f ? acc / post_div : acc;
 }
 
 int vjp_coef_blocks(int64_t n_win) {
@@ -399,7 +402,7 @@ int launch_generic_vjp_coef(const KxGeom& g, const KxProgram& prog, const void* 
                                                     n_win);
   int rc = after_launch("generic_vjp_coef_stage1");
   if (rc) return rc;
-  generic_vjp_coef_stage2<<<ntaps, 32, 0, s>>>((const float*)scratch, (float*)dcoef, nb);
+  generic_vjp_coef_stage2<<<ntaps, 32, 0, s>>>((const float*)scratch, (float*)dcoef, nb, (float)prog.func[0].post_div);
   return after_launch("generic_vjp_coef_stage2");
 }
 

@@ -309,6 +309,17 @@ def column_exchange_plan(nx_global: int, world: int, rank: int, t_rows: int, rl:
     c0, c1 = min(rank * per, nx_global), min((rank + 1) * per, nx_global)
     gl = 0 if rank == 0 else -(-t_rows * rl // 4) * 4
     gr = 0 if c1 >= nx_global else -(-t_rows * rr // 4) * 4
+    # every rank must own columns, and a ghost zone must lie entirely inside the NEIGHBOUR's own columns (it is
+    # refreshed from that one rank): otherwise the isend / irecv sizes of the two sides disagree (hang) or the
+    # ghost covers columns nobody sends (silently wrong values)
+    last_width = nx_global - (world - 1) * per
+    if last_width <= 0:
+        raise ValueError(f"column exchange: nx={nx_global} leaves rank(s) without columns at world={world} "
+                         f"(shards are {per} columns wide)")
+    need_l, need_r = -(-t_rows * rl // 4) * 4, -(-t_rows * rr // 4) * 4
+    if world > 1 and (need_l > per or need_r > per):   # (the last shard may be narrower: its ghost is clipped to nx)
+        raise ValueError(f"column exchange: ghost zones of {need_l} / {need_r} columns do not fit inside the neighbouring "
+                         f"shards ({per} columns, last shard {last_width}); use fewer ranks or exchange=False")
     lo, hi = c0 - gl, min(nx_global, c1 + gr)
     return lo, hi - lo, c0 - lo, c1 - lo, gl, hi - c1
 

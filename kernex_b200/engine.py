@@ -37,6 +37,14 @@ __all__ = ["kernel_map", "kernel_scan", "offset_kernel_map", "offset_kernel_scan
 _NP2KX = {np.dtype(np.float32): _lib.KX_F32, np.dtype(np.int32): _lib.KX_I32}
 _KX2TORCH = {_lib.KX_F32: torch.float32, _lib.KX_I32: torch.int32}
 _TORCH2KX = {torch.float32: _lib.KX_F32, torch.int32: _lib.KX_I32}
+# JAX keeps narrow integer / bool arrays narrow (results wrap at 8 / 16 bits, `sum` promotes, bool arithmetic is
+# logical); widening them silently to int32 would return different values AND a different dtype than the reference,
+# so they are refused instead (float64 / int64 are demoted exactly like JAX without x64).
+_NARROW_NP = (np.dtype(np.int16), np.dtype(np.int8), np.dtype(np.uint8), np.dtype(np.uint16), np.dtype(np.bool_))
+_NARROW_TORCH = (torch.int16, torch.int8, torch.uint8, torch.bool)
+_NARROW_MSG = ("dtype {} is not supported: the engine computes in float32 / int32 and will not widen a narrow integer "
+               "or bool array silently (the reference keeps the narrow dtype and its wraparound); cast the input "
+               "explicitly, e.g. x.astype(np.int32)")
 
 
 # --------------------------------------------------------------------------- #
@@ -79,8 +87,10 @@ class _Arr:
             host = np.asarray(array)
             if host.dtype == np.float64:       # JAX without x64 demotes too
                 host = host.astype(np.float32)
-            elif host.dtype in (np.int64, np.int16, np.int8, np.uint8, np.bool_):
+            elif host.dtype == np.int64:         # ... and int64 -> int32
                 host = host.astype(np.int32)
+            elif host.dtype in _NARROW_NP:
+                raise UnsupportedStencilError(_NARROW_MSG.format(host.dtype))
             if host.dtype not in _NP2KX:
                 raise UnsupportedStencilError(f"dtype {host.dtype} is not supported (float32 / int32 only)")
             _require_cuda()
@@ -91,6 +101,8 @@ class _Arr:
                 t = t.float()
             elif t.dtype == torch.int64:
                 t = t.int()
+            elif t.dtype in _NARROW_TORCH:
+                raise UnsupportedStencilError(_NARROW_MSG.format(t.dtype))
             if t.dtype not in _TORCH2KX:
                 raise UnsupportedStencilError(f"dtype {t.dtype} is not supported (float32 / int32 only)")
             if not t.is_cuda:
@@ -363,14 +375,73 @@ def _arg_signature(v):
     raise TypeError("unhashable argument kind")
 
 
+def _captured_signature(v, depth):
+    """Signature of a value a window function captured (closure cell / referenced global)."""
+    import types
+    if isinstance(v, (types.ModuleType, type, types.BuiltinFunctionType)) or isinstance(v, np.ufunc):
+        return ("id", id(v))
+    if isinstance(v, (types.FunctionType, types.MethodType)) or hasattr(v, "__wrapped__"):
+        return _func_fingerprint(v, depth + 1)
+    if isinstance(v, (list, tuple)) and len(v) <= 64:
+        return (type(v).__name__,) + tuple(_captured_signature(e, depth) for e in v)
+    if isinstance(v, dict) and len(v) <= 64:
+        return ("dict",) + tuple((repr(n), _captured_signature(e, depth)) for n, e in v.items())
+    if isinstance(v, torch.Tensor) and (v.is_cuda or v.requires_grad):
+        raise TypeError("captured device tensor: its values are baked at trace time, not cached")
+    return _arg_signature(v)
+
+
+def _func_fingerprint(f, depth=0):
+    """The tracer bakes the values a window function reads from its closure and globals (dt, alpha, host weight
+    tables) into the coefficients, while the un-jitted reference re-evaluates the function on every call
+    (kernel_interface.py:130-157).  The plan cache therefore keys on those VALUES too: a captured variable that
+    changes -- rebinding or in-place mutation of a small array -- gives a new key and a fresh trace.  Anything the
+    fingerprint cannot describe (large arrays, device tensors, arbitrary objects) raises -> the call is not cached."""
+    if depth > 3:
+        raise TypeError("captured functions nest too deeply")
+    fn = getattr(f, "__func__", f)
+    code = getattr(fn, "__code__", None)
+    if code is None:
+        fn = getattr(f, "__wrapped__", None) or getattr(type(f), "__call__", None)
+        code = getattr(fn, "__code__", None)
+        if code is None:
+            raise TypeError("callable without code object")
+    parts = [("code", id(code))]
+    for name, cell in zip(code.co_freevars, fn.__closure__ or ()):
+        try:
+            val = cell.cell_contents
+        except ValueError:            # empty cell
+            continue
+        parts.append((name, _captured_signature(val, depth)))
+    glb = fn.__globals__
+    names = set(code.co_names)
+    for const in code.co_consts:      # nested lambdas / comprehensions read globals too
+        if hasattr(const, "co_names"):
+            names.update(const.co_names)
+    for name in sorted(names):
+        if name in glb:
+            parts.append((name, _captured_signature(glb[name], depth)))
+    if getattr(fn, "__defaults__", None):
+        parts.append(("defaults", tuple(_captured_signature(v, depth) for v in fn.__defaults__)))
+    if getattr(fn, "__kwdefaults__", None):
+        parts.append(("kwdefaults", tuple((n, _captured_signature(v, depth)) for n, v in sorted(fn.__kwdefaults__.items()))))
+    return tuple(parts)
+
+
+def clear_plan_cache():
+    """Drop every cached trace (public: ``kernex_b200.clear_plan_cache()``)."""
+    _PLAN_CACHE.clear()
+
+
 def _plan_key(tag, func_map, shape, kernel_size, strides, border, relative, in_kx, a=(), k=None):
     try:
         keys = repr([v for v in func_map.values()])
         sig = tuple(_arg_signature(v) for v in a) + tuple((n, _arg_signature(v)) for n, v in sorted((k or {}).items()))
+        captured = tuple(_func_fingerprint(f) for f in func_map)
     except Exception:
         return None
     return (tag, tuple(id(f) for f in func_map), keys, shape, kernel_size, strides, border, bool(relative), in_kx,
-            sig)
+            sig, captured)
 
 
 def _map_plan(func_map, shape, kernel_size, strides, border, relative, in_kx, a, k):
@@ -603,7 +674,7 @@ def _try_host_pipeline(func_map, shape, kernel_size, strides, border, relative, 
     if tuple(array.shape) != tuple(shape) or not array.flags.c_contiguous:
         return None
     t_host = torch.from_numpy(array)
-    if not hostpipe.eligible(array, t_host, strides, a, k):
+    if not hostpipe.eligible(array, t_host, strides, a, k, func_map):
         return None
     _require_cuda()
     out = hostpipe.pipelined_map(func_map, shape, kernel_size, strides, border, relative, t_host)

@@ -30,7 +30,11 @@ SLAB_BYTES = int(os.environ.get("KX_HOSTPIPE_SLAB_MB", "64")) << 20   # target s
 DEPTH = 3                   # slabs in flight
 
 
-def eligible(host: np.ndarray, t_host: torch.Tensor, strides, a, k) -> bool:
+def eligible(host: np.ndarray, t_host: torch.Tensor, strides, a, k, func_map=None) -> bool:
+    # Region keys are GLOBAL window-centre coordinates while every slab launch sees slab-local ones, so only
+    # key-less single-function maps are cut into slabs; meshes take the plain (whole-array) path.
+    if func_map is not None and (len(func_map) != 1 or any(tuple(v) != () for v in func_map.values())):
+        return False
     return (host.nbytes >= MIN_BYTES and host.ndim >= 1 and t_host.is_pinned() and not a and not k
             and host.flags.c_contiguous and host.dtype in (np.float32, np.int32))
 

@@ -45,3 +45,37 @@ def test_halo_pull_plan_fills_the_halos_like_the_two_sided_exchange(world, rows,
     for r, L in enumerate(layouts):
         g0 = r * rows - L.halo_top
         np.testing.assert_array_equal(exts[r], glob[g0:g0 + L.ext_rows])
+
+
+@pytest.mark.parametrize("world", [2, 3, 4])
+def test_column_exchange_plan_rejects_shards_narrower_than_their_ghosts(world):
+    """The exchange form refreshes a ghost zone from ONE neighbour: a ghost wider than the neighbouring shard, or a
+    rank left without columns after rounding the shard width up to 4, must raise instead of hanging / returning
+    garbage; and every accepted plan pairs each irecv with an isend of the same size."""
+    from kernex_b200.dist import column_exchange_plan
+    t_rows = 64
+    for nx in (world * 64 - 3, world * 64 + 1, world * 129 + 2, 4099, 1000 + world):
+        for rl, rr in ((1, 0), (1, 1), (2, 2), (0, 1)):
+            try:
+                plans = [column_exchange_plan(nx, world, r, t_rows, rl, rr) for r in range(world)]
+            except ValueError:
+                per = -(-nx // world)
+                per += (-per) % 4
+                need = max(-(-t_rows * rl // 4) * 4, -(-t_rows * rr // 4) * 4)
+                assert need > per or nx - (world - 1) * per <= 0
+                continue
+            covered = 0
+            for r, (base, width, k0, k1, gl, gr) in enumerate(plans):
+                assert base >= 0 and base + width <= nx and k1 > k0      # no negative base, nobody is empty
+                assert base + k0 == covered
+                covered += k1 - k0
+                if r > 0:                                                 # my left ghost = the left neighbour's last gl own columns
+                    pb, pw, pk0, pk1, _, pgr = plans[r - 1]
+                    assert gl <= pk1 - pk0 and base == pb + pk1 - gl
+                    assert pgr <= k1 - k0                                 # its right ghost = my first pgr own columns
+                    assert pb + pk1 + pgr == base + k0 + pgr
+            assert covered == nx
+    with pytest.raises(ValueError):
+        column_exchange_plan(world * 8, world, 1, t_rows, 1, 0)           # 8-column shards, 64-column ghosts
+    with pytest.raises(ValueError):
+        column_exchange_plan(9, 4, 0, 1, 1, 0)                            # shards rounded up to 4: rank 3 is empty

@@ -425,8 +425,10 @@ def test_weight_gradient_matches_oracle(kex):
     y = conv(xt, wt)
     (y * g).sum().backward()
     b = ((0, 0), (1, 1), (1, 1))
-    dw = ko.weight_grad(x, g.cpu().numpy(), (C, 3, 3), (1, 1, 1), b)
-    np.testing.assert_allclose(wt.grad.cpu().numpy(), dw, rtol=1e-4, atol=1e-4)
+    from vjp_ref import assert_within, dw_reference, dx_reference
+    taps = list(itertools.product(range(C), range(3), range(3)))
+    dw, dw_mag = dw_reference(x, g.cpu().numpy(), (C, 3, 3), (1, 1, 1), b, taps)
+    assert_within(wt.grad.cpu().numpy().reshape(-1), dw, dw_mag, "dW")      # 1e-5 * sum |g x|
     # dx = flipped-tap stencil of g: compare against finite structure via float64 numpy
     dx = np.zeros_like(x, dtype=np.float64)
     gp = np.pad(g.cpu().numpy()[0].astype(np.float64), 1)
@@ -435,7 +437,9 @@ def test_weight_gradient_matches_oracle(kex):
             for bb in range(3):
                 # x[c, i+a-1, j+bb-1] contributes w[c,a,bb] to out[i,j]
                 dx[c] += w[c, a, bb] * gp[2 - a:2 - a + H, 2 - bb:2 - bb + H]
-    np.testing.assert_allclose(xt.grad.cpu().numpy(), dx, rtol=1e-4, atol=1e-4)
+    dx2, dx_mag = dx_reference(g.cpu().numpy(), (C, H, H), (C, 3, 3), (1, 1, 1), b, taps, [float(w[t]) for t in taps])
+    np.testing.assert_allclose(dx, dx2, rtol=1e-12, atol=1e-12)               # the two float64 transposes agree
+    assert_within(xt.grad.cpu().numpy(), dx2, dx_mag, "dx")                  # 1e-5 * sum |c g|
 
 
 @pytest.mark.parametrize("case", range(12))
@@ -470,8 +474,9 @@ def test_conv_rows_kernels_geometry(kex, case):
     if not integer:
         g = rng.standard_normal(tuple(got.shape)).astype(np.float32)
         (dw,) = torch.autograd.grad(got, wt, torch.from_numpy(g).cuda())
-        want = ko.weight_grad(x, g, (C, 3, 3), (1, 1, 1), border)
-        np.testing.assert_allclose(dw.cpu().numpy(), want, rtol=2e-4, atol=2e-4 * float(np.sqrt(H * W)))
+        from vjp_ref import assert_within, dw_reference
+        want, mag = dw_reference(x, g, (C, 3, 3), (1, 1, 1), border, taps)
+        assert_within(dw.cpu().numpy().reshape(-1), want, mag, "dW")          # 1e-5 * sum |g x|
 
 
 def test_conv_rows_batched_and_host_weights(kex):

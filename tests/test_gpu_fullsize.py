@@ -77,6 +77,110 @@ def test_config3a_conv_full_size(kex):
     torch.cuda.empty_cache()
 
 
+def test_config2_backward_full_size(kex):
+    """configs[1] "plus its custom_vjp backward" at 16384^2: dx = flipped-tap stencil of the (16382, 16382)
+    cotangent.  float64 transpose on row bands (top edge, interior, bottom edge) at 1e-5 * sum |c g|, exact
+    power-of-two linearity, exact annihilation of a constant cotangent in the interior, and the adjoint identity
+    <L x, g> == <x, L^T g> in float64 over the whole grid."""
+    from vjp_ref import assert_within, dx_reference
+    n = 16384
+    gen = torch.Generator(device="cuda").manual_seed(7)
+    x = torch.randn((n, n), device="cuda", generator=gen).requires_grad_()
+    lap = kex.kmap(kernel_size=(3, 3), padding="valid", relative=True)(
+        lambda v: (0 * v[1, -1] + 1 * v[1, 0] + 0 * v[1, 1] + 1 * v[0, -1] + -4 * v[0, 0] + 1 * v[0, 1]
+                   + 0 * v[-1, -1] + 1 * v[-1, 0] + 0 * v[-1, 1]))
+    y = lap(x)
+    g = torch.randn((n - 2, n - 2), device="cuda", generator=gen)
+    (dx,) = torch.autograd.grad(y, x, g, retain_graph=True)
+    assert _last_kernel() == "stencil2d_kernel" and dx.shape == (n, n)
+    taps, coefs = [(2, 1), (1, 0), (1, 1), (1, 2), (0, 1)], [1.0, 1.0, -4.0, 1.0, 1.0]
+    border = ((0, 0), (0, 0))
+    # dx rows [r0, r1) depend on cotangent rows [r0-2, r1): run the float64 transpose on that band of g as if it
+    # were the whole cotangent of a (rows+2, n) grid and compare the rows whose every contribution is in the band
+    for r0, r1 in ((0, 64), (8000, 8064), (n - 64, n)):
+        j0, j1 = max(r0 - 2, 0), min(r1, n - 2)
+        gb = g[j0:j1].cpu().numpy()
+        want, mag = dx_reference(gb, (j1 - j0 + 2, n), (3, 3), (1, 1), border, taps, coefs)
+        # band-local row i is global row j0 + i; rows r0..r1 are complete when j0 <= r - 2 or r < 2, and r <= j1 + 1 ...
+        lo = r0 - j0
+        hi = lo + (r1 - r0)
+        assert_within(dx[r0:r1].cpu().numpy(), want[lo:hi], mag[lo:hi], f"dx rows [{r0},{r1})")
+    (dx2,) = torch.autograd.grad(y, x, 2 * g, retain_graph=True)
+    assert torch.equal(dx2, 2 * dx)
+    del dx2
+    (dxc,) = torch.autograd.grad(y, x, torch.full_like(g, 3.0), retain_graph=True)
+    assert float(dxc[2:n - 2, 2:n - 2].abs().max()) == 0.0          # coefficients sum to zero
+    del dxc
+    lhs = float((y.detach().double() * g.double()).sum())
+    rhs = float((x.detach().double() * dx.double()).sum())
+    mag = float((y.detach().abs().double() * g.abs().double()).sum())
+    assert abs(lhs - rhs) <= 1e-6 * mag, (lhs, rhs, mag)
+    del x, y, g, dx
+    torch.cuda.empty_cache()
+
+
+def test_config3a_weight_gradient_full_size(kex):
+    """configs[2] weight gradient at (3, 8192, 8192): dW[t] = sum_j g[j] x[origin(j)+t] (27 numbers out of 2 x 10^8
+    products each).  (1) cotangent supported on three row bands -> the NumPy float64 oracle over those bands, at
+    1e-5 * sum |g x|; (2) dense cotangent -> the same correlation restated in float64 with torch slices on the device
+    (the oracle's formula, evaluated where the data is; cross-checked against the NumPy oracle by (1)); (3) exact
+    power-of-two linearity; (4) determinism (fixed-order reduction: two runs are bit-identical)."""
+    from vjp_ref import TOL, assert_within, dw_reference
+    n = 8192
+    gen = torch.Generator(device="cuda").manual_seed(11)
+    x = torch.randn((3, n, n), device="cuda", generator=gen)
+    w = torch.randn((3, 3, 3), device="cuda", generator=gen).requires_grad_()
+    conv = kex.kmap(kernel_size=(3, 3, 3), padding=("valid", "same", "same"))(lambda v, w: np.sum(v * w))
+    y = conv(x, w)
+    assert y.shape == (1, n, n)
+    taps = list(itertools.product(range(3), range(3), range(3)))
+    border = ((0, 0), (1, 1), (1, 1))
+
+    def dw_f64(g):
+        """float64 window correlation with zero padding, torch slices (restates oracle/kx_oracle.py weight_grad)."""
+        xp = torch.nn.functional.pad(x, (1, 1, 1, 1)).double()
+        g64, out, mag = g[0].double(), [], []
+        for (c, a, b) in taps:
+            sl = xp[c, a:a + n, b:b + n]
+            out.append(float((g64 * sl).sum()))
+            mag.append(float((g64.abs() * sl.abs()).sum()))
+        del xp
+        return np.asarray(out), np.asarray(mag)
+
+    # (1) banded cotangent against the NumPy oracle
+    bands = [(0, 48), (4000, 4064), (n - 48, n)]
+    g = torch.zeros((1, n, n), device="cuda")
+    for r0, r1 in bands:
+        g[0, r0:r1].normal_(generator=gen)
+    (dw,) = torch.autograd.grad(y, w, g, retain_graph=True)
+    assert _last_kernel() in ("conv_wgrad_finish", "conv_wgrad_rows_kernel", "conv_wgrad_kernel"), _last_kernel()
+    want = np.zeros(27)
+    mag = np.zeros(27)
+    for r0, r1 in bands:
+        lo, hi = max(r0 - 1, 0), min(r1 + 1, n)
+        bx = x[:, lo:hi].cpu().numpy()
+        bb = ((0, 0), (1 if r0 == 0 else 0, 1 if r1 == n else 0), (1, 1))
+        d, m = dw_reference(bx, g[:, r0:r1].cpu().numpy(), (3, 3, 3), (1, 1, 1), bb, taps)
+        want += d
+        mag += m
+    assert_within(dw.cpu().numpy().reshape(-1), want, mag, "dW (banded cotangent, NumPy oracle)")
+    t_want, t_mag = dw_f64(g)
+    np.testing.assert_allclose(t_want, want, rtol=0, atol=1e-9 * float(mag.max()))   # the torch restatement == the oracle
+    # (2) dense cotangent
+    g.normal_(generator=gen)
+    (dw,) = torch.autograd.grad(y, w, g, retain_graph=True)
+    want, mag = dw_f64(g)
+    assert_within(dw.cpu().numpy().reshape(-1), want, mag, "dW (dense cotangent)")
+    # (3) + (4)
+    (dw2,) = torch.autograd.grad(y, w, 2 * g, retain_graph=True)
+    assert torch.equal(dw2, 2 * dw)
+    (dw3,) = torch.autograd.grad(y, w, g, retain_graph=True)
+    assert torch.equal(dw3, dw)
+    assert TOL == 1e-5
+    del x, y, g
+    torch.cuda.empty_cache()
+
+
 def test_config3b_patches_full_size(kex):
     """3x3 patch extraction 'same' on 8192^2: every patch slot is a shifted copy of the input, bit exact."""
     n = 8192

@@ -145,6 +145,19 @@ def test_rowmarch_config4_prefix_strip_full_depth(kex):
                (1, nt, 1, W, (kappa, 1.0 - kappa, 0.0), 0.0)]
     want = kc.rowmarch(nt, W, regions)
     np.testing.assert_allclose(out[:, :W].cpu().numpy(), want, rtol=1e-5, atol=1e-5)
+    # ... and ON THE WAVE FRONT, where the recurrence is non-trivial for all 4096 rows: column q1-1 reads only
+    # ones (it stays exactly 1), so the strip [q1-1, q1-1+W) is the same mesh with a constant-1 left boundary,
+    # row 0 = 2 and the update below; row n of it is 1 + P(Binomial(n, 1/2) <= j), the smoothed front that
+    # sits near column q1 + n/2 (inside the strip down to the last row).
+    assert q1 - 1 + W <= q2
+    front = [(0, nt, 0, 1, (0, 0, 0), 1.0), (0, 1, 1, W, (0, 0, 0), 2.0), (1, nt, 1, W, (kappa, 1.0 - kappa, 0.0), 0.0)]
+    want_f = kc.rowmarch(nt, W, front)
+    got_f = out[:, q1 - 1:q1 - 1 + W].cpu().numpy()
+    for n in (1, 63, 64, 65, 1000, 2048, 4095):                 # the strip really varies at every depth
+        assert np.ptp(want_f[n]) > 0.9, n
+        mid = np.count_nonzero((want_f[n] > 1.01) & (want_f[n] < 1.99))
+        assert mid >= min(n, 15), (n, mid)
+    np.testing.assert_allclose(got_f, want_f, rtol=1e-5, atol=1e-5)
     # boundary / initial conditions hold exactly
     assert torch.all(out[:, 0] == 1) and torch.all(out[:, -1] == 1)
     assert torch.all(out[0, q1:q2] == 2) and torch.all(out[0, :q1] == 1) and torch.all(out[0, q2:] == 1)

@@ -130,3 +130,17 @@ def test_live_comparison_with_the_reference_modules():
         sys.path[:] = saved
         for m in [m for m in sys.modules if m == "jax" or m.startswith("jax.") or m == "kernex" or m.startswith("kernex.")]:
             del sys.modules[m]
+
+
+@pytest.mark.parametrize("dtype", [np.int8, np.int16, np.uint8, np.uint16, np.bool_])
+def test_narrow_integer_inputs_are_refused_not_widened(dtype):
+    """JAX keeps int8 / int16 / uint8 / bool arrays narrow (wraparound, `sum` promotion, logical bool arithmetic); the
+    engine computes in int32 / float32 only, so these inputs raise instead of silently returning int32 results.
+    The check runs before any device work, so it is testable without a GPU."""
+    import kernex_b200 as kex
+    from kernex_b200.errors import UnsupportedStencilError
+    x = np.arange(8).astype(dtype)
+    with pytest.raises(UnsupportedStencilError, match="narrow"):
+        kex.kmap(kernel_size=(3,))(lambda v: np.sum(v))(x)
+    with pytest.raises(UnsupportedStencilError, match="narrow"):
+        kex.kscan(kernel_size=(3,))(lambda v: np.sum(v))(x)
