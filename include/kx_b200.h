@@ -119,7 +119,7 @@ int kx_abi_version(void);
 const char* kx_last_error(void);
 /* number of kernels this library has launched since load (bench.py's gpu_launches) */
 uint64_t kx_launch_count(void);
-/* name of the kernel template the last launcher on this thread chose (diagnostics) */
+/* name of the kernel template the last launcher in this process chose (diagnostics) */
 const char* kx_last_kernel(void);
 
 /* ---- kmap -------------------------------------------------------------------
@@ -168,8 +168,9 @@ int kx_map_vjp_coef(const KxGeom* geom, const KxProgram* prog, const void* x, co
  * The launcher analyses the tap offsets: if no function reads the row
  * being written (all taps at axis-0 offset < centre, or never-written cells) the
  * rows are independent given the previous ones and a row-marching kernel
- * parallelises each row; otherwise a single-CTA sequential kernel preserves the
- * exact sweep order.  `reverse` = lax.scan(reverse=True).
+ * parallelises each row; otherwise the wavefront kernels run every hyperplane of
+ * mutually independent windows in parallel (warp-skewed for 2-D in-row dependencies),
+ * which reproduces the exact sweep order's values.  `reverse` = lax.scan(reverse=True).
  */
 int64_t kx_scan_state_bytes(const KxGeom* geom);
 int kx_scan(const KxGeom* geom, const KxProgram* prog, const void* in, const void* coef_dev,
@@ -195,6 +196,43 @@ int kx_scan_rowmarch_shard(const KxGeom* geom, const KxProgram* prog, int64_t co
 int kx_scan_rowmarch_rows_per_launch(void);
 int kx_scan_rowmarch_shard_rows(const KxGeom* geom, const KxProgram* prog, int64_t col_base, int64_t global_nx,
                                 int32_t row_begin, int32_t row_end, void* out, void* stream);
+
+/* ---- multi-GPU halo transport (axis-0 slab decomposition, one process per GPU) -----------------------------
+ * The reference has no multi-device data path to mirror: kernex/_src/utils.py:25-30 only offers jax.pmap with one
+ * WINDOW per device.  The slab decomposition of kernex_b200/dist.py keeps every rank's rows in a buffer allocated
+ * here (cudaMalloc), exports it with CUDA IPC and lets the neighbouring ranks map it, so the halo rows travel over
+ * NVLink by ONE one-sided kernel per step (kx_halo_pull) instead of a two-sided NCCL send/recv.
+ * A slab buffer starts with KX_PEER_FLAG_BYTES of zero-initialised 64-bit flags (monotonic epochs). */
+#define KX_PEER_HANDLE_BYTES 64
+#define KX_PEER_FLAG_BYTES 256
+int kx_peer_alloc(int64_t bytes, void** ptr);             /* zero-filled device buffer on the current device       */
+int kx_peer_free(void* ptr);
+int kx_peer_export(const void* ptr, void* handle64);      /* KX_PEER_HANDLE_BYTES opaque bytes for another PROCESS  */
+int kx_peer_open(const void* handle64, void** ptr);       /* map a neighbour's buffer (peer access enabled lazily)  */
+int kx_peer_close(void* ptr);
+
+typedef struct KxHaloSide {
+  void* dst;             /* my halo rows (local device memory)                                              */
+  const void* src;       /* the neighbour's edge rows (peer-mapped); bytes == 0: nothing to pull from it    */
+  int64_t bytes;         /* multiple of 16, both pointers 16-byte aligned                                   */
+  uint64_t* peer_ready;  /* neighbour's flag: set to `epoch` = "my own rows are final"                      */
+  const uint64_t* my_ready; /* my flag the neighbour sets the same way; waited for when bytes > 0           */
+  uint64_t* peer_done;   /* neighbour's flag: set to `epoch` = "I have read your rows, overwrite them"       */
+} KxHaloSide;
+
+typedef struct KxHaloPull {
+  int32_t n_sides;       /* 0..2 neighbours                                                                  */
+  int32_t reserved;
+  uint64_t epoch;        /* strictly increasing per step, the same sequence on every rank                    */
+  uint32_t* counter;     /* local scratch word, zero between launches                                        */
+  KxHaloSide side[2];
+} KxHaloPull;
+
+/* signal READY to the neighbours, wait for theirs, pull their edge rows, signal DONE -- one launch on `stream`.
+ * A neighbour that never signals traps the kernel after 20 s (the error surfaces at the next synchronisation). */
+int kx_halo_pull(const KxHaloPull* p, void* stream);
+/* enqueue a wait until *flag >= value (before own rows are overwritten: the neighbours' DONE flags) */
+int kx_flag_wait(const uint64_t* flag, uint64_t value, void* stream);
 
 #ifdef __cplusplus
 }

@@ -73,6 +73,20 @@ class KxProgram(C.Structure):
     ]
 
 
+KX_PEER_HANDLE_BYTES = 64
+KX_PEER_FLAG_BYTES = 256
+
+
+class KxHaloSide(C.Structure):
+    _fields_ = [("dst", C.c_void_p), ("src", C.c_void_p), ("bytes", C.c_int64), ("peer_ready", C.c_void_p),
+                ("my_ready", C.c_void_p), ("peer_done", C.c_void_p)]
+
+
+class KxHaloPull(C.Structure):
+    _fields_ = [("n_sides", C.c_int32), ("reserved", C.c_int32), ("epoch", C.c_uint64), ("counter", C.c_void_p),
+                ("side", KxHaloSide * 2)]
+
+
 _SIGNATURES = {
     "kx_abi_version": (C.c_int, []),
     "kx_last_error": (C.c_char_p, []),
@@ -95,6 +109,13 @@ _SIGNATURES = {
     "kx_scan_rowmarch_rows_per_launch": (C.c_int, []),
     "kx_scan_rowmarch_shard_rows": (C.c_int, [C.POINTER(KxGeom), C.POINTER(KxProgram), C.c_int64, C.c_int64,
                                               C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    "kx_peer_alloc": (C.c_int, [C.c_int64, C.POINTER(C.c_void_p)]),
+    "kx_peer_free": (C.c_int, [C.c_void_p]),
+    "kx_peer_export": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "kx_peer_open": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "kx_peer_close": (C.c_int, [C.c_void_p]),
+    "kx_halo_pull": (C.c_int, [C.POINTER(KxHaloPull), C.c_void_p]),
+    "kx_flag_wait": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p]),
 }
 
 _lock = threading.Lock()

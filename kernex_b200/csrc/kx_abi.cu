@@ -130,7 +130,7 @@ extern "C" {
 int kx_abi_version(void) { return KX_ABI_VERSION; }
 const char* kx_last_error(void) { return err_buf(); }
 uint64_t kx_launch_count(void) { return launch_counter().load(); }
-const char* kx_last_kernel(void) { return last_kernel_name(); }
+const char* kx_last_kernel(void) { return last_kernel_name().load(std::memory_order_relaxed); }
 
 int kx_map(const KxGeom* geom, const KxProgram* prog, const void* in, const void* coef_dev, int64_t coef_batch_stride,
            void* out, int64_t batch, void* stream) {

@@ -19,8 +19,10 @@ inline char* err_buf() {
   static thread_local char buf[512] = {0};
   return buf;
 }
-inline const char*& last_kernel_name() {
-  static thread_local const char* name = "";
+// process-wide (not thread-local): autograd runs backward passes on its own thread, and the tests / bench ask
+// "which kernel ran last" from the main thread
+inline std::atomic<const char*>& last_kernel_name() {
+  static std::atomic<const char*> name{""};
   return name;
 }
 inline std::atomic<uint64_t>& launch_counter() {
@@ -45,7 +47,7 @@ inline int fail(int status, const char* fmt, ...) {
   } while (0)
 
 inline int after_launch(const char* name) {
-  last_kernel_name() = name;
+  last_kernel_name().store(name, std::memory_order_relaxed);
   launch_counter().fetch_add(1, std::memory_order_relaxed);
   cudaError_t e = cudaPeekAtLastError();
   if (e != cudaSuccess) {

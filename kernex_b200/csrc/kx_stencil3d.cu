@@ -282,7 +282,7 @@ int try_stencil3d(const MapArgs& m, const KxProgram& p, cudaStream_t s) {
     if (rc != KX_ERR_UNSUPPORTED) return rc;
   }
   if (batch <= 65535) {
-    // opt-in (KX_DENSE3D_PLANES=1): plane-stationary dense 3x3x3 kernel (kx_stencil3d_dense.cu), not yet the default
+    // dense 3x3x3 windows with host weights: plane-stationary kernel (kx_stencil3d_dense.cu)
     const int rc = try_stencil3d_dense(m, p, batch, s);
     if (rc != KX_ERR_UNSUPPORTED) return rc;
   }

@@ -84,13 +84,12 @@ __device__ __forceinline__ void store4(T* o, const T (&acc)[4], int n_valid) {
   }
 }
 
-// PAIR (opt-in, KX_STAR_PAIR=1): a 4-stage ring and ONE block barrier per TWO planes -- the r1b ncu capture has 30 % of
-// the stall samples on the per-plane barrier.  Written at the end of round 1 without GPU time left: NOT yet run on
-// hardware, off by default.
-template <typename T, int SHIFT, bool FULL, bool PAIR>
+// (A variant with a 4-stage ring and one block barrier per TWO planes was measured in round 2: 617 vs 720 GLUP/s at
+// 2048^3 -- the extra stage costs a resident block per SM -- and removed.)
+template <typename T, int SHIFT, bool FULL>
 __global__ void __launch_bounds__(kThreads3)
 stencil3d_star_kernel(const __grid_constant__ StarArgs<T> a) {
-  constexpr int STG = PAIR ? 4 : kStages;
+  constexpr int STG = kStages;
   constexpr int NV = (SHIFT + 6 + 3) / 4;          // aligned 4-vectors covering the 6 needed columns
   constexpr int SW = kTX + 4 * NV;                  // tile width (columns), multiple of 4
   constexpr int SR = kTY + 2;
@@ -210,56 +209,12 @@ stencil3d_star_kernel(const __grid_constant__ StarArgs<T> a) {
     }
   };
 
-  if constexpr (!PAIR) {
-    int pl = 0;
-    for (; pl + 1 < nplanes; pl += 2) {   // unrolled by two: the plane buffers swap roles by name
-      step(pl, bufB, bufA);
-      step(pl + 1, bufA, bufB);
-    }
-    if (pl < nplanes) step(pl, bufB, bufA);
-  } else {
-    // the math of one ring step without its synchronisation
-    auto math = [&](int pl, T (&mid)[kRY + 2][6], T (&up)[kRY + 2][6]) {
-      read_plane(pl, up);
-      if (pl >= 2) {
-#pragma unroll
-        for (int r = 0; r < kRY; ++r) {
-          T acc[4];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            T v = a.bias;
-            if (FULL || (a.mask & 1u)) v = mad_wrap(a.c[0], below[r][i], v);
-            if (FULL || (a.mask & 2u)) v = mad_wrap(a.c[1], mid[r][i + 1], v);
-            if (FULL || (a.mask & 4u)) v = mad_wrap(a.c[2], mid[r + 1][i], v);
-            if (FULL || (a.mask & 8u)) v = mad_wrap(a.c[3], mid[r + 1][i + 1], v);
-            if (FULL || (a.mask & 16u)) v = mad_wrap(a.c[4], mid[r + 1][i + 2], v);
-            if (FULL || (a.mask & 32u)) v = mad_wrap(a.c[5], mid[r + 2][i + 1], v);
-            if (FULL || (a.mask & 64u)) v = mad_wrap(a.c[6], up[r + 1][i + 1], v);
-            acc[i] = v;
-          }
-          if (col_ok && (y0 + iy + r < a.hout)) store4(orow + (int64_t)r * a.wout, acc, n_valid);
-        }
-        orow += out_plane;
-      }
-#pragma unroll
-      for (int r = 0; r < kRY; ++r) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) below[r][i] = mid[r + 1][i + 1];
-      }
-    };
-    // prologue above issued planes 0 and 1 (kStages - 1 = 2 groups).  Per pair: both planes of the pair have
-    // landed (wait_group 0), one barrier, the next pair goes into the two stages read by the previous pair, math.
-    for (int pl = 0; pl < nplanes; pl += 2) {
-      cp_wait<0>();
-      __syncthreads();
-      if (pl + 2 < nplanes) issue(pl + 2);
-      cp_commit();
-      if (pl + 3 < nplanes) issue(pl + 3);
-      cp_commit();
-      math(pl, bufB, bufA);
-      if (pl + 1 < nplanes) math(pl + 1, bufA, bufB);
-    }
+  int pl = 0;
+  for (; pl + 1 < nplanes; pl += 2) {   // unrolled by two: the plane buffers swap roles by name
+    step(pl, bufB, bufA);
+    step(pl + 1, bufA, bufB);
   }
+  if (pl < nplanes) step(pl, bufB, bufA);
 }
 
 template <typename T>
@@ -302,11 +257,9 @@ int run_star(const MapArgs& m, const KxProgram& p, int64_t batch, cudaStream_t s
   dim3 grid(tiles_x, tiles_y, (unsigned)(a.nzc * batch)), block(32, kTYB);
   const int shift = (((-a.lx) % 4) + 4) % 4;
   const bool full = a.mask == 0x7fu;
-  const bool pair = getenv("KX_STAR_PAIR") != nullptr;   // opt-in variant, see the kernel
-#define KX_STAR(S)                                                                        \
-  if (full && pair) stencil3d_star_kernel<T, S, true, true><<<grid, block, 0, s>>>(a);    \
-  else if (full) stencil3d_star_kernel<T, S, true, false><<<grid, block, 0, s>>>(a);      \
-  else stencil3d_star_kernel<T, S, false, false><<<grid, block, 0, s>>>(a);
+#define KX_STAR(S)                                                                 \
+  if (full) stencil3d_star_kernel<T, S, true><<<grid, block, 0, s>>>(a);           \
+  else stencil3d_star_kernel<T, S, false><<<grid, block, 0, s>>>(a);
   switch (shift) {
     case 0: KX_STAR(0) break;
     case 1: KX_STAR(1) break;

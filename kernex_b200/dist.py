@@ -153,35 +153,45 @@ def exchange_halo_grads(dext: torch.Tensor, layout: SlabLayout, group=None):
 
 
 class SlabStencil:
-    """A kmap applied to a row-slab-decomposed global array on CUDA."""
+    """A kmap applied to a row-slab-decomposed global array on CUDA.
+
+    ``transport``:
+
+    * ``"p2p"`` (default on several GPUs): the slab lives in a CUDA-IPC exported buffer (``peer.py``) that the two
+      neighbouring ranks have mapped; one ``kx_halo_pull`` launch per step signals "my rows are final" to the
+      neighbours, waits for theirs, pulls their edge rows over NVLink and signals "read" back -- no NCCL kernel, no
+      rendezvous of host threads, nothing between the previous step and the strip launches but that one kernel.
+    * ``"nccl"``: ``batch_isend_irecv`` of the halo rows (the round-1 transport; also what the CPU/gloo tests run).
+
+    ``KX_DIST_TRANSPORT`` overrides the default.  If the peer mapping cannot be set up (no IPC / no peer access) the
+    constructor falls back to NCCL on EVERY rank (the decision is all-reduced) and records why in ``transport_note``.
+    """
 
     def __init__(self, func, kernel_size, relative, rows_per_rank, width=None, device=None, padding="valid",
-                 trailing_shape=None, group=None, args=(), transport=None):
+                 trailing_shape=None, group=None, args=(), transport=None, rank=None, world=None, peers=None):
         import os
 
         from .engine import PreparedMap
         from .resolve import resolve_padding
 
-        # "nccl" (default): isend / irecv of the halo rows.  "p2p" (opt-in, KX_DIST_TRANSPORT=p2p; written at the end
-        # of round 1 without GPU time left, not yet run on hardware): the slab lives in torch symmetric memory and every
-        # rank PULLS its halo rows out of the neighbours' buffers over NVLink peer mappings, fenced by two device-side
-        # barriers -- no NCCL kernel, no rendezvous between the ranks' host threads.
-        self.transport = transport or os.environ.get("KX_DIST_TRANSPORT", "nccl")
+        self.group = group
+        self.world = world if world is not None else (dist.get_world_size(group) if dist.is_initialized() else 1)
+        self.rank = rank if rank is not None else (dist.get_rank(group) if dist.is_initialized() else 0)
+        self.device = device or torch.device("cuda", torch.cuda.current_device())
+        self.transport = transport or os.environ.get("KX_DIST_TRANSPORT") or ("p2p" if self.world > 1 else "nccl")
         if self.transport not in ("nccl", "p2p"):
             raise ValueError(f"transport must be 'nccl' or 'p2p', got {self.transport!r}")
-        self.group = group
-        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
-        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
-        self.device = device or torch.device("cuda", torch.cuda.current_device())
+        self.transport_note = ""
         kernel_size = tuple(kernel_size)
         trailing = tuple(trailing_shape) if trailing_shape is not None else (int(width),)
         border = resolve_padding(padding, kernel_size)
         self.layout = SlabLayout(self.rank, self.world, rows_per_rank, kernel_size[0], border[0])
         L = self.layout
-        self._hdl = None
+        self._peers, self._pull, self._epoch = None, None, 0
         if self.transport == "p2p" and self.world > 1:
-            self._init_peer_memory(kernel_size[0], rows_per_rank, trailing)
-        else:
+            self._init_peer_memory(kernel_size[0], rows_per_rank, trailing, peers)
+        if self._peers is None:
+            self.transport = "nccl" if self.world > 1 else self.transport
             self.ext = torch.zeros((L.ext_rows,) + trailing, dtype=torch.float32, device=self.device)
         strides = (1,) * len(kernel_size)
         self.maps = []
@@ -194,37 +204,89 @@ class SlabStencil:
             out_trailing = tuple(pm.out_shape[1:])
         self.out = torch.empty((L.out_rows,) + out_trailing, dtype=torch.float32, device=self.device)
         self.local_windows = int(self.out.numel())
-        self.side = torch.cuda.Stream(device=self.device)
+        # high priority: the O(halo) work must not queue behind the blocks of the interior launch
+        self.side = torch.cuda.Stream(device=self.device, priority=-1)
 
-    def _init_peer_memory(self, k0, rows, trailing):
-        """Allocate the slab in symmetric memory (same size on every rank) and map the neighbours' buffers."""
-        import torch.distributed._symmetric_memory as symm
+    # ---- peer-memory transport ------------------------------------------------------------------------------
+    def _init_peer_memory(self, k0, rows, trailing, peers):
+        """Allocate the slab in a peer-mapped buffer (same size on every rank) and prepare the pull descriptor."""
+        import ctypes as C
+
+        from . import _lib, peer
 
         L = self.layout
+        row_bytes = 4
+        for t in trailing:
+            row_bytes *= int(t)
         rows_max = rows + (k0 - 1) // 2 + k0 // 2          # the interior ranks' ext_rows: identical everywhere
-        shape = (rows_max,) + trailing
-        self._sym = symm.empty(*shape, dtype=torch.float32, device=self.device)
-        self._sym.zero_()
-        self._hdl = symm.rendezvous(self._sym, self.group if self.group is not None else dist.group.WORLD)
-        self.ext = self._sym[:L.ext_rows]
-        self._pulls = []                                     # (my ext rows, neighbour's view of the rows I need)
-        for mine, peer_rank, theirs in halo_pull_plan(self.rank, self.world, rows, k0, (L.lo, L.hi)):
-            peer = self._hdl.get_buffer(peer_rank, shape, torch.float32)
-            self._pulls.append((mine, peer[theirs]))
+        nbytes = _lib.KX_PEER_FLAG_BYTES + rows_max * row_bytes
+        why = "" if row_bytes % 16 == 0 else f"rows of {row_bytes} bytes are not 16-byte multiples"
+        grp = peers
+        if grp is None and not why:
+            try:
+                grp = peer.PeerGroup.create(nbytes, self.device, self.group)
+            except Exception as e:   # no CUDA IPC / peer access on this box
+                why = f"peer mapping failed: {e}"
+        if peers is None and dist.is_initialized():
+            ok = torch.tensor([0 if why else 1], device=self.device)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
+            if not bool(ok.item()):
+                if grp is not None:
+                    grp.close()
+                self.transport_note = why or "peer mapping failed on another rank"
+                return
+        elif why:
+            raise ValueError(f"p2p transport: {why}")
+        self._peers = grp
+        F = _lib.KX_PEER_FLAG_BYTES
+        self.ext = grp.tensor(F, (L.ext_rows,) + tuple(trailing))
+        pull = _lib.KxHaloPull()
+        pull.n_sides, pull.epoch = 0, 0
+        pull.counter = grp.local_ptr + peer.COUNTER_BYTE
+        plan = {pr: (mine, theirs) for mine, pr, theirs in halo_pull_plan(self.rank, self.world, rows, k0, (L.lo, L.hi))}
+        for nb, my_ready, their_ready, their_done in ((self.rank - 1, peer.READY_FROM_UP, peer.READY_FROM_DOWN, peer.DONE_FROM_DOWN),
+                                                      (self.rank + 1, peer.READY_FROM_DOWN, peer.READY_FROM_UP, peer.DONE_FROM_UP)):
+            if not (0 <= nb < self.world):
+                continue
+            sd = pull.side[pull.n_sides]
+            mine, theirs = plan.get(nb, (slice(0, 0), slice(0, 0)))
+            sd.bytes = (mine.stop - mine.start) * row_bytes
+            sd.dst = grp.local_ptr + F + mine.start * row_bytes
+            sd.src = grp.peer_ptrs[nb] + F + theirs.start * row_bytes
+            sd.peer_ready = grp.flag_ptr(nb, their_ready)     # the neighbour waits on ITS flag "ready from me"
+            sd.my_ready = grp.flag_ptr(self.rank, my_ready)
+            sd.peer_done = grp.flag_ptr(nb, their_done)
+            pull.n_sides += 1
+        self._pull, self._C, self._klib = pull, C, _lib
+        self._done_flags = [grp.flag_ptr(self.rank, s) for nb, s in ((self.rank - 1, peer.DONE_FROM_UP),
+                                                                     (self.rank + 1, peer.DONE_FROM_DOWN))
+                            if 0 <= nb < self.world]
 
-    def _pull_halos(self):
-        """One-sided halo exchange on the current stream: barrier (every rank's own rows are final), peer reads over
-        NVLink, barrier (every rank has read, own rows may change again)."""
-        self._hdl.barrier(channel=0)
-        for mine, theirs in self._pulls:
-            if theirs.numel():
-                self.ext[mine].copy_(theirs)
-        self._hdl.barrier(channel=1)
+    def _pull_halos(self, stream):
+        """One launch on ``stream``: READY -> wait -> pull over NVLink -> DONE (kx_peer.cu)."""
+        self._epoch += 1
+        self._pull.epoch = self._epoch
+        self._klib.check(self._klib.load().kx_halo_pull(self._C.byref(self._pull), self._C.c_void_p(stream.cuda_stream)))
+
+    def _wait_neighbours_done(self):
+        """Before my own rows change: the neighbours must have pulled the rows of the last step (their DONE flags)."""
+        if self._peers is not None and self._epoch:
+            s = self._C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+            lib = self._klib.load()
+            for f in self._done_flags:
+                self._klib.check(lib.kx_flag_wait(self._C.c_void_p(f), self._C.c_uint64(self._epoch), s))
+
+    def close(self):
+        if self._peers is not None:
+            self._peers.close()
+            self._peers = None
 
     def fill_random(self, generator=None):
+        self._wait_neighbours_done()
         self.ext[self.layout.own].normal_(generator=generator)
 
     def set_local(self, rows: torch.Tensor):
+        self._wait_neighbours_done()
         self.ext[self.layout.own].copy_(rows)
 
     def step(self):
@@ -232,15 +294,15 @@ class SlabStencil:
         reqs = []
         if self.world > 1:
             self.side.wait_stream(main)  # own rows written by earlier work on `main` must be visible
-            with torch.cuda.stream(self.side):
-                if self._hdl is not None:
-                    self._pull_halos()
-                else:
+            if self._peers is not None:
+                self._pull_halos(self.side)
+            else:
+                with torch.cuda.stream(self.side):
                     reqs = exchange_halos(self.ext, self.layout, self.group)
         for p, pm in self.maps:          # interior first: overlaps the exchange
             if not p.needs_halo:
                 pm(self.ext[p.in0:p.in1], out=self.out[p.out0:p.out1])
-        # the O(halo)-row strips run on the side stream right behind the receives, i.e.
+        # the O(halo)-row strips run on the side stream right behind the halo rows, i.e.
         # concurrently with the tail of the interior launch; `main` joins at the end
         with torch.cuda.stream(self.side):
             for r in reqs:
@@ -251,7 +313,6 @@ class SlabStencil:
         if self.world > 1:
             main.wait_stream(self.side)
         return self.out
-
 
     def vjp(self, g_local: torch.Tensor, want_input=True, want_coef=False):
         """Adjoint of :meth:`step`: ``g_local`` is the cotangent of this rank's output rows.

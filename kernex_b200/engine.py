@@ -614,11 +614,13 @@ def _fold_leading_axes(func_map, shape, kernel_size, strides, border, relative):
 
 
 def _fold_1d(func_map, shape, kernel_size, strides, border, relative):
-    """Opt-in (``KX_FOLD_1D=1``): large 1-D arrays run as 2-D row problems plus a seam fix-up (``fold1d.py``)."""
+    """Large 1-D arrays run as 2-D row problems plus a seam fix-up (``fold1d.py``): measured on B200 at 2^27 elements,
+    15-tap FIR 0.53 -> 0.72 of the HBM roofline, moving average 0.64 -> 0.85, running max 0.65 -> 0.84
+    (profiles/README.md, r2).  ``KX_NO_FOLD_1D=1`` keeps the one-row launch (cross-check)."""
     import os
 
     from .fold1d import plan_fold
-    if not os.environ.get("KX_FOLD_1D") or len(shape) != 1 or len(func_map) != 1 or any(v != () for v in func_map.values()):
+    if os.environ.get("KX_NO_FOLD_1D") or len(shape) != 1 or len(func_map) != 1 or any(v != () for v in func_map.values()):
         return None
     (n,), (k,), (st,), ((lo, hi),) = shape, kernel_size, strides, border
     w = plan_fold(int(n), int(k), int(lo), int(hi), int(st))
@@ -629,25 +631,30 @@ def _fold_1d(func_map, shape, kernel_size, strides, border, relative):
     def lifted(win, *a, _f=f, **kw):        # the (1, k) window of the folded array is the user's 1-D window
         return _f(win.reshape((k,)), *a, **kw)
 
-    main = kernel_map({lifted: ()}, (n // w, w), (1, k), (1, 1), ((0, 0), (lo, k - 1 - lo)), relative)
+    main_geom = ({lifted: ()}, (n // w, w), (1, k), (1, 1), ((0, 0), (lo, k - 1 - lo)), relative)
+    main = kernel_map(*main_geom)
     seam = kernel_map({lifted: ()}, (n // w - 1, 2 * (k - 1)), (1, k), (1, 1), ((0, 0), (0, 0)), relative) if k > 1 else None
-    return _Fold1dCall(main, seam, int(n), int(k), int(lo), int(hi), w)
+    return _Fold1dCall(main, seam, int(n), int(k), int(lo), int(hi), w, main_geom)
 
 
 class _Fold1dCall:
-    def __init__(self, main, seam, n, k, lo, hi, w):
+    def __init__(self, main, seam, n, k, lo, hi, w, main_geom):
         self.main, self.seam, self.n, self.k, self.lo, self.hi, self.w = main, seam, n, k, lo, hi, w
+        self.main_geom = main_geom
 
     def applies(self, array, a, kw):
-        """Device-resident contiguous tensors outside autograd (the seam write-back is an in-place strided copy)."""
+        """Device-resident contiguous tensors outside autograd (the seam write-back is an in-place strided copy) and
+        SCALAR window functions only: the fold flattens the (H, W) main result and overwrites (H-1, k-1) seam cells,
+        which has no meaning for a vector-valued (GATHER / patch) function."""
         if not isinstance(array, torch.Tensor) or not array.is_cuda or not array.is_contiguous():
             return False
-        if tuple(array.shape) != (self.n,):
+        if tuple(array.shape) != (self.n,) or array.dtype not in _TORCH2KX:
             return False
         if torch.is_grad_enabled() and (array.requires_grad or any(
                 isinstance(v, torch.Tensor) and v.requires_grad for v in list(a) + list(kw.values()))):
             return False
-        return True
+        specs = _map_plan(*self.main_geom, _TORCH2KX[array.dtype], a, kw)[0]
+        return all(s.kind != "gather" for s in specs)
 
     def __call__(self, array, *a, **kw):
         from .fold1d import folded_map_1d

@@ -1,5 +1,6 @@
-"""Large 1-D arrays as 2-D row problems (opt-in: ``KX_FOLD_1D=1``; written at the end of round 1, the fold itself is
-CPU-tested against the oracle, the CUDA integration has not run on hardware yet).
+"""Large 1-D arrays as 2-D row problems (default for scalar window functions on device tensors of >= 2^22 elements;
+``KX_NO_FOLD_1D=1`` disables it).  The fold is CPU-tested against the oracle (tests/test_fold1d_cpu.py) and bit-identical
+to the one-row launch on the GPU (tests/test_gpu_fastpaths.py::test_folded_1d_map_equals_the_one_row_launch).
 
 A 1-D array is a one-row problem for the row-marching kernel: every thread loads, computes four outputs, stores and
 retires, so nothing overlaps the load latency (15-tap FIR: 0.51 of the HBM roofline, ``profiles/README.md``).  Folding
@@ -36,7 +37,9 @@ def folded_map_1d(x, k: int, lo: int, hi: int, w: int, run_main, run_seam):
     n = x.numel()
     h = n // w
     assert h * w == n and x.dim() == 1 and x.is_contiguous()
-    out = run_main(x.view(h, w)).reshape(-1)
+    main = run_main(x.view(h, w))
+    assert main.dim() == 2, "the 1-D fold needs a scalar window function"
+    out = main.reshape(-1)
     if h > 1 and k > 1:
         seams = x.as_strided((h - 1, 2 * (k - 1)), (w, 1), x.storage_offset() + w - (k - 1)).contiguous()
         fixed = run_seam(seams)

@@ -37,23 +37,28 @@ def main():
     ]:
         g = torch.Generator(device=dev).manual_seed(100 + rank)
         slab = SlabStencil(fn, kernel_size=ksize, relative=True, rows_per_rank=rows, trailing_shape=trailing,
-                           device=dev, padding=padding)
+                           device=dev, padding=padding, transport="nccl")
         slab.fill_random(g)
         for _ in range(2):  # a second step must give the same answer (halos re-exchanged)
             out = slab.step()
         torch.cuda.synchronize()
-        if os.environ.get("KX_TEST_EXPERIMENTAL"):   # opt-in: halo rows pulled from peer memory instead of NCCL send/recv
-            p2p = SlabStencil(fn, kernel_size=ksize, relative=True, rows_per_rank=rows, trailing_shape=trailing,
-                              device=dev, padding=padding, transport="p2p")
-            p2p.set_local(slab.ext[slab.layout.own])
-            for _ in range(2):
-                out2 = p2p.step()
-            torch.cuda.synchronize()
-            same2 = torch.tensor([1 if torch.equal(out2, out) else 0], device=dev)
-            dist.all_reduce(same2, op=dist.ReduceOp.MIN)
-            ok = ok and bool(same2.item())
-            if rank == 0:
-                print(f"  p2p transport: {'bit-identical' if same2.item() else 'MISMATCH'}", flush=True)
+        # the default transport on several GPUs: halo rows pulled out of the neighbours' peer-mapped slabs by one kernel
+        p2p = SlabStencil(fn, kernel_size=ksize, relative=True, rows_per_rank=rows, trailing_shape=trailing,
+                          device=dev, padding=padding)
+        row_bytes = 4 * int(torch.tensor(trailing).prod())
+        expect = "p2p" if row_bytes % 16 == 0 else "nccl"
+        assert p2p.transport == expect, (p2p.transport, p2p.transport_note)
+        p2p.set_local(slab.ext[slab.layout.own])
+        for it in range(3):
+            out2 = p2p.step()
+            if it == 1:   # new rows between steps: the neighbours' DONE flags gate the overwrite, the next pull sees them
+                p2p.set_local(slab.ext[slab.layout.own])
+        torch.cuda.synchronize()
+        same2 = torch.tensor([1 if torch.equal(out2, out) else 0], device=dev)
+        dist.all_reduce(same2, op=dist.ReduceOp.MIN)
+        ok = ok and bool(same2.item())
+        if rank == 0:
+            print(f"  {p2p.transport} transport vs nccl: {'bit-identical' if same2.item() else 'MISMATCH'}", flush=True)
         own = slab.ext[slab.layout.own].contiguous()
         parts = [torch.empty_like(own) for _ in range(world)]
         dist.all_gather(parts, own)

@@ -81,3 +81,46 @@ def test_tensor_on_a_non_current_device(kex):
     assert torch.equal(y1.cpu(), y0.cpu())
     s1 = kex.kscan(kernel_size=(3, 3), padding="same", relative=True)(lambda u: 0.25 * (u[0, -1] + u[-1, 0] + u[0, 1] + u[1, 0]))
     assert torch.equal(s1(x1).cpu(), s1(torch.from_numpy(xh).to("cuda:0")).cpu())
+
+
+def lap3(x):
+    return (x[1, 0, 0] + x[-1, 0, 0] + x[0, 1, 0] + x[0, -1, 0] + x[0, 0, 1] + x[0, 0, -1] - 6 * x[0, 0, 0])
+
+
+@pytest.mark.parametrize("world,fn,ksize,rows,trailing,padding", [
+    (2, lap, (3, 3), 64, (256,), "valid"), (3, lap, (3, 3), 50, (132,), "same"), (4, lap3, (3, 3, 3), 12, (20, 36), "same"),
+    (3, lap3, (3, 3, 3), 16, (24, 64), "valid"), (2, lambda v: v[0, 0] + 2 * v[1, 1], (2, 2), 40, (64,), ((0, 1), (0, 1)))])
+def test_peer_halo_pull_with_emulated_ranks_on_one_gpu(kex, world, fn, ksize, rows, trailing, padding):
+    """The multi-GPU transport on a 1-GPU box: `world` emulated ranks in this process, every rank with its own streams
+    and its own peer buffer (`PeerGroup.local`: the "peer" pointers are local).  Exercises halo_pull_kernel, the
+    READY / DONE flag protocol over three steps with new rows in between, and the strip launches; the stitched output
+    must equal the single-launch kmap of the whole array bit for bit."""
+    from kernex_b200 import _lib, peer
+    from kernex_b200.dist import SlabStencil
+    dev = torch.device("cuda", 0)
+    row_bytes = 4 * int(np.prod(trailing))
+    rows_max = rows + (ksize[0] - 1) // 2 + ksize[0] // 2
+    groups = peer.PeerGroup.local(world, _lib.KX_PEER_FLAG_BYTES + rows_max * row_bytes, dev)
+    mains = [torch.cuda.Stream(device=dev) for _ in range(world)]
+    slabs = [SlabStencil(fn, kernel_size=ksize, relative=True, rows_per_rank=rows, trailing_shape=trailing, device=dev,
+                         padding=padding, transport="p2p", rank=r, world=world, peers=groups[r]) for r in range(world)]
+    assert all(s.transport == "p2p" for s in slabs)
+    gen = torch.Generator(device=dev).manual_seed(5)
+    f1 = kex.kmap(kernel_size=ksize, padding=padding, relative=True)(fn)
+    for trial in range(3):
+        glob = torch.randn((world * rows,) + tuple(trailing), device=dev, generator=gen)
+        torch.cuda.synchronize()
+        for r, s in enumerate(slabs):
+            with torch.cuda.stream(mains[r]):
+                s.set_local(glob[r * rows:(r + 1) * rows])   # waits for the neighbours' DONE flags of the last step
+        outs = []
+        for r, s in enumerate(slabs):                        # launches only: rank r's pull spins until r+1's has started
+            with torch.cuda.stream(mains[r]):
+                outs.append(s.step())
+        torch.cuda.synchronize()
+        assert _lib.last_kernel() in ("stencil2d_kernel", "stencil3d_star_kernel", "stencil3d_kernel", "halo_pull_kernel")
+        want = f1(glob)
+        got = torch.cat(outs, dim=0)
+        assert got.shape == want.shape and torch.equal(got, want), trial
+    for g in groups:
+        g.close()

@@ -320,9 +320,11 @@ _DENSE3D = [((9, 37, 132), "same"), ((3, 20, 64), "same"), ((5, 18, 260), "valid
 
 @pytest.mark.parametrize("case", range(len(_DENSE3D)))
 @pytest.mark.parametrize("dtype", ["f32", "i32"])
-def test_dense3d_runs_on_the_conv_row_ring(kex, case, dtype):
-    """Dense 27-point windows over a volume: the conv row-ring kernel with the three z planes as channels;
-    output planes at a padded z face use the 1- and 2-plane instantiations (kx_conv2d.cu run_dense3d)."""
+def test_dense3d_runs_on_the_conv_row_ring(kex, case, dtype, monkeypatch):
+    """Dense 27-point windows over a volume on the conv row-ring kernel with the three z planes as channels (the path
+    of device-resident weights; host weights reach it with KX_NO_DENSE3D_PLANES=1); output planes at a padded z face
+    use the 1- and 2-plane instantiations (kx_conv2d.cu run_dense3d)."""
+    monkeypatch.setenv("KX_NO_DENSE3D_PLANES", "1")
     shape, pad = _DENSE3D[case]
     rng = np.random.default_rng(7000 + case)
     ks = (3, 3, 3)
@@ -493,29 +495,10 @@ def test_conv_rows_batched_and_host_weights(kex):
         _check_affine(got[b].cpu().numpy(), x[b], (C, 3, 3), (1, 1, 1), border[1:], taps, [float(w[t]) for t in taps])
 
 
-@pytest.mark.skipif(not __import__("os").environ.get("KX_TEST_EXPERIMENTAL"),
-                    reason="opt-in kernel variants written without GPU time left (set KX_TEST_EXPERIMENTAL=1)")
-def test_star_kernel_pair_variant_is_bit_identical(kex, monkeypatch):
-    """KX_STAR_PAIR=1: one block barrier per two planes (kx_stencil3d_star.cu).  Must equal the default kernel bit for bit."""
-    rng = np.random.default_rng(31)
-    lap = kex.kmap(kernel_size=(3, 3, 3), padding="same", relative=True)(
-        lambda v: v[1, 0, 0] + v[-1, 0, 0] + v[0, 1, 0] + v[0, -1, 0] + v[0, 0, 1] + v[0, 0, -1] - 6 * v[0, 0, 0])
-    for shape in [(70, 40, 260), (33, 17, 132), (5, 64, 128), (2, 20, 64)]:
-        x = torch.from_numpy(rng.standard_normal(shape).astype(np.float32)).cuda()
-        want = lap(x).clone()
-        assert _last_kernel() == "stencil3d_star_kernel"
-        monkeypatch.setenv("KX_STAR_PAIR", "1")
-        got = lap(x)
-        monkeypatch.delenv("KX_STAR_PAIR")
-        assert torch.equal(got, want)
-
-
-@pytest.mark.skipif(not __import__("os").environ.get("KX_TEST_EXPERIMENTAL"),
-                    reason="opt-in kernel variants written without GPU time left (set KX_TEST_EXPERIMENTAL=1)")
 @pytest.mark.parametrize("case", range(len(_DENSE3D)))
 @pytest.mark.parametrize("dtype", ["f32", "i32"])
-def test_plane_stationary_dense3d_kernel(kex, case, dtype, monkeypatch):
-    """KX_DENSE3D_PLANES=1: stencil3d_dense_kernel (kx_stencil3d_dense.cu) against the oracle on the dense-3-D cases."""
+def test_plane_stationary_dense3d_kernel(kex, case, dtype):
+    """Dense 27-point windows with host weights: stencil3d_dense_kernel (kx_stencil3d_dense.cu) against the oracle."""
     shape, pad = _DENSE3D[case]
     rng = np.random.default_rng(7100 + case)
     ks = (3, 3, 3)
@@ -534,25 +517,51 @@ def test_plane_stationary_dense3d_kernel(kex, case, dtype, monkeypatch):
             acc = acc + cf * v[t]
         return acc
 
-    monkeypatch.setenv("KX_DENSE3D_PLANES", "1")
     got = kex.kernel_map({fn: ()}, shape, ks, (1, 1, 1), border, False)(x)
     assert _last_kernel() == "stencil3d_dense_kernel"
     _check_affine(got, x, ks, (1, 1, 1), border, taps, coefs, bias)
 
 
-@pytest.mark.skipif(not __import__("os").environ.get("KX_TEST_EXPERIMENTAL"),
-                    reason="opt-in paths written without GPU time left (set KX_TEST_EXPERIMENTAL=1)")
 @pytest.mark.parametrize("k,pad", [(3, "same"), (3, "valid"), (15, "same"), (6, ((2, 1),)), (9, "valid")])
 def test_folded_1d_map_equals_the_one_row_launch(kex, k, pad, monkeypatch):
-    """KX_FOLD_1D=1 (kernex_b200/fold1d.py): a large 1-D array as rows + seam fix-up must equal the plain launch bit for bit."""
+    """kernex_b200/fold1d.py: a large 1-D array as rows + seam fix-up must equal the plain one-row launch bit for bit
+    (KX_NO_FOLD_1D=1), for weighted sums, integer max and int -> float promotion."""
     rng = np.random.default_rng(9900 + k)
     x = torch.from_numpy(rng.standard_normal(1 << 22).astype(np.float32)).cuda()
-    w = rng.standard_normal(k).astype(np.float32)
-    want = kex.kmap(kernel_size=(k,), padding=pad)(lambda v: np.sum(v * w))(x)
-    monkeypatch.setenv("KX_FOLD_1D", "1")
-    got = kex.kmap(kernel_size=(k,), padding=pad)(lambda v: np.sum(v * w))(x)
-    assert got.shape == want.shape and torch.equal(got, want)
     xi = torch.from_numpy(rng.integers(-1000, 1000, 1 << 22).astype(np.int32)).cuda()
-    goti = kex.kmap(kernel_size=(k,), padding=pad)(lambda v: np.max(v))(xi)
-    monkeypatch.delenv("KX_FOLD_1D")
-    assert torch.equal(goti, kex.kmap(kernel_size=(k,), padding=pad)(lambda v: np.max(v))(xi))
+    w = rng.standard_normal(k).astype(np.float32)
+    fs = [kex.kmap(kernel_size=(k,), padding=pad)(lambda v: np.sum(v * w)),
+          kex.kmap(kernel_size=(k,), padding=pad)(lambda v: np.max(v)),
+          kex.kmap(kernel_size=(k,), padding=pad)(lambda v: 0.5 * v[0] + v[k - 1])]
+    monkeypatch.setenv("KX_NO_FOLD_1D", "1")
+    want = [fs[0](x), fs[1](xi), fs[2](xi)]
+    monkeypatch.delenv("KX_NO_FOLD_1D")
+    got = [kex.kmap(kernel_size=(k,), padding=pad)(lambda v: np.sum(v * w))(x),
+           kex.kmap(kernel_size=(k,), padding=pad)(lambda v: np.max(v))(xi),
+           kex.kmap(kernel_size=(k,), padding=pad)(lambda v: 0.5 * v[0] + v[k - 1])(xi)]
+    for g_, w_ in zip(got, want):
+        assert g_.shape == w_.shape and g_.dtype == w_.dtype and torch.equal(g_, w_)
+    # ... and against the oracle on the first and last 4096 outputs (true array ends = zero padding)
+    border = ko.resolve_padding(pad, (k,))
+    taps = [(i,) for i in range(k)]
+    n_out = got[0].shape[0]
+    head = ko.affine_map(x[:4096 + k].cpu().numpy(), (k,), (1,), (border[0][0:1] + (0,),), taps, [float(c) for c in w])
+    m = min(4096, head.shape[0])
+    scale = ko.affine_map(np.abs(x[:4096 + k].cpu().numpy()), (k,), (1,), (border[0][0:1] + (0,),), taps, np.abs(w))
+    assert np.all(np.abs(got[0][:m].cpu().numpy() - head[:m]) <= 1e-5 * scale[:m] + 1e-30)
+    tail = ko.affine_map(x[-(4096 + k):].cpu().numpy(), (k,), (1,), ((0,) + border[0][1:2],), taps, [float(c) for c in w])
+    scale = ko.affine_map(np.abs(x[-(4096 + k):].cpu().numpy()), (k,), (1,), ((0,) + border[0][1:2],), taps, np.abs(w))
+    m = min(4096, tail.shape[0])
+    assert np.all(np.abs(got[0][n_out - m:].cpu().numpy() - tail[-m:]) <= 1e-5 * scale[-m:] + 1e-30)
+
+
+def test_vector_valued_1d_functions_do_not_take_the_fold(kex):
+    """A GATHER function (patch extraction) on a large 1-D device array: the fold only serves scalar functions, the
+    patches must still be bit exact (BASELINE test_benchmark_patch shape: k=3, 'same')."""
+    n = 1 << 22
+    x = torch.arange(n, dtype=torch.int32, device="cuda")
+    p = kex.kmap(kernel_size=(3,), padding="same")(lambda v: v)(x)
+    assert p.shape == (n, 3)
+    want = torch.stack([torch.cat([torch.zeros(1, dtype=torch.int32, device="cuda"), x[:-1]]), x,
+                        torch.cat([x[1:], torch.zeros(1, dtype=torch.int32, device="cuda")])], dim=1)
+    assert torch.equal(p, want)
