@@ -256,6 +256,7 @@ def run_ours(args):
         slab.fill_random(gen)
         step = slab.step
         n_win = slab.local_windows
+        halo_transport = slab.transport + (f" ({slab.transport_note})" if slab.transport_note else "")
     else:
         x = torch.randn((N, N), device=dev, dtype=torch.float32, generator=gen)
         holder = {}
@@ -386,7 +387,8 @@ def run_ours(args):
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "C2: 2-D 5-pt relative Laplacian kmap, 16384x16384 fp32 per GPU, padding=valid",
-                       "parallelism": "single GPU" if world == 1 else f"axis-0 row slabs x{world}, 1-row NCCL halo exchange per step",
+                       "parallelism": "single GPU" if world == 1 else
+                       f"axis-0 row slabs x{world}, 1-row halo exchange per step, transport={halo_transport}",
                        "cache": "input 1.07 GB + output 1.07 GB per GPU >> 126 MB L2; no flush needed",
                        "lattice_updates_per_step": total_win},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),

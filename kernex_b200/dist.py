@@ -206,6 +206,23 @@ class SlabStencil:
         self.local_windows = int(self.out.numel())
         # high priority: the O(halo) work must not queue behind the blocks of the interior launch
         self.side = torch.cuda.Stream(device=self.device, priority=-1)
+        self._warm_up()
+
+    def _warm_up(self):
+        """Launch every kernel of a step once before the first real step.  CUDA loads kernels lazily, and loading one
+        can wait for the running kernels of the context: a first-time load issued while this rank's pull kernel spins
+        on a neighbour's flag would serialise behind it.  After this, a step only launches resident kernels."""
+        for p, pm in self.maps:
+            if self.out[p.out0:p.out1].numel():
+                pm(self.ext[p.in0:p.in1], out=self.out[p.out0:p.out1])
+        if self._peers is not None:
+            lib, C = self._klib.load(), self._C
+            s = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+            idle = self._klib.KxHaloPull()
+            idle.n_sides, idle.epoch, idle.counter = 1, 0, self._pull.counter     # one side, no bytes, no flags
+            self._klib.check(lib.kx_halo_pull(C.byref(idle), s))
+            self._klib.check(lib.kx_flag_wait(C.c_void_p(self._peers.flag_ptr(self.rank, 0)), C.c_uint64(0), s))
+        torch.cuda.synchronize(self.device)
 
     # ---- peer-memory transport ------------------------------------------------------------------------------
     def _init_peer_memory(self, k0, rows, trailing, peers):

@@ -88,13 +88,15 @@ def lap3(x):
 
 
 @pytest.mark.parametrize("world,fn,ksize,rows,trailing,padding", [
-    (2, lap, (3, 3), 64, (256,), "valid"), (3, lap, (3, 3), 50, (132,), "same"), (4, lap3, (3, 3, 3), 12, (20, 36), "same"),
+    (2, lap, (3, 3), 64, (256,), "valid"), (3, lap, (3, 3), 50, (132,), "same"), (3, lap3, (3, 3, 3), 12, (20, 36), "same"),
     (3, lap3, (3, 3, 3), 16, (24, 64), "valid"), (2, lambda v: v[0, 0] + 2 * v[1, 1], (2, 2), 40, (64,), ((0, 1), (0, 1)))])
 def test_peer_halo_pull_with_emulated_ranks_on_one_gpu(kex, world, fn, ksize, rows, trailing, padding):
     """The multi-GPU transport on a 1-GPU box: `world` emulated ranks in this process, every rank with its own streams
     and its own peer buffer (`PeerGroup.local`: the "peer" pointers are local).  Exercises halo_pull_kernel, the
     READY / DONE flag protocol over three steps with new rows in between, and the strip launches; the stitched output
-    must equal the single-launch kmap of the whole array bit for bit."""
+    must equal the single-launch kmap of the whole array bit for bit.  (At most 3 emulated ranks: every rank needs two
+    streams that make progress independently, and one process has 8 hardware queues by default -- with more streams than
+    queues a spinning pull kernel can sit in front of the kernel it is waiting for.  Real ranks are separate processes.)"""
     from kernex_b200 import _lib, peer
     from kernex_b200.dist import SlabStencil
     dev = torch.device("cuda", 0)
