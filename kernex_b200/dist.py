@@ -194,6 +194,7 @@ class SlabStencil:
             self.transport = "nccl" if self.world > 1 else self.transport
             self.ext = torch.zeros((L.ext_rows,) + trailing, dtype=torch.float32, device=self.device)
         strides = (1,) * len(kernel_size)
+        self._func_map, self._relative, self._args = {func: ()}, relative, tuple(args)
         self.maps = []
         out_trailing = None
         for p in L.pieces:
@@ -330,6 +331,94 @@ class SlabStencil:
         if self.world > 1:
             main.wait_stream(self.side)
         return self.out
+
+    def step_host(self, x_host: torch.Tensor, y_host: torch.Tensor, chunk_bytes: int = 64 << 20):
+        """One application with this rank's rows in PINNED HOST memory on both sides (the end-to-end path of a
+        host-resident global grid): ``x_host`` = my ``rows_per_rank`` rows, ``y_host`` = my output rows.
+
+        PCIe is full duplex and the link, not HBM, bounds this call, so the slab is streamed: the edge rows the
+        neighbours need go first (their halo pull over NVLink then overlaps everything else), the remaining rows
+        follow in chunks on a copy-in stream, every chunk's windows are launched as soon as its rows have landed,
+        and finished output rows leave on a copy-out stream.  Synchronises before returning."""
+        if self.world == 1:
+            raise ValueError("step_host is the multi-GPU path; on one GPU call the kmap on the NumPy array (hostpipe.py)")
+        from .engine import PreparedMap
+        L, rows, k0 = self.layout, self.layout.rows, self.layout.k0
+        if tuple(x_host.shape) != (rows,) + tuple(self.ext.shape[1:]) or tuple(y_host.shape) != tuple(self.out.shape):
+            raise ValueError(f"step_host expects host rows {(rows,) + tuple(self.ext.shape[1:])} -> {tuple(self.out.shape)}")
+        if not (x_host.is_pinned() and y_host.is_pinned()):
+            raise ValueError("step_host needs pinned host tensors (asynchronous copies)")
+        main = torch.cuda.current_stream(self.device)
+        if not hasattr(self, "_s_in"):
+            self._s_in, self._s_out = torch.cuda.Stream(self.device), torch.cuda.Stream(self.device)
+            self._chunk_maps = {}
+        s_in, s_out = self._s_in, self._s_out
+        own = self.ext[L.halo_top:L.halo_top + rows]
+        self._wait_neighbours_done()
+        e_up, e_dn = L.send_up, L.send_down
+        if e_up:
+            own[:e_up].copy_(x_host[:e_up], non_blocking=True)
+        if e_dn:
+            own[rows - e_dn:].copy_(x_host[rows - e_dn:], non_blocking=True)
+        reqs = []
+        self.side.wait_stream(main)
+        if self._peers is not None:
+            self._pull_halos(self.side)
+        else:
+            with torch.cuda.stream(self.side):
+                reqs = exchange_halos(self.ext, L, self.group)
+        s_in.wait_stream(main)
+        s_out.wait_stream(main)
+        mid = next((p, pm) for p, pm in self.maps if not p.needs_halo and p.in0 == L.halo_top)[0]
+        mid_cnt = mid.out1 - mid.out0
+        row_bytes = own[0].numel() * 4
+        step_rows = max(int(chunk_bytes // max(row_bytes, 1)), k0)
+        c0, j_done = e_up, 0
+        hi = rows - e_dn
+        while c0 < hi or j_done < mid_cnt:
+            c1 = min(c0 + step_rows, hi)
+            if c1 > c0:
+                with torch.cuda.stream(s_in):
+                    own[c0:c1].copy_(x_host[c0:c1], non_blocking=True)
+                    ev_in = torch.cuda.Event()
+                    ev_in.record(s_in)
+                main.wait_event(ev_in)
+            loaded = rows if c1 >= hi else c1                 # own rows [0, loaded) are on the device (edges went first)
+            j_end = min(max(loaded - k0 + 1, j_done), mid_cnt)
+            if j_end > j_done:
+                n_in = j_end - j_done + k0 - 1
+                pm = self._chunk_maps.get(n_in)
+                if pm is None:
+                    ref = self.maps[[p for p, _ in self.maps].index(mid)][1]
+                    border = ((0, 0),) + tuple((int(ref.geom.lo[d]), int(ref.geom.hi[d])) for d in range(1, ref.geom.ndim))
+                    ksize = tuple(int(ref.geom.ksize[d]) for d in range(ref.geom.ndim))
+                    pm = PreparedMap(self._func_map, (n_in,) + tuple(self.ext.shape[1:]), ksize, (1,) * len(ksize), border,
+                                     self._relative, args=self._args)
+                    self._chunk_maps[n_in] = pm
+                a0 = L.halo_top + j_done
+                o0 = mid.out0 + j_done
+                pm(self.ext[a0:a0 + n_in], out=self.out[o0:o0 + (j_end - j_done)])
+                ev_k = torch.cuda.Event()
+                ev_k.record(main)
+                with torch.cuda.stream(s_out):
+                    s_out.wait_event(ev_k)
+                    y_host[o0:o0 + (j_end - j_done)].copy_(self.out[o0:o0 + (j_end - j_done)], non_blocking=True)
+                j_done = j_end
+            c0 = c1
+            if c1 >= hi and j_done >= mid_cnt:
+                break
+        with torch.cuda.stream(self.side):
+            for r in reqs:
+                r.wait()
+            self.side.wait_stream(s_in)                       # the strips read own rows next to the halos
+            for p, pm in self.maps:
+                if p.needs_halo and p.out1 > p.out0:
+                    pm(self.ext[p.in0:p.in1], out=self.out[p.out0:p.out1])
+                    y_host[p.out0:p.out1].copy_(self.out[p.out0:p.out1], non_blocking=True)
+        main.wait_stream(self.side)
+        main.wait_stream(s_out)
+        main.synchronize()
+        return y_host
 
     def vjp(self, g_local: torch.Tensor, want_input=True, want_coef=False):
         """Adjoint of :meth:`step`: ``g_local`` is the cotangent of this rank's output rows.

@@ -550,9 +550,13 @@ class PreparedMap:
         """Cotangent of the coefficient table ``[n_taps]`` (``kx_map_vjp_coef``: fused window correlation,
         deterministic two-stage reduction)."""
         self._check_vjp(g)
-        nbytes = int(self._lib.kx_vjp_coef_scratch_bytes(C.byref(self.geom), C.byref(self.prog.c)))
-        scratch = torch.empty(max(nbytes, 4), dtype=torch.uint8, device=x.device)
-        dcoef = torch.zeros(self.prog.c.n_taps, dtype=torch.float32, device=x.device)
+        scratch = self.__dict__.get("_wgrad_scratch")
+        if scratch is None or scratch.device != x.device:   # per-block partials: sized once per plan, reused per call
+            nbytes = int(self._lib.kx_vjp_coef_scratch_bytes(C.byref(self.geom), C.byref(self.prog.c)))
+            scratch = self._wgrad_scratch = torch.empty(max(nbytes, 4), dtype=torch.uint8, device=x.device)
+        dcoef = torch.empty(self.prog.c.n_taps, dtype=torch.float32, device=x.device)
+        if not g.numel():
+            dcoef.zero_()
         if g.numel():
             _lib.check(self._lib.kx_map_vjp_coef(C.byref(self.geom), C.byref(self.prog.c), _ptr(x), _ptr(g), _ptr(scratch),
                                                  _ptr(dcoef), _stream_ptr(x.device)))

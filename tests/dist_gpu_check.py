@@ -59,6 +59,19 @@ def main():
         ok = ok and bool(same2.item())
         if rank == 0:
             print(f"  {p2p.transport} transport vs nccl: {'bit-identical' if same2.item() else 'MISMATCH'}", flush=True)
+        # end-to-end form: my rows in pinned host memory on both sides, streamed in small chunks (several per slab)
+        xh = torch.empty(tuple(slab.ext[slab.layout.own].shape), dtype=torch.float32, pin_memory=True)
+        xh.copy_(slab.ext[slab.layout.own])
+        yh = torch.empty(tuple(out.shape), dtype=torch.float32, pin_memory=True)
+        for it in range(2):
+            yh.zero_()
+            p2p.step_host(xh, yh, chunk_bytes=7 * xh[0].numel() * 4)
+        same3 = torch.tensor([1 if torch.equal(yh, out.cpu()) else 0], device=dev)
+        dist.all_reduce(same3, op=dist.ReduceOp.MIN)
+        ok = ok and bool(same3.item())
+        if rank == 0:
+            print(f"  step_host (pinned host rows, chunked) vs device step: {'bit-identical' if same3.item() else 'MISMATCH'}",
+                  flush=True)
         own = slab.ext[slab.layout.own].contiguous()
         parts = [torch.empty_like(own) for _ in range(world)]
         dist.all_gather(parts, own)
