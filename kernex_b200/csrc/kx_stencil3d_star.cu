@@ -1,31 +1,40 @@
 // Fast path: 3-D 7-point STAR stencils (taps on the three axes through the window centre
 // of a 3x3x3 window), stride 1, f32 / i32, rows 16-byte aligned -- BASELINE config 5.
 //
-// 2.5-D blocking with an asynchronous shared-memory plane ring (tuned in benchmarks/exp3d.cu):
-//   * a block owns a 16-row x 128-column tile and marches kZC = 32 output planes along
-//     axis 0.  Short z chunks keep the resident wave of blocks on a compact slab of the
-//     volume, so the y/x halo of neighbouring tiles is found in L2 instead of HBM (measured:
-//     full-depth marches run at 4.0 TB/s, 32-plane chunks at 6.0 TB/s);
-//   * every input plane tile (18 rows x 136 columns) is fetched ONCE with 16-byte
-//     cp.async.cg (LDGSTS: global -> shared, no registers, zero-fill outside the array =
-//     the reference's zero padding) into a 3-stage ring, two planes ahead of the math; the
-//     per-thread chunk offsets / validity are computed once, outside the plane loop;
-//   * each thread owns 4 columns x 2 rows; per plane it reads its rows from shared memory
-//     with 128-bit loads and keeps the previous / current plane in registers (z queue); the
-//     plane loop is unrolled by two so the queue rotates by renaming instead of moves;
-//   * 128-bit streaming stores; the window misalignment (-lo_x) mod 4 and "all seven taps
-//     present" are template parameters (the first ncu pass showed the kernel issue-bound at
-//     80 % with per-FMA tap-mask tests: they are compiled out for the full star).
+// 2.5-D blocking with an asynchronous shared-memory plane ring (first tuned in benchmarks/exp3d.cu):
+//   * a block (8 warps) owns an 8-row x 256-column tile and marches kZC = 64 output planes along axis 0;
+//   * every input plane tile (10 rows x 264 columns) is fetched ONCE with 16-byte cp.async.cg (LDGSTS: global ->
+//     shared, no registers, zero-fill outside the array = the reference's zero padding) into a 3-stage ring, two
+//     planes ahead of the math; the per-thread chunk offsets / validity are computed once, outside the plane loop;
+//   * each thread owns 4 columns x 2 rows; per plane it reads its rows from shared memory with 128-bit loads and
+//     keeps the previous / current plane in registers (z queue); the plane loop is unrolled by two so the queue
+//     rotates by renaming instead of moves;
+//   * 128-bit streaming stores; the window misalignment (-lo_x) mod 4 and "all seven taps present" are template
+//     parameters (the first ncu pass showed the kernel issue-bound at 80 % with per-FMA tap-mask tests: they are
+//     compiled out for the full star).
+//
+// Round-2 measurements on B200 at 2048^3 (one box, back to back; profiles/r2_star_*):
+//   16 x 128 tiles, zc 32, blocks in x / y / z-chunk order           720 GLUP/s   DRAM read 36.5 GB (1.063 x algorithmic)
+//   + z chunk of a wave-sized tile GROUP runs faster than the group   720          DRAM read 34.6 GB (1.006 x): the
+//     (block_coords below)                                                        z-halo planes hit L2 -- but the kernel
+//                                                                                 was not limited by the extra bytes
+//   + 8 x 256 tiles (1 KB contiguous per row segment, KX_STAR_WX=2)   745
+//   + zc 64                                                           765-770     = 0.935-0.94 of the measured copy peak
+//   4 x 512 tiles 727-763, a 4-stage ring 666-705, 4 blocks / SM at 64 registers 625, one barrier per two planes 617,
+//   cp.async L2::128B / L2::256B prefetch hints: no change.  Without the groups zc 64 gives 749.
+// KX_STAR_WX=1|2|4, KX_STAR_ZC=n, KX_STAR_NO_GROUPS=1 and KX_STAR_GRID3D=1 select the other variants (bit-identical
+// results; cross-checks and A/B timing).
 #include "kx_internal.cuh"
 
 namespace kx {
 
 namespace {
 
-constexpr int kTX = 128, kTYB = 8, kRY = 2, kTY = kTYB * kRY;   // tile 16 x 128, 256 threads
-constexpr int kThreads3 = 32 * kTYB;
+constexpr int kWarps = 8;                     // 256 threads; a warp covers 128 columns x RY rows
+constexpr int kThreads3 = 32 * kWarps;
+// tile = (kWarps / WX * RY) rows x (128 * WX) columns: WX = 1, RY = 2 -> 16 x 128; WX = 2, RY = 2 -> 8 x 256
 constexpr int kStages = 3;
-constexpr int kZC = 32;
+constexpr int kZC = 64;
 
 template <typename T>
 struct StarArgs {
@@ -35,6 +44,8 @@ struct StarArgs {
   int din, hin, win, dout, hout, wout;
   int lz, ly, lx;
   int nzc, zc;           // z chunks per volume, planes per chunk
+  int tiles_x, ntiles;   // xy tiles per plane
+  int group;             // tiles per scheduling group (see block_coords)
   uint32_t mask;        // bit t set = tap t present; taps in row-major window order:
   T bias;               // 0:(z-1) 1:(y-1) 2:(x-1) 3:centre 4:(x+1) 5:(y+1) 6:(z+1)
   T c[7];
@@ -86,10 +97,42 @@ __device__ __forceinline__ void store4(T* o, const T (&acc)[4], int n_valid) {
 
 // (A variant with a 4-stage ring and one block barrier per TWO planes was measured in round 2: 617 vs 720 GLUP/s at
 // 2048^3 -- the extra stage costs a resident block per SM -- and removed.)
-template <typename T, int SHIFT, bool FULL>
-__global__ void __launch_bounds__(kThreads3)
+// Block -> (batch, z chunk, tile) mapping.  Blocks are dispatched in linear order, so the order decides what the
+// ~444 resident blocks (one "wave") share in L2.  Tiles are cut into GROUPS of about one wave (whole rows of tiles: a
+// compact patch, so the y / x halos of its tiles are read by blocks of the same wave), and inside a group the z chunk
+// runs FASTER than the group index: wave w marches chunk k of the group, wave w+1 chunk k+1 of the SAME tiles.  The
+// two input planes consecutive chunks share (2 of zc+2: 6.3 % of the reads at zc = 32, ncu r1b: 36.5 GB read vs
+// 34.4 GB algorithmic) were the last planes the previous wave touched and are still in L2.
+template <typename T>
+__device__ __forceinline__ void block_coords(const StarArgs<T>& a, int& b, int& zchunk, int& tx_tile, int& ty_tile) {
+  if (a.group == 0) {   // 3-D grid launch: x tiles, y tiles, batch * z chunks (A/B switch KX_STAR_GRID3D=1)
+    b = blockIdx.z / a.nzc;
+    zchunk = blockIdx.z - b * a.nzc;
+    tx_tile = blockIdx.x;
+    ty_tile = blockIdx.y;
+    return;
+  }
+  const unsigned per_batch = (unsigned)a.ntiles * (unsigned)a.nzc;
+  unsigned l = blockIdx.x;
+  b = (int)(l / per_batch);
+  l -= (unsigned)b * per_batch;
+  const unsigned gsz = (unsigned)a.group * (unsigned)a.nzc;
+  const unsigned ngroups = ((unsigned)a.ntiles + a.group - 1) / a.group;
+  unsigned g = l / gsz;
+  if (g > ngroups - 1) g = ngroups - 1;
+  const unsigned r = l - g * gsz;
+  const unsigned in_group = min((unsigned)a.group, (unsigned)a.ntiles - g * a.group);
+  zchunk = (int)(r / in_group);
+  const unsigned tile = g * a.group + (r - (unsigned)zchunk * in_group);
+  ty_tile = (int)(tile / (unsigned)a.tiles_x);
+  tx_tile = (int)(tile - (unsigned)ty_tile * a.tiles_x);
+}
+
+template <typename T, int SHIFT, bool FULL, int WX, int kRY>
+__global__ void __launch_bounds__(kThreads3, kRY == 2 ? 3 : 2)
 stencil3d_star_kernel(const __grid_constant__ StarArgs<T> a) {
   constexpr int STG = kStages;
+  constexpr int kTX = 128 * WX, kTY = kWarps / WX * kRY;
   constexpr int NV = (SHIFT + 6 + 3) / 4;          // aligned 4-vectors covering the 6 needed columns
   constexpr int SW = kTX + 4 * NV;                  // tile width (columns), multiple of 4
   constexpr int SR = kTY + 2;
@@ -98,10 +141,11 @@ stencil3d_star_kernel(const __grid_constant__ StarArgs<T> a) {
   __shared__ __align__(16) T smem[STG * SR * SW];
 
   const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * 32 + tx;
-  const int b = blockIdx.z / a.nzc;
-  const int z0 = (blockIdx.z - b * a.nzc) * a.zc;
+  int b, zchunk, tile_x, tile_y;
+  block_coords(a, b, zchunk, tile_x, tile_y);
+  const int z0 = zchunk * a.zc;
   const int z1 = min(z0 + a.zc, a.dout);
-  const int x0 = blockIdx.x * kTX, y0 = blockIdx.y * kTY;
+  const int x0 = tile_x * kTX, y0 = tile_y * kTY;
   const T* __restrict__ in = a.in + (int64_t)b * a.in_batch;
   T* __restrict__ out = a.out + (int64_t)b * a.out_batch;
   const int gz0 = z0 - a.lz;                        // global plane of ring plane 0
@@ -141,13 +185,13 @@ stencil3d_star_kernel(const __grid_constant__ StarArgs<T> a) {
   };
 
 #pragma unroll
-  for (int s = 0; s < kStages - 1; ++s) {
+  for (int s = 0; s < STG - 1; ++s) {
     if (s < nplanes) issue(s);
     cp_commit();
   }
 
-  const int jx = 4 * tx;        // thread's first output column inside the tile
-  const int iy = ty * kRY;      // thread's first output row inside the tile
+  const int jx = 4 * tx + 128 * (ty % WX);   // thread's first output column inside the tile
+  const int iy = (ty / WX) * kRY;            // thread's first output row inside the tile
   const int ox = x0 + jx;
   const int n_valid = min(4, a.wout - ox);
   const bool col_ok = ox < a.wout;
@@ -177,9 +221,9 @@ stencil3d_star_kernel(const __grid_constant__ StarArgs<T> a) {
 
   // one ring step: `up` receives plane pl, `mid` holds plane pl-1, `below` plane pl-2
   auto step = [&](int pl, T (&mid)[kRY + 2][6], T (&up)[kRY + 2][6]) {
-    cp_wait<kStages - 2>();
+    cp_wait<STG - 2>();
     __syncthreads();            // plane pl landed for all threads; the stage read last step is free
-    if (pl + kStages - 1 < nplanes) issue(pl + kStages - 1);
+    if (pl + STG - 1 < nplanes) issue(pl + STG - 1);
     cp_commit();
     read_plane(pl, up);
     if (pl >= 2) {
@@ -252,14 +296,34 @@ int run_star(const MapArgs& m, const KxProgram& p, int64_t batch, cudaStream_t s
   a.zc = kZC;
   if (const char* e = getenv("KX_STAR_ZC")) a.zc = atoi(e) > 0 ? atoi(e) : a.zc;   // tuning knob
   a.nzc = (a.dout + a.zc - 1) / a.zc;
+  int wx = 2, ry = 2;
+  if (const char* e = getenv("KX_STAR_WX")) wx = atoi(e) == 2 ? 2 : (atoi(e) == 4 ? 4 : 1);
+  const int kTX = 128 * wx, kTY = kWarps / wx * ry;
   const int tiles_x = (a.wout + kTX - 1) / kTX, tiles_y = (a.hout + kTY - 1) / kTY;
-  if ((int64_t)a.nzc * batch > 65535 || tiles_y > 65535) return KX_ERR_UNSUPPORTED;
-  dim3 grid(tiles_x, tiles_y, (unsigned)(a.nzc * batch)), block(32, kTYB);
+  const int64_t nblocks = (int64_t)tiles_x * tiles_y * a.nzc * batch;
+  if (nblocks > 0x7fffffffll || (int64_t)tiles_x * tiles_y > 0x7fffffll) return KX_ERR_UNSUPPORTED;
+  a.tiles_x = tiles_x;
+  a.ntiles = tiles_x * tiles_y;
+  // one group = whole rows of tiles filling about one wave of resident blocks (3 per SM)
+  const int minb = ry == 2 ? 3 : 2;
+  const int wave = sm_count() * minb;
+  int gy = wave / tiles_x;
+  if (gy < 1) gy = 1;
+  a.group = getenv("KX_STAR_NO_GROUPS") ? a.ntiles : gy * tiles_x;              // whole volume = the old x, y, z-chunk order
+  if (a.group > a.ntiles) a.group = a.ntiles;
+  dim3 grid((unsigned)nblocks), block(32, kWarps);
+  if (getenv("KX_STAR_GRID3D") && (int64_t)a.nzc * batch <= 65535 && tiles_y <= 65535) {
+    a.group = 0;
+    grid = dim3(tiles_x, tiles_y, (unsigned)(a.nzc * batch));
+  }
   const int shift = (((-a.lx) % 4) + 4) % 4;
   const bool full = a.mask == 0x7fu;
-#define KX_STAR(S)                                                                 \
-  if (full) stencil3d_star_kernel<T, S, true><<<grid, block, 0, s>>>(a);           \
-  else stencil3d_star_kernel<T, S, false><<<grid, block, 0, s>>>(a);
+#define KX_STAR3(S, WXV, RYV)                                                          \
+  if (full) stencil3d_star_kernel<T, S, true, WXV, RYV><<<grid, block, 0, s>>>(a);     \
+  else stencil3d_star_kernel<T, S, false, WXV, RYV><<<grid, block, 0, s>>>(a);
+#define KX_STAR2(S, RYV) \
+  if (wx == 2) { KX_STAR3(S, 2, RYV) } else if (wx == 4) { KX_STAR3(S, 4, RYV) } else { KX_STAR3(S, 1, RYV) }
+#define KX_STAR(S) KX_STAR2(S, 2)
   switch (shift) {
     case 0: KX_STAR(0) break;
     case 1: KX_STAR(1) break;
@@ -267,6 +331,8 @@ int run_star(const MapArgs& m, const KxProgram& p, int64_t batch, cudaStream_t s
     default: KX_STAR(3) break;
   }
 #undef KX_STAR
+#undef KX_STAR2
+#undef KX_STAR3
   return after_launch("stencil3d_star_kernel");
 }
 

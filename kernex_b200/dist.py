@@ -369,7 +369,7 @@ class SlabStencil:
                 reqs = exchange_halos(self.ext, L, self.group)
         s_in.wait_stream(main)
         s_out.wait_stream(main)
-        mid = next((p, pm) for p, pm in self.maps if not p.needs_halo and p.in0 == L.halo_top)[0]
+        mid = next(p for p, _ in self.maps if p.in0 == L.halo_top and p.in1 == L.halo_top + rows)   # the interior piece
         mid_cnt = mid.out1 - mid.out0
         row_bytes = own[0].numel() * 4
         step_rows = max(int(chunk_bytes // max(row_bytes, 1)), k0)
@@ -411,8 +411,8 @@ class SlabStencil:
             for r in reqs:
                 r.wait()
             self.side.wait_stream(s_in)                       # the strips read own rows next to the halos
-            for p, pm in self.maps:
-                if p.needs_halo and p.out1 > p.out0:
+            for p, pm in self.maps:               # halo strips and, on the edge ranks, the global-padding strips
+                if p is not mid and p.out1 > p.out0:
                     pm(self.ext[p.in0:p.in1], out=self.out[p.out0:p.out1])
                     y_host[p.out0:p.out1].copy_(self.out[p.out0:p.out1], non_blocking=True)
         main.wait_stream(self.side)
