@@ -397,6 +397,30 @@ def run_config_suite(world, rank, dev, clocks, peak, budget_s=60.0):
         del x
         torch.cuda.empty_cache()
 
+    if world > 1 and not over_budget():
+        # ---- C2 backward on the slabs: flipped-tap stencil per piece + the TRANSPOSED halo exchange (the cotangent
+        # rows that landed in my halos are sent back to their owners and added there) -------------------------------
+        from kernex_b200.dist import SlabStencil
+        slab = SlabStencil(laplacian, kernel_size=(3, 3), relative=True, rows_per_rank=N, width=N, device=dev)
+        slab.fill_random(gen)
+        o = slab.step()
+        g = torch.randn(o.shape, device=dev, generator=gen)
+        dx, _ = slab.vjp(g)
+        torch.cuda.synchronize()
+        # rows 8000..8063 of my slab: interior, the float64-free oracle form of the forward check applies to g
+        off = 0 if slab.layout.first else 1     # my output row j is the window starting at own row j - off
+        gb = g[7998 + off:8064 + off].cpu().numpy()
+        flipped = [(2 - a, 2 - b) for a, b in TAPS]
+        want = ko.affine_map(gb, (3, 3), (1, 1), ((0, 0), (2, 2)), flipped, COEFS)
+        scale = ko.affine_map(np.abs(gb), (3, 3), (1, 1), ((0, 0), (2, 2)), flipped, np.abs(COEFS))
+        par = all_ok(within(dx[8000:8064].cpu().numpy(), want, scale))
+        ms, win = timed(lambda: slab.vjp(g), 20)
+        emit("C2 backward on axis-0 slabs (VJP wrt x, transposed halo exchange)", total(N * N), 8, ms, win, par,
+             kernel="stencil2d_kernel", halo_transport="nccl (cotangent halo rows are sent back and added)")
+        slab.close()
+        del slab, o, g, dx
+        torch.cuda.empty_cache()
+
     # ---- C4: kscan linear convection, nt=4096, nx = 2^21 columns per GPU (2^24 on 8), axis-1 shards -------------
     if not over_budget():
         from kernex_b200.dist import ColumnShardedScan

@@ -434,7 +434,15 @@ class SlabStencil:
         g_local = g_local.contiguous()
         dx_own = dcoef = None
         if want_input:
-            dext = torch.zeros_like(self.ext)
+            # the interior piece writes every own row; only the halo rows need zeros before the strips accumulate
+            dext = torch.empty_like(self.ext)
+            if L.halo_top:
+                dext[:L.halo_top].zero_()
+            if L.halo_bot:
+                dext[L.halo_top + L.rows:].zero_()
+            if not any((not p.needs_halo and p.in0 == L.halo_top and p.in1 == L.halo_top + L.rows and
+                        g_local[p.out0:p.out1].shape[0] > 0) for p, _ in self.maps):
+                dext.zero_()
             for p, pm in self.maps:
                 gp = g_local[p.out0:p.out1]
                 if gp.shape[0] == 0:
