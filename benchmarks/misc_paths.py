@@ -159,3 +159,21 @@ if want("dense3d"):
     rep("3-D maxpool 3x3x3 s2 on 1024^3", x.numel() * 4 + y.numel() * 4, med, y.numel())
     del x, y
     torch.cuda.empty_cache()
+
+if want("pool3d"):
+    # 3-D pooling (kx_pool3d): cubic windows, stride 2 / 3, whole-depth z march per warp
+    x = torch.randn((1024, 1024, 1024), device=dev, generator=g)
+    for name, fn, k, s in [("3-D maxpool 3x3x3 s2", lambda v: np.max(v), 3, 2), ("3-D avgpool 3x3x3 s2", lambda v: np.mean(v), 3, 2),
+                           ("3-D maxpool 2x2x2 s2", lambda v: np.max(v), 2, 2), ("3-D avgpool 3x3x3 s3", lambda v: np.mean(v), 3, 3)]:
+        f = kex.kmap(kernel_size=(k,) * 3, strides=(s,) * 3)(fn)
+        y = f(x)
+        med, _ = timeit(lambda: f(x), 4)
+        rep(f"{name} on 1024^3", x.numel() * 4 + y.numel() * 4, med, y.numel())
+    del x, y
+    xb = torch.randn((16, 256, 512, 512), device=dev, generator=g)
+    f = kex.vmap(kex.kmap(kernel_size=(3, 3, 3), strides=(2, 2, 2))(lambda v: np.mean(v)))
+    y = f(xb)
+    med, _ = timeit(lambda: f(xb), 4)
+    rep("3-D avgpool 3x3x3 s2 under vmap on (16,256,512,512)", xb.numel() * 4 + y.numel() * 4, med, y.numel())
+    del xb, y
+    torch.cuda.empty_cache()

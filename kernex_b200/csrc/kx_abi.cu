@@ -88,6 +88,8 @@ int dispatch_map(const MapArgs& a, const KxProgram& prog, cudaStream_t s) {
   if (rc != KX_ERR_UNSUPPORTED) return rc;
   rc = try_pool2d(a, prog, s);
   if (rc != KX_ERR_UNSUPPORTED) return rc;
+  rc = try_pool3d(a, prog, s);
+  if (rc != KX_ERR_UNSUPPORTED) return rc;
   return launch_generic_map(a, prog, s);
 }
 

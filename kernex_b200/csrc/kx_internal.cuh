@@ -123,6 +123,7 @@ int try_conv2d(const MapArgs& a, const KxProgram& prog, cudaStream_t s);
 int try_conv_dense3d(const MapArgs& a, const KxProgram& prog, int64_t batch, cudaStream_t s);
 int try_stencil3d_dense(const MapArgs& a, const KxProgram& prog, int64_t batch, cudaStream_t s);
 int try_pool2d(const MapArgs& a, const KxProgram& prog, cudaStream_t s);
+int try_pool3d(const MapArgs& a, const KxProgram& prog, cudaStream_t s);
 int64_t conv_wgrad_scratch_bytes(const KxGeom& g, const KxProgram& prog);
 int try_conv_wgrad(const KxGeom& g, const KxProgram& prog, const void* x, const void* gout, void* scratch,
                    void* dcoef, cudaStream_t s);
