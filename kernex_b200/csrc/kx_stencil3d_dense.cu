@@ -22,10 +22,13 @@ namespace kx {
 
 namespace {
 
-constexpr int kDX = 128, kDYB = 8, kDRY = 2, kDY = kDYB * kDRY;   // tile 16 x 128, 256 threads
+// tile 8 rows x 256 columns (two warps side by side, 1 KB contiguous per row segment), 256 threads, 64-plane z chunks,
+// wave-sized tile groups whose z chunk runs fastest: the geometry measured best on kx_stencil3d_star.cu (see there)
+constexpr int kDWX = 2, kDYB = 8, kDRY = 2;
+constexpr int kDX = 128 * kDWX, kDY = kDYB / kDWX * kDRY;
 constexpr int kDThreads = 32 * kDYB;
 constexpr int kDStages = 3;
-constexpr int kDZC = 32;
+constexpr int kDZC = 64;
 
 template <typename T>
 struct DenseArgs {
@@ -35,6 +38,7 @@ struct DenseArgs {
   int din, hin, win, dout, hout, wout;
   int lz, ly, lx;
   int nzc, zc;
+  int tiles_x, ntiles, group;   // block -> (z chunk, tile) mapping, see block_coords in kx_stencil3d_star.cu
   T bias;
   T c[27];              // row-major (kz, ky, kx)
 };
@@ -86,10 +90,28 @@ stencil3d_dense_kernel(const __grid_constant__ DenseArgs<T> a) {
   __shared__ __align__(16) T smem[kDStages * SR * SW];
 
   const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * 32 + tx;
-  const int b = blockIdx.z / a.nzc;
-  const int z0 = (blockIdx.z - b * a.nzc) * a.zc;
+  // linear block id -> (batch, tile group, z chunk, tile in group): the z chunk of a wave-sized group of tiles runs
+  // faster than the group index, so the planes two consecutive chunks share are L2 hits
+  int b, zchunk, tile_x, tile_y;
+  {
+    const unsigned per_batch = (unsigned)a.ntiles * (unsigned)a.nzc;
+    unsigned l = blockIdx.x;
+    b = (int)(l / per_batch);
+    l -= (unsigned)b * per_batch;
+    const unsigned gsz = (unsigned)a.group * (unsigned)a.nzc;
+    const unsigned ngroups = ((unsigned)a.ntiles + a.group - 1) / a.group;
+    unsigned g = l / gsz;
+    if (g > ngroups - 1) g = ngroups - 1;
+    const unsigned r = l - g * gsz;
+    const unsigned in_group = min((unsigned)a.group, (unsigned)a.ntiles - g * a.group);
+    zchunk = (int)(r / in_group);
+    const unsigned tile = g * a.group + (r - (unsigned)zchunk * in_group);
+    tile_y = (int)(tile / (unsigned)a.tiles_x);
+    tile_x = (int)(tile - (unsigned)tile_y * a.tiles_x);
+  }
+  const int z0 = zchunk * a.zc;
   const int z1 = min(z0 + a.zc, a.dout);
-  const int x0 = blockIdx.x * kDX, y0 = blockIdx.y * kDY;
+  const int x0 = tile_x * kDX, y0 = tile_y * kDY;
   const T* __restrict__ in = a.in + (int64_t)b * a.in_batch;
   T* __restrict__ out = a.out + (int64_t)b * a.out_batch;
   const int gz0 = z0 - a.lz;                        // global plane of ring plane 0
@@ -133,8 +155,8 @@ stencil3d_dense_kernel(const __grid_constant__ DenseArgs<T> a) {
     d_cp_commit();
   }
 
-  const int jx = 4 * tx;        // thread's first output column inside the tile
-  const int iy = ty * kDRY;     // thread's first output row inside the tile
+  const int jx = 4 * tx + 128 * (ty % kDWX);   // thread's first output column inside the tile
+  const int iy = (ty / kDWX) * kDRY;            // thread's first output row inside the tile
   const int ox = x0 + jx;
   const int n_valid = min(4, a.wout - ox);
   const bool col_ok = ox < a.wout;
@@ -257,9 +279,25 @@ int run_dense(const MapArgs& m, const KxProgram& p, int64_t batch, cudaStream_t 
   a.bias = (T)f.bias;
   a.zc = kDZC;
   a.nzc = (a.dout + a.zc - 1) / a.zc;
+  if (const char* e = getenv("KX_DENSE3D_ZC")) {   // tuning knob
+    a.zc = atoi(e) > 0 ? atoi(e) : a.zc;
+    a.nzc = (a.dout + a.zc - 1) / a.zc;
+  }
   const int tiles_x = (a.wout + kDX - 1) / kDX, tiles_y = (a.hout + kDY - 1) / kDY;
-  if ((int64_t)a.nzc * batch > 65535 || tiles_y > 65535) return KX_ERR_UNSUPPORTED;
-  dim3 grid(tiles_x, tiles_y, (unsigned)(a.nzc * batch)), block(32, kDYB);
+  const int64_t nblocks = (int64_t)tiles_x * tiles_y * a.nzc * batch;
+  if (nblocks > 0x7fffffffll || (int64_t)tiles_x * tiles_y > 0x7fffffll) return KX_ERR_UNSUPPORTED;
+  a.tiles_x = tiles_x;
+  a.ntiles = tiles_x * tiles_y;
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, stencil3d_dense_kernel<T, 0>, kDThreads, 0) != cudaSuccess || per_sm < 1) {
+    cudaGetLastError();
+    per_sm = 2;
+  }
+  int gy = sm_count() * per_sm / tiles_x;          // one group = whole rows of tiles filling about one wave
+  if (gy < 1) gy = 1;
+  a.group = getenv("KX_DENSE3D_NO_GROUPS") ? a.ntiles : gy * tiles_x;
+  if (a.group > a.ntiles) a.group = a.ntiles;
+  dim3 grid((unsigned)nblocks), block(32, kDYB);
   const int shift = (((-a.lx) % 4) + 4) % 4;
   switch (shift) {
     case 0: stencil3d_dense_kernel<T, 0><<<grid, block, 0, s>>>(a); break;
