@@ -7,17 +7,12 @@
 // Same row-marching skeleton as kx_stencil2d.cu (a thread owns 4 output columns, keeps the last KY
 // input rows in a register queue, 128-bit loads).  Region selection follows select_func
 // (kernex/_src/utils.py:338-382: keys scanned from the LAST inserted, first match wins, no match =
-// function 0) but is factored so that the row loop only does bit operations:
-//   * column part of every key, per owned column: a 32-bit mask, computed once per thread;
-//   * row part of every key (plus the leading batch axes), per row of the band: a 32-bit mask in
-//     shared memory, computed once per block;
-//   * per output: m = row_mask & col_mask, function = m ? func_of_key[31 - clz(m)] : 0.
-// A thread keeps the coefficients (bias, KY*KX taps, tap mask) of ONE function in registers: the one its 4
-// columns agree on, reloaded from the parameter bank only when the selection changes (at region boundaries).
-// Inside a region the row loop is therefore the plain stencil loop with register coefficients, whatever the
-// number of functions; a thread whose columns disagree (vertical region boundary) evaluates each column with
-// that column's own coefficients.  Accumulation order: bias, then the window in row-major order (as
-// kx_stencil2d.cu).
+// function 0); a key matches a window iff its row part (plus the leading batch axes) and its column part match, so
+// both parts are 32-bit masks over the keys and per output m = row_mask & col_mask,
+// function = m ? func_of_key[31 - clz(m)] : 0.
+// Tiles (a band's rows x a warp's 128 columns) that ONE function covers are classified up front from any / all masks
+// and run the plain stencil loop; only tiles cut by a region boundary select a function per output (see the kernel).
+// Accumulation order: bias, then the window in row-major order (as kx_stencil2d.cu).
 #include <algorithm>
 #include <climits>
 
@@ -46,8 +41,10 @@ struct MeshArgs {
   int hin, win, hout, wout;
   int ly, lx, th;
   int n_funcs, n_keys;
+  int split;                             // 1: warps whose tile ONE function covers take the plain stencil loop
   int ay, ax, ndim;                      // axes of the 2-D window inside the key items
   int64_t lead_shape[KX_MAX_DIMS];       // leading (batch) axes, for keys that constrain them
+  uint32_t umask;                        // tap mask of the function with the most taps (tested as a uniform predicate)
   uint32_t mask[kMaxNF];                 // tap mask per function
   T bias[kMaxNF];
   T coef[kMaxNF][9];
@@ -70,61 +67,92 @@ __device__ __forceinline__ void ld4(const T* p, T (&d)[4]) {
   d[3] = reinterpret_cast<const T&>(raw.w);
 }
 
-// VW = 4: rows 16-byte aligned (SHIFT = (-lx) mod 4); VW = 1: scalar loads (SHIFT = 0)
-// U = rows fetched back to back
+// Classification of a WARP's tile (the band's rows x the warp's 128 columns) by interval arithmetic, lane k <-> key k:
+// returns the function that covers ALL windows of the tile, or -1 when a region boundary cuts it (or might: strided
+// items are treated conservatively -- "matches somewhere" if the interval overlaps, "matches everywhere" never).
+// A key matches a window iff every axis item matches, so with per-key any / all bits over the tile the last-inserted
+// key that matches anywhere decides (select_func scans the keys from the last to the first): it covers the whole tile
+// -> its function; only part of it -> mixed.  ~30 instructions per lane, no shared memory, no barrier.
+template <typename T>
+__device__ __forceinline__ int warp_tile_function(const MeshArgs<T>& a, int lane, int rc0, int rc1, int cc0, int cc1,
+                                                  const int (&lead)[KX_MAX_DIMS]) {
+  bool any = false, all = false;
+  if (lane < a.n_keys) {
+    const MeshKey& k = a.key[lane];
+    any = all = true;
+#pragma unroll 1
+    for (int d = 0; d < a.ndim; ++d) {
+      int c0, c1;                                   // inclusive coordinate range of the tile's window centres on axis d
+      if (d == a.ax) c0 = cc0, c1 = cc1;
+      else if (d == a.ay) c0 = rc0, c1 = rc1;
+      else c0 = c1 = lead[d];
+      const int lo = k.lo[d], hi = k.hi[d], st = k.step[d];
+      if (c0 == c1) {                               // a single coordinate: exact
+        const bool m = (c0 >= lo) && (c0 < hi) && (st == 1 || c0 % st == 0);
+        any = any && m;
+        all = all && m;
+      } else {
+        any = any && (c1 >= lo) && (c0 < hi);
+        all = all && (c0 >= lo) && (c1 < hi) && (st == 1);
+      }
+    }
+  }
+  const uint32_t any_m = __ballot_sync(0xffffffffu, any), all_m = __ballot_sync(0xffffffffu, all);
+  if (any_m == 0u) return 0;                        // no key matches anywhere: function 0 (utils.py:379)
+  const int k = 31 - __clz(any_m);
+  return (all_m >> k) & 1u ? (int)a.key_func[k] : -1;
+}
+
+// ONE launch, every warp on its own (no block barrier, no shared memory), one tile per warp:
+//   * a warp whose tile ONE function covers -- the interior of a PDE mesh, nearly all tiles -- runs the plain stencil
+//     loop of kx_stencil2d.cu (U rows in flight) with that function's coefficients in registers and a warp-uniform tap
+//     mask;
+//   * a warp whose tile is cut by a region boundary (with KX_MESH_NO_UNIFORM=1: every warp) selects the function per
+//     output: row part of every key per row by one ballot (lane k <-> key k), column part per owned column in a 32-bit
+//     mask, function = key_func[31 - clz(row & col)] or 0, coefficients from the parameter bank.  This loop keeps ONE
+//     row in flight and a KY-row queue, so it fits in the registers of the fast loop; it is latency-bound, but its few
+//     warps (~4 % of an 8192^2 mesh: the boundary columns and rows, the rim of a source block) run under the others.
+// Both accumulate bias first, then the window in row-major order.
+// How it got here, 3-function 8192^2 mesh (profiles/r2_mesh_*; the single-function kernel on that grid: 87 us = 0.94 of
+// the roofline): round-1 kernel (block-wide mask prologue worth ~18 % of its instructions, per-thread coefficient
+// caching, 78 registers) 124 us = 0.66; uniform / cut tiles as two launches back to back 112-130 us (the uniform pass
+// alone reaches the single-function kernel's speed, the cut tiles need 28-45 us of pure latency whatever the grid);
+// overlapped through a helper stream 112 us (~10 us per event hop); as programmatic dependent launches 128 us (the
+// dependent cannot start before EVERY block of the first launch has begun); this kernel 106 us = 0.77 (dispatching the
+// column blocks that hold a boundary warp first: 110 us).
+// VW = 4: rows 16-byte aligned (SHIFT = (-lx) mod 4); VW = 1: scalar loads (SHIFT = 0); U = rows fetched back to back
 template <typename T, int KY, int KX, int SHIFT, int VW, int U>
 __global__ void __launch_bounds__(kMT)
 stencil2d_mesh_kernel(const __grid_constant__ MeshArgs<T> a) {
   constexpr int NV = (SHIFT + KX + kMCols - 1 + VW - 1) / VW;
   constexpr int NE = NV * VW;
-  __shared__ uint32_t row_mask[kMaxTH];
-  const int tid = threadIdx.x;
-  const int j0 = (blockIdx.x * kMT + tid) * kMCols;
-  const int r0 = blockIdx.y * a.th, r1 = min(r0 + a.th, a.hout);
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int bx = blockIdx.x, by = blockIdx.y;
+  const int j0 = (bx * kMT + tid) * kMCols;
+  const int jw = (bx * kMT + (tid & ~31)) * kMCols;                   // the warp's first output column
+  if (jw >= a.wout) return;                                           // whole warp outside
+  const int r0 = by * a.th, r1 = min(r0 + a.th, a.hout);
   const T* __restrict__ in = a.in + (int64_t)blockIdx.z * a.in_batch;
   T* __restrict__ out = a.out + (int64_t)blockIdx.z * a.out_batch;
   const int cy = (KY - 1) / 2, cx = (KX - 1) / 2;
 
-  // ---- row part of the keys (and the leading axes), once per block ----
-  if (tid < a.th) {
-    const int rc = (r0 + tid) - a.ly + cy;                  // window-centre row in array coordinates
-    int lead[KX_MAX_DIMS] = {0, 0, 0, 0};
+  int lead[KX_MAX_DIMS] = {0, 0, 0, 0};
+  {
     int64_t b = blockIdx.z;
     for (int d = a.ndim - 3; d >= 0; --d) {
       lead[d] = (int)(b % a.lead_shape[d]);
       b /= a.lead_shape[d];
     }
-    uint32_t m = 0;
-#pragma unroll 1
-    for (int k = 0; k < a.n_keys; ++k) {
-      bool ok = true;
-#pragma unroll 1
-      for (int d = 0; d < a.ndim; ++d) {
-        if (d == a.ax) continue;
-        ok = ok && item_match(a.key[k], d, d == a.ay ? rc : lead[d]);
-      }
-      if (ok) m |= 1u << k;
-    }
-    row_mask[tid] = m;
   }
-  // ---- column part of the keys, once per thread ----
-  uint32_t col_mask[kMCols];
-#pragma unroll
-  for (int i = 0; i < kMCols; ++i) {
-    const int ccol = (j0 + i) - a.lx + cx;
-    uint32_t m = 0;
-#pragma unroll 1
-    for (int k = 0; k < a.n_keys; ++k)
-      if (item_match(a.key[k], a.ax, ccol)) m |= 1u << k;
-    col_mask[i] = m;
-  }
-  __syncthreads();
-  if (j0 >= a.wout) return;
+  int fn = -1;
+  if (a.split)
+    fn = warp_tile_function<T>(a, lane, r0 - a.ly + cy, r1 - 1 - a.ly + cy, jw - a.lx + cx,
+                               min(jw + 32 * kMCols, a.wout) - 1 - a.lx + cx, lead);
   const int xa = j0 - a.lx - SHIFT;
-  const int n_valid = min(kMCols, a.wout - j0);
+  const int n_valid = min(kMCols, a.wout - j0);                       // <= 0 for lanes past the last column
 
   auto load_row = [&](int iy, T(&dst)[NE]) {
-    const bool row_ok = (iy >= 0) && (iy < a.hin);
+    const bool row_ok = (iy >= 0) && (iy < a.hin) && n_valid > 0;
     const T* rp = in + (int64_t)iy * a.win;
     if (VW == 4) {
 #pragma unroll
@@ -143,90 +171,112 @@ stencil2d_mesh_kernel(const __grid_constant__ MeshArgs<T> a) {
       }
     }
   };
+  auto store_row = [&](int r, const T(&acc)[kMCols]) {
+    T* o = out + (int64_t)r * a.wout + j0;
+    const uintptr_t addr = reinterpret_cast<uintptr_t>(o);
+    if (n_valid == 4 && (addr & 15) == 0) {
+      int4 raw;
+      raw.x = reinterpret_cast<const int&>(acc[0]);
+      raw.y = reinterpret_cast<const int&>(acc[1]);
+      raw.z = reinterpret_cast<const int&>(acc[2]);
+      raw.w = reinterpret_cast<const int&>(acc[3]);
+      __stcs(reinterpret_cast<int4*>(o), raw);
+    } else {
+#pragma unroll
+      for (int i = 0; i < kMCols; ++i)
+        if (i < n_valid) o[i] = acc[i];
+    }
+  };
 
-  T q[KY - 1 + U][NE];
+  if (fn >= 0) {
+    // ---- the tile belongs to ONE function ----
+    T q[KY - 1 + U][NE];
 #pragma unroll
-  for (int ky = 0; ky < KY - 1; ++ky) load_row(r0 - a.ly + ky, q[ky]);
-  int f[kMCols] = {0, 0, 0, 0};       // function of each owned column in the current row
-  int cur_f = -1;                     // function whose coefficients sit in cb / cc / cm
-  T cb = T(0), cc[KY * KX];
-  uint32_t cm = 0;
+    for (int ky = 0; ky < KY - 1; ++ky) load_row(r0 - a.ly + ky, q[ky]);
+    const uint32_t um = a.mask[fn];                  // warp-uniform
+    const T cb = a.bias[fn];
+    T cc[KY * KX];
 #pragma unroll
-  for (int t = 0; t < KY * KX; ++t) cc[t] = T(0);
-  uint32_t rm_prev = 0;               // row mask the selection was computed for
-  bool have_sel = false;
-
-  for (int r = r0; r < r1; r += U) {
+    for (int t = 0; t < KY * KX; ++t) cc[t] = a.coef[fn][t];
+    for (int r = r0; r < r1; r += U) {
 #pragma unroll
-    for (int u = 0; u < U; ++u)
-      if (r + u < r1) load_row(r + u - a.ly + KY - 1, q[KY - 1 + u]);
+      for (int u = 0; u < U; ++u)
+        if (r + u < r1) load_row(r + u - a.ly + KY - 1, q[KY - 1 + u]);
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      if (r + u < r1) {
-        const uint32_t rm = row_mask[r + u - r0];
-        if (!have_sel || rm != rm_prev) {   // block-uniform: the selection only changes at a row boundary of some region
-          rm_prev = rm;
-          have_sel = true;
-#pragma unroll
-          for (int i = 0; i < kMCols; ++i) {
-            const uint32_t m = rm & col_mask[i];
-            f[i] = m ? (int)a.key_func[31 - __clz(m)] : 0;
-          }
-        }
-        T acc[kMCols];
-        if (f[0] == f[1] && f[1] == f[2] && f[2] == f[3]) {
-          if (f[0] != cur_f) {   // entering another region: this thread's coefficient registers follow
-            cur_f = f[0];
-            cb = a.bias[cur_f];
-            cm = a.mask[cur_f];
-#pragma unroll
-            for (int t = 0; t < KY * KX; ++t) cc[t] = a.coef[cur_f][t];
-          }
+      for (int u = 0; u < U; ++u) {
+        if (r + u < r1) {
+          T acc[kMCols];
 #pragma unroll
           for (int i = 0; i < kMCols; ++i) acc[i] = cb;
 #pragma unroll
           for (int ky = 0; ky < KY; ++ky)
 #pragma unroll
             for (int kx = 0; kx < KX; ++kx)
-              if (cm & (1u << (ky * KX + kx))) {
+              if (um & (1u << (ky * KX + kx))) {
 #pragma unroll
                 for (int i = 0; i < kMCols; ++i) acc[i] = mad_wrap(cc[ky * KX + kx], q[u + ky][SHIFT + kx + i], acc[i]);
               }
-        } else {
-          // vertical region boundary inside the thread's 4 columns: every column with its own function
-#pragma unroll
-          for (int i = 0; i < kMCols; ++i) {
-            const int fi = f[i];
-            const uint32_t m = a.mask[fi];
-            T v = a.bias[fi];
-#pragma unroll
-            for (int ky = 0; ky < KY; ++ky)
-#pragma unroll
-              for (int kx = 0; kx < KX; ++kx)
-                if (m & (1u << (ky * KX + kx))) v = mad_wrap(a.coef[fi][ky * KX + kx], q[u + ky][SHIFT + kx + i], v);
-            acc[i] = v;
-          }
-        }
-        T* o = out + (int64_t)(r + u) * a.wout + j0;
-        const uintptr_t addr = reinterpret_cast<uintptr_t>(o);
-        if (n_valid == 4 && (addr & 15) == 0) {
-          int4 raw;
-          raw.x = reinterpret_cast<const int&>(acc[0]);
-          raw.y = reinterpret_cast<const int&>(acc[1]);
-          raw.z = reinterpret_cast<const int&>(acc[2]);
-          raw.w = reinterpret_cast<const int&>(acc[3]);
-          __stcs(reinterpret_cast<int4*>(o), raw);
-        } else {
-#pragma unroll
-          for (int i = 0; i < kMCols; ++i)
-            if (i < n_valid) o[i] = acc[i];
+          store_row(r + u, acc);
         }
       }
+#pragma unroll
+      for (int ky = 0; ky < KY - 1; ++ky) {
+#pragma unroll
+        for (int e = 0; e < NE; ++e) q[ky][e] = q[U + ky][e];
+      }
     }
+    return;
+  }
+
+  // ---- a region boundary cuts the tile ----
+  // column part of every key, per owned column; lane k's copy of key k's other axes for the per-row ballot
+  uint32_t col_mask[kMCols];
+#pragma unroll
+  for (int i = 0; i < kMCols; ++i) {
+    const int ccol = (j0 + i) - a.lx + cx;
+    uint32_t m = 0;
+#pragma unroll 1
+    for (int k = 0; k < a.n_keys; ++k)
+      if (item_match(a.key[k], a.ax, ccol)) m |= 1u << k;
+    col_mask[i] = m;
+  }
+  bool lead_ok = lane < a.n_keys;
+  int ylo = 0, yhi = 0, yst = 1;
+  if (lead_ok) {
+    const MeshKey& k = a.key[lane];
+#pragma unroll 1
+    for (int d = 0; d < a.ndim; ++d)
+      if (d != a.ax && d != a.ay) lead_ok = lead_ok && item_match(k, d, lead[d]);
+    if (a.ay >= 0) ylo = k.lo[a.ay], yhi = k.hi[a.ay], yst = k.step[a.ay];
+  }
+  T w[KY][NE];                                       // the window rows of the current output row
+#pragma unroll
+  for (int ky = 0; ky < KY - 1; ++ky) load_row(r0 - a.ly + ky, w[ky]);
+#pragma unroll 1
+  for (int r = r0; r < r1; ++r) {
+    load_row(r - a.ly + KY - 1, w[KY - 1]);
+    const int rc = r - a.ly + cy;
+    const bool rmatch = lead_ok && (a.ay < 0 || ((rc >= ylo) && (rc < yhi) && (yst == 1 || rc % yst == 0)));
+    const uint32_t rm = __ballot_sync(0xffffffffu, rmatch);
+    T acc[kMCols];
+#pragma unroll
+    for (int i = 0; i < kMCols; ++i) {
+      const uint32_t m = rm & col_mask[i];
+      const int fi = m ? (int)a.key_func[31 - __clz(m)] : 0;
+      const uint32_t tm = a.mask[fi];
+      T v = a.bias[fi];
+#pragma unroll
+      for (int ky = 0; ky < KY; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < KX; ++kx)
+          if (tm & (1u << (ky * KX + kx))) v = mad_wrap(a.coef[fi][ky * KX + kx], w[ky][SHIFT + kx + i], v);
+      acc[i] = v;
+    }
+    store_row(r, acc);
 #pragma unroll
     for (int ky = 0; ky < KY - 1; ++ky) {
 #pragma unroll
-      for (int e = 0; e < NE; ++e) q[ky][e] = q[U + ky][e];
+      for (int e = 0; e < NE; ++e) w[ky][e] = w[ky + 1][e];
     }
   }
 }
@@ -279,6 +329,10 @@ int run_mesh(const MapArgs& m, const KxProgram& p, cudaStream_t s) {
   }
   a.n_funcs = p.n_funcs;
   a.n_keys = p.n_keys;
+  // the uniform-predicate path serves the function with the most taps (ties: the first); its mask is `umask`
+  a.umask = a.mask[0];
+  for (int f = 1; f < p.n_funcs; ++f)
+    if (__builtin_popcount(a.mask[f]) > __builtin_popcount(a.umask)) a.umask = a.mask[f];
   for (int k = 0; k < p.n_keys; ++k) {
     a.key_func[k] = (unsigned char)p.key[k].func;
     for (int d = 0; d < KX_MAX_DIMS; ++d) {
@@ -316,14 +370,16 @@ int run_mesh(const MapArgs& m, const KxProgram& p, cudaStream_t s) {
   a.lx = g.lo[ax];
   a.in_batch = (int64_t)a.hin * a.win;
   a.out_batch = (int64_t)a.hout * a.wout;
-  // band height measured on the 3-function 8192^2 mesh (U = 4): 8 rows 484 GLUP/s, 12 531, 16 550, 24 563, 32 566,
-  // 48 529, 64 512, 128 400
-  a.th = a.hout >= 512 ? 32 : (a.hout >= 64 ? 16 : 8);
+  // band height, measured on the 3-function 8192^2 mesh with the per-warp classification (U = 4): 6 rows 0.63 of the
+  // roofline, 8 0.69, 10 0.70, 12 0.72, 14 0.72, 16 0.71, 24 0.67, 32 0.63, 48 0.58 (round 1, block-wide mask
+  // prologue: 32 rows were best)
+  a.th = a.hout >= 64 ? 12 : 8;
   if (const char* e = getenv("KX_MESH_TH")) a.th = atoi(e) > 0 ? atoi(e) : a.th;
   while ((a.hout + a.th - 1) / a.th > 65535) a.th *= 2;
   if (a.th > kMaxTH) return KX_ERR_UNSUPPORTED;
   const bool vec = (a.win % 4 == 0) && ((reinterpret_cast<uintptr_t>(m.in) & 15) == 0) && (a.in_batch % 4 == 0);
   dim3 grid((a.wout + kMT * kMCols - 1) / (kMT * kMCols), (a.hout + a.th - 1) / a.th, (unsigned)batch);
+  a.split = getenv("KX_MESH_NO_UNIFORM") ? 0 : 1;   // 0: every tile on the general loop (cross-check)
   if (KY == 3 && KX == 3) return launch_mesh<T, 3, 3>(a, grid, vec, s);
   if (KY == 1 && KX == 3) return launch_mesh<T, 1, 3>(a, grid, vec, s);
   if (KY == 1 && KX == 1) return launch_mesh<T, 1, 1>(a, grid, vec, s);

@@ -119,3 +119,61 @@ def test_interface_mesh_large_matches_generic_kernel(kex, monkeypatch):
     assert _last_kernel() == "stencil2d_mesh_kernel"
     wb = ko.kernel_map(keys, (3, 40, 64), (1, 3, 3), (1, 1, 1), ((0, 0), (1, 1), (1, 1)), False)(xb.cpu().numpy())
     np.testing.assert_array_equal(gb.cpu().numpy(), wb)
+
+
+@pytest.mark.parametrize("dtype", ["f32", "i32"])
+def test_two_pass_mesh_equals_one_pass_bit_for_bit(kex, dtype, monkeypatch):
+    """stencil2d_mesh_kernel runs the plain stencil loop on tiles ONE function covers and the per-output selection loop on
+    tiles a region boundary cuts.  Same accumulation order in both, so the result must equal the run with every tile on
+    the general loop (KX_MESH_NO_UNIFORM=1) bit for bit -- with rectangular regions, regions narrower than a tile or
+    a thread's 4 columns, and strided keys (every 64th row of tiles mixed)."""
+    from kernex_b200 import _lib
+    n = 8192
+    rng = np.random.default_rng(77)
+    if dtype == "f32":
+        x = torch.from_numpy(rng.standard_normal((n, n)).astype(np.float32)).cuda()
+        src = lambda v: 0.5 * v[0, 0] + 1.0            # noqa: E731
+    else:
+        x = torch.from_numpy(rng.integers(-1000, 1000, (n, n)).astype(np.int32)).cuda()
+        src = lambda v: 3 * v[0, 0] + 1                # noqa: E731
+
+    def mesh(strided):
+        F = kex.kmap(kernel_size=(3, 3), padding="same", relative=True)
+        F[:, :] = lambda v: v[0, 0]
+        F[1:-1, 1:-1] = lambda v: v[1, 0] + v[0, -1] - 4 * v[0, 0] + v[0, 1] + v[-1, 0]
+        F[n // 4: n // 2, n // 4: n // 2] = src
+        F[4000:4003, 100:7000] = lambda v: v[0, 1] - v[0, -1]        # thinner than a band
+        F[6000:6500, 5000:5003] = lambda v: 2 * v[-1, 0]             # thinner than a thread's 4 columns
+        if strided:
+            F[::64, ::2] = lambda v: v[1, 1]                         # cuts every 64th row of tiles
+        return F
+
+    for strided in (False, True):
+        F = mesh(strided)
+        got = F(x)
+        assert _last_kernel() == "stencil2d_mesh_kernel"
+        monkeypatch.setenv("KX_MESH_NO_UNIFORM", "1")
+        want = mesh(strided)(x)
+        monkeypatch.delenv("KX_MESH_NO_UNIFORM")
+        assert torch.equal(got, want)
+        # spot check against the literal oracle on a corner block and on the source-block corner
+        for (r0, c0) in ((0, 0), (n // 4 - 8, n // 4 - 8), (3996, 96), (n - 24, n - 40)):
+            blk = x[max(r0 - 1, 0):r0 + 17, max(c0 - 1, 0):c0 + 33].cpu().numpy()
+            g = got[r0:r0 + 16, c0:c0 + 32].cpu().numpy()
+            xh = np.zeros((18, 34), blk.dtype)
+            xh[(1 if r0 == 0 else 0):(1 if r0 == 0 else 0) + blk.shape[0], (1 if c0 == 0 else 0):(1 if c0 == 0 else 0) + blk.shape[1]] = blk
+            lap = xh[2:, 1:-1] + xh[1:-1, :-2] - 4 * xh[1:-1, 1:-1] + xh[1:-1, 2:] + xh[:-2, 1:-1]
+            rr, cc = np.meshgrid(np.arange(r0, r0 + 16), np.arange(c0, c0 + 32), indexing="ij")
+            interior = (rr >= 1) & (rr < n - 1) & (cc >= 1) & (cc < n - 1)
+            plain = interior & ~((rr >= n // 4) & (rr < n // 2) & (cc >= n // 4) & (cc < n // 2)) \
+                & ~((rr >= 4000) & (rr < 4003) & (cc >= 100) & (cc < 7000)) & ~((rr >= 6000) & (rr < 6500) & (cc >= 5000) & (cc < 5003))
+            if strided:
+                plain &= ~((rr % 64 == 0) & (cc % 2 == 0))
+            if dtype == "i32":
+                np.testing.assert_array_equal(g[plain], lap[plain])
+            else:
+                np.testing.assert_allclose(g[plain], lap[plain], rtol=1e-5, atol=1e-5)
+            edge = ~interior
+            if strided:
+                edge &= ~((rr % 64 == 0) & (cc % 2 == 0))
+            np.testing.assert_array_equal(g[edge], xh[1:-1, 1:-1][edge])
