@@ -40,10 +40,10 @@
 extern "C" {
 #endif
 
-#define KX_ABI_VERSION 1
+#define KX_ABI_VERSION 2
 
 #define KX_MAX_DIMS 4      /* leading batch axes are folded by the host            */
-#define KX_MAX_TAPS 512    /* total taps over all functions of one program        */
+#define KX_MAX_TAPS 1024   /* total taps over all functions of one program (a (64,3,3) conv window has 576) */
 #define KX_MAX_FUNCS 8     /* functions of one F[slice] = fn mesh                 */
 #define KX_MAX_KEYS 32     /* total region keys over all functions                */
 

@@ -13,10 +13,10 @@ import threading
 from .errors import EngineUnavailableError
 
 KX_MAX_DIMS = 4
-KX_MAX_TAPS = 512
+KX_MAX_TAPS = 1024
 KX_MAX_FUNCS = 8
 KX_MAX_KEYS = 32
-KX_ABI_VERSION = 1
+KX_ABI_VERSION = 2
 
 KX_F32, KX_I32 = 0, 1
 KX_AFFINE, KX_REDUCE_MAX, KX_REDUCE_MIN, KX_GATHER = 0, 1, 2, 3

@@ -80,6 +80,8 @@ int dispatch_map(const MapArgs& a, const KxProgram& prog, cudaStream_t s) {
   if (rc != KX_ERR_UNSUPPORTED) return rc;
   rc = try_conv2d(a, prog, s);
   if (rc != KX_ERR_UNSUPPORTED) return rc;
+  rc = try_convc(a, prog, s);
+  if (rc != KX_ERR_UNSUPPORTED) return rc;
   rc = try_stencil3d(a, prog, s);
   if (rc != KX_ERR_UNSUPPORTED) return rc;
   rc = try_patch2d(a, prog, s);
@@ -123,6 +125,70 @@ bool transpose_program(const KxGeom& g, const KxProgram& p, KxGeom& gt, KxProgra
     pt.coef[t] = p.coef[src];
   }
   return true;
+}
+
+// conv-as-kmap over the WHOLE leading axis: window (C, KY, KX) with ksize[0] == in_shape[0] (output depth 1), stride 1,
+// every tap present in row-major (c, ky, kx) order -- tests_and_benchmarks/test_benchmark_conv2d.py, C up to 64
+bool full_depth_conv(const KxGeom& g, const KxProgram& p, int& C, int& NT) {
+  if (g.ndim != 3 || g.in_shape[0] < 2 || g.ksize[0] != g.in_shape[0] || g.lo[0] != 0 || g.hi[0] != 0) return false;
+  for (int d = 0; d < 3; ++d)
+    if (g.stride[d] != 1) return false;
+  C = g.ksize[0];
+  NT = g.ksize[1] * g.ksize[2];
+  const KxFunc& f = p.func[0];
+  if (f.tap_end - f.tap_begin != C * NT || f.post_div != 0.0) return false;
+  for (int t = 0; t < C * NT; ++t) {
+    const int16_t* o = p.tap_off[f.tap_begin + t];
+    if ((o[0] * g.ksize[1] + o[1]) * g.ksize[2] + o[2] != t) return false;
+  }
+  return true;
+}
+
+// dx of a full-depth conv: channel c of dx is the 2-D flipped-tap stencil of the (single-plane) cotangent with the
+// weights of channel c.  Device weights: ONE batched stencil2d launch (batch = C, every item reads the same g, item c
+// takes weights [c*NT, (c+1)*NT) in reversed order).  Host weights: one 2-D launch per channel.
+int vjp_input_full_depth(const KxGeom& g, const KxProgram& p, int C, int NT, const void* gout, const void* coef_dev,
+                         void* dx, cudaStream_t s) {
+  static thread_local KxGeom gt;
+  static thread_local KxProgram pt;
+  memset(&gt, 0, sizeof(gt));
+  gt.ndim = 2;
+  gt.in_dtype = gt.out_dtype = KX_F32;
+  for (int d = 0; d < 2; ++d) {
+    gt.in_shape[d] = g.out_shape[d + 1];
+    gt.out_shape[d] = g.in_shape[d + 1];
+    gt.ksize[d] = g.ksize[d + 1];
+    gt.stride[d] = 1;
+    gt.lo[d] = g.ksize[d + 1] - 1 - g.lo[d + 1];
+    gt.hi[d] = g.ksize[d + 1] - 1 - g.hi[d + 1];
+  }
+  memset(&pt, 0, sizeof(pt));
+  pt.n_funcs = 1;
+  pt.n_taps = NT;
+  pt.func[0].kind = KX_AFFINE;
+  pt.func[0].tap_begin = 0;
+  pt.func[0].tap_end = NT;
+  pt.func[0].coef_is_int = p.func[0].coef_is_int;
+  for (int t = 0; t < NT; ++t) {   // tap t = (ky, kx) row-major reads the flipped offset: table order is REVERSED slot order
+    pt.tap_off[t][0] = (int16_t)(g.ksize[1] - 1 - t / g.ksize[2]);
+    pt.tap_off[t][1] = (int16_t)(g.ksize[2] - 1 - t % g.ksize[2]);
+  }
+  const int first = p.func[0].tap_begin;
+  const int64_t plane_out = gt.out_shape[0] * gt.out_shape[1];
+  if (plane_out <= 0 || gt.in_shape[0] * gt.in_shape[1] <= 0) return KX_ERR_UNSUPPORTED;
+  MapArgs a;
+  if (coef_dev) {
+    fill_map_args(a, gt, pt, gout, (const float*)coef_dev + first, NT, dx, C);
+    a.in_bcast = 1;
+    return try_stencil2d(a, pt, s);   // KX_ERR_UNSUPPORTED: the caller falls back to the generic kernel
+  }
+  for (int c = 0; c < C; ++c) {
+    for (int t = 0; t < NT; ++t) pt.coef[t] = p.coef[first + c * NT + t];
+    fill_map_args(a, gt, pt, gout, nullptr, 0, (float*)dx + (int64_t)c * plane_out, 1);
+    const int rc = dispatch_map(a, pt, s);
+    if (rc) return rc;
+  }
+  return KX_OK;
 }
 
 }  // namespace
@@ -210,6 +276,13 @@ int kx_map_vjp_input(const KxGeom* geom, const KxProgram* prog, const void* g, c
     return fail(KX_ERR_UNSUPPORTED, "VJP is implemented for single-function float32 AFFINE programs");
   if (!g || !dx) return fail(KX_ERR_INVALID, "null device pointer");
   DeviceGuard guard(dx);
+  {
+    int C = 0, NT = 0;
+    if (full_depth_conv(*geom, *prog, C, NT) && C > 4) {   // C <= 4: the conv row ring takes the transposed program
+      rc = vjp_input_full_depth(*geom, *prog, C, NT, g, coef_dev, dx, (cudaStream_t)stream);
+      if (rc != KX_ERR_UNSUPPORTED) return rc;
+    }
+  }
   static thread_local KxGeom gt;
   static thread_local KxProgram pt;
   const int first = prog->func[0].tap_begin;
@@ -224,7 +297,21 @@ int kx_map_vjp_input(const KxGeom* geom, const KxProgram* prog, const void* g, c
 
 int64_t kx_vjp_coef_scratch_bytes(const KxGeom* geom, const KxProgram* prog) {
   if (!geom || !prog) return 0;
-  const int64_t a = generic_vjp_coef_scratch_bytes(*geom, *prog), b = conv_wgrad_scratch_bytes(*geom, *prog);
+  int64_t a = generic_vjp_coef_scratch_bytes(*geom, *prog), b = conv_wgrad_scratch_bytes(*geom, *prog);
+  int C = 0, NT = 0;
+  if (prog->n_funcs == 1 && full_depth_conv(*geom, *prog, C, NT) && C > 4 && NT == 9) {   // groups of 4 channels, one at a time
+    KxGeom gs = *geom;
+    gs.in_shape[0] = gs.ksize[0] = 4;
+    static thread_local KxProgram ps;
+    memset(&ps, 0, sizeof(ps));
+    ps.n_funcs = 1;
+    ps.n_taps = 36;
+    ps.func[0] = prog->func[0];
+    ps.func[0].tap_begin = 0;
+    ps.func[0].tap_end = 36;
+    const int64_t c = conv_wgrad_scratch_bytes(gs, ps);
+    b = c > b ? c : b;
+  }
   return a > b ? a : b;
 }
 
@@ -238,6 +325,38 @@ int kx_map_vjp_coef(const KxGeom* geom, const KxProgram* prog, const void* x, co
   DeviceGuard guard(dcoef);
   rc = try_conv_wgrad(*geom, *prog, x, g, scratch, dcoef, (cudaStream_t)stream);
   if (rc != KX_ERR_UNSUPPORTED) return rc;
+  {
+    // full-depth conv with more than 4 channels: the fused window-correlation kernel per group of <= 4 channels
+    // (the cotangent plane is re-read once per group: (4 C + C) / (4 C + 4) of the ideal traffic)
+    int C = 0, NT = 0;
+    if (full_depth_conv(*geom, *prog, C, NT) && C > 4 && NT == 9) {
+      static thread_local KxGeom gs;
+      static thread_local KxProgram ps;
+      const int first = prog->func[0].tap_begin;
+      const int64_t plane = geom->in_shape[1] * geom->in_shape[2];
+      (void)first;
+      for (int c0 = 0; c0 < C; c0 += 4) {
+        const int cn = C - c0 < 4 ? C - c0 : 4;
+        gs = *geom;
+        gs.in_shape[0] = gs.ksize[0] = cn;
+        memset(&ps, 0, sizeof(ps));
+        ps.n_funcs = 1;
+        ps.n_taps = cn * 9;
+        ps.func[0] = prog->func[0];
+        ps.func[0].tap_begin = 0;
+        ps.func[0].tap_end = cn * 9;
+        for (int t = 0; t < cn * 9; ++t) {
+          ps.tap_off[t][0] = (int16_t)(t / 9);
+          ps.tap_off[t][1] = prog->tap_off[first + c0 * 9 + t][1];
+          ps.tap_off[t][2] = prog->tap_off[first + c0 * 9 + t][2];
+        }
+        rc = try_conv_wgrad(gs, ps, (const float*)x + (int64_t)c0 * plane, g, scratch, (float*)dcoef + c0 * 9,
+                            (cudaStream_t)stream);
+        if (rc) break;
+      }
+      if (rc != KX_ERR_UNSUPPORTED) return rc;
+    }
+  }
   return launch_generic_vjp_coef(*geom, *prog, x, g, scratch, dcoef, (cudaStream_t)stream);
 }
 

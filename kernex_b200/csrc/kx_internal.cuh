@@ -94,6 +94,7 @@ struct MapArgs {
   int64_t out_pitch[KX_MAX_DIMS];  // element pitch of the window index along each axis
   int64_t out_base;
   int32_t fn_elems;            // 1, or n_taps for KX_GATHER
+  int32_t in_bcast;            // 1: all batch items read the same input array (stencil2d only; others must decline)
   // offset maps (smap) fused into one pass: windows whose centre lies outside [box_lo, box_hi) copy the
   // centre input element instead of evaluating the function ('same'-style geometry only)
   int32_t use_box;
@@ -120,6 +121,7 @@ int try_stencil3d_star(const MapArgs& a, const KxProgram& prog, int64_t batch, c
 int try_patch(const MapArgs& a, const KxProgram& prog, cudaStream_t s);
 int try_patch2d(const MapArgs& a, const KxProgram& prog, cudaStream_t s);
 int try_conv2d(const MapArgs& a, const KxProgram& prog, cudaStream_t s);
+int try_convc(const MapArgs& a, const KxProgram& prog, cudaStream_t s);
 int try_conv_dense3d(const MapArgs& a, const KxProgram& prog, int64_t batch, cudaStream_t s);
 int try_stencil3d_dense(const MapArgs& a, const KxProgram& prog, int64_t batch, cudaStream_t s);
 int try_pool2d(const MapArgs& a, const KxProgram& prog, cudaStream_t s);

@@ -41,7 +41,7 @@ int run(const MapArgs& m, const KxProgram& p, int ay, int ax, int64_t batch, cud
   a.wout = (int)g.out_shape[ax];
   a.ly = ay >= 0 ? g.lo[ay] : 0;
   a.lx = g.lo[ax];
-  a.in_batch = (int64_t)a.hin * a.win;
+  a.in_batch = m.in_bcast ? 0 : (int64_t)a.hin * a.win;   // in_bcast: every batch item reads the SAME input
   a.out_batch = (int64_t)a.hout * a.wout;
   a.bias = (T)f.bias;
   if (m.use_box) {
@@ -61,7 +61,7 @@ int run(const MapArgs& m, const KxProgram& p, int ay, int ax, int64_t batch, cud
   for (int i = 0; i < kMaxK * kMaxK; ++i) dense[i] = T(0);
   // device tables are indexed by tap slot; the kernel wants a dense KY*KX table: only
   // usable directly when the program lists every window element in row-major order
-  bool dense_order = (f.tap_end - f.tap_begin) == KY * KX;
+  bool dense_order = (f.tap_end - f.tap_begin) == KY * KX, rev_order = dense_order;
   bool seen[kMaxK * kMaxK] = {false};
   int n_seen = 0;
   for (int t = f.tap_begin; t < f.tap_end; ++t) {
@@ -74,10 +74,12 @@ int run(const MapArgs& m, const KxProgram& p, int ay, int ax, int64_t batch, cud
     else if (slot < 64) a.mask_hi |= 1u << (slot - 32);
     dense[slot] = (T)p.coef[t];
     if (slot != t - f.tap_begin) dense_order = false;
+    if (slot != KY * KX - 1 - (t - f.tap_begin)) rev_order = false;   // a transposed program: flipped taps, same table
   }
   const bool full = n_seen == KY * KX;
   if (dev) {
-    if (!dense_order) return KX_ERR_UNSUPPORTED;
+    if (!dense_order && !rev_order) return KX_ERR_UNSUPPORTED;
+    a.coef_rev = dense_order ? 0 : 1;
     a.coef_dev = (const T*)m.coef_dev;
     a.coef_batch = m.coef_batch_stride;
   }

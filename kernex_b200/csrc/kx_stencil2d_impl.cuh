@@ -36,7 +36,8 @@ template <typename T>
 struct S2Args {
   const T* in;
   T* out;
-  const T* coef_dev;           // optional [KY*KX] device table (dense, row-major)
+  const T* coef_dev;           // optional [KY*KX] device table (dense, row-major; coef_rev: in REVERSED order)
+  int coef_rev;
   int64_t in_batch, out_batch, coef_batch;
   int hin, win, hout, wout;
   int ly, lx;                  // left borders
@@ -132,7 +133,7 @@ stencil2d_kernel(const __grid_constant__ S2Args<T> a) {
   } else if (a.coef_dev) {
     const T* cd = a.coef_dev + (int64_t)blockIdx.z * a.coef_batch;
 #pragma unroll
-    for (int i = 0; i < KY * KX; ++i) coef[i] = cd[i];
+    for (int i = 0; i < KY * KX; ++i) coef[i] = cd[a.coef_rev ? KY * KX - 1 - i : i];   // reversed: a transposed program
   } else {
 #pragma unroll
     for (int i = 0; i < KY * KX; ++i) coef[i] = a.coef[i];
