@@ -391,6 +391,48 @@ def _captured_signature(v, depth):
     return _arg_signature(v)
 
 
+class _CapturePlan:
+    """What a function can capture, resolved once per function object: its closure cells, the global names its code
+    (and nested code objects) reads that are not modules / types / builtins, its defaults.  Evaluating the fingerprint
+    is then a walk over these few references -- or nothing at all for a plain lambda."""
+
+    __slots__ = ("code_id", "cells", "glb", "names", "fn", "trivial")
+
+    def __init__(self, f):
+        import types
+        fn = getattr(f, "__func__", f)
+        code = getattr(fn, "__code__", None)
+        if code is None:
+            fn = getattr(f, "__wrapped__", None) or getattr(type(f), "__call__", None)
+            code = getattr(fn, "__code__", None)
+            if code is None:
+                raise TypeError("callable without code object")
+        self.fn, self.code_id = fn, id(code)
+        self.cells = tuple(zip(code.co_freevars, fn.__closure__ or ()))
+        self.glb = fn.__globals__
+        names = set(code.co_names)
+        for const in code.co_consts:      # nested lambdas / comprehensions read globals too
+            if hasattr(const, "co_names"):
+                names.update(const.co_names)
+        skip = (types.ModuleType, type, types.BuiltinFunctionType, np.ufunc)
+        self.names = tuple(n for n in sorted(names) if n in self.glb and not isinstance(self.glb[n], skip))
+        self.trivial = not self.cells and not self.names
+
+
+_CAPTURE_PLANS: "dict[int, tuple]" = {}
+
+
+def _capture_plan(f):
+    ent = _CAPTURE_PLANS.get(id(f))
+    if ent is not None and ent[0] is f:
+        return ent[1]
+    plan = _CapturePlan(f)
+    if len(_CAPTURE_PLANS) > 4096:
+        _CAPTURE_PLANS.clear()
+    _CAPTURE_PLANS[id(f)] = (f, plan)   # keeps f alive: the id stays unique
+    return plan
+
+
 def _func_fingerprint(f, depth=0):
     """The tracer bakes the values a window function reads from its closure and globals (dt, alpha, host weight
     tables) into the coefficients, while the un-jitted reference re-evaluates the function on every call
@@ -399,31 +441,24 @@ def _func_fingerprint(f, depth=0):
     fingerprint cannot describe (large arrays, device tensors, arbitrary objects) raises -> the call is not cached."""
     if depth > 3:
         raise TypeError("captured functions nest too deeply")
-    fn = getattr(f, "__func__", f)
-    code = getattr(fn, "__code__", None)
-    if code is None:
-        fn = getattr(f, "__wrapped__", None) or getattr(type(f), "__call__", None)
-        code = getattr(fn, "__code__", None)
-        if code is None:
-            raise TypeError("callable without code object")
-    parts = [("code", id(code))]
-    for name, cell in zip(code.co_freevars, fn.__closure__ or ()):
+    plan = _capture_plan(f)
+    fn = plan.fn
+    if plan.trivial and not fn.__defaults__ and not fn.__kwdefaults__:
+        return plan.code_id
+    parts = [plan.code_id]
+    for name, cell in plan.cells:
         try:
             val = cell.cell_contents
         except ValueError:            # empty cell
             continue
         parts.append((name, _captured_signature(val, depth)))
-    glb = fn.__globals__
-    names = set(code.co_names)
-    for const in code.co_consts:      # nested lambdas / comprehensions read globals too
-        if hasattr(const, "co_names"):
-            names.update(const.co_names)
-    for name in sorted(names):
+    glb = plan.glb
+    for name in plan.names:
         if name in glb:
             parts.append((name, _captured_signature(glb[name], depth)))
-    if getattr(fn, "__defaults__", None):
+    if fn.__defaults__:
         parts.append(("defaults", tuple(_captured_signature(v, depth) for v in fn.__defaults__)))
-    if getattr(fn, "__kwdefaults__", None):
+    if fn.__kwdefaults__:
         parts.append(("kwdefaults", tuple((n, _captured_signature(v, depth)) for n, v in sorted(fn.__kwdefaults__.items()))))
     return tuple(parts)
 
@@ -433,22 +468,35 @@ def clear_plan_cache():
     _PLAN_CACHE.clear()
 
 
-def _plan_key(tag, func_map, shape, kernel_size, strides, border, relative, in_kx, a=(), k=None):
+def _static_key(tag, func_map, shape, kernel_size, strides, border, relative):
+    """The part of a plan key that cannot change between two calls of one engine closure."""
     try:
-        keys = repr([v for v in func_map.values()])
-        sig = tuple(_arg_signature(v) for v in a) + tuple((n, _arg_signature(v)) for n, v in sorted((k or {}).items()))
+        return (tag, tuple(id(f) for f in func_map), repr([v for v in func_map.values()]), shape, kernel_size, strides,
+                border, bool(relative))
+    except Exception:
+        return None
+
+
+def _plan_key(tag, func_map, shape, kernel_size, strides, border, relative, in_kx, a=(), k=None, static=None):
+    if static is None:
+        static = _static_key(tag, func_map, shape, kernel_size, strides, border, relative)
+        if static is None:
+            return None
+    try:
+        sig = tuple(_arg_signature(v) for v in a) if a else ()
+        if k:
+            sig += tuple((n, _arg_signature(v)) for n, v in sorted(k.items()))
         captured = tuple(_func_fingerprint(f) for f in func_map)
     except Exception:
         return None
-    return (tag, tuple(id(f) for f in func_map), keys, shape, kernel_size, strides, border, bool(relative), in_kx,
-            sig, captured)
+    return (static, in_kx, sig, captured)
 
 
-def _map_plan(func_map, shape, kernel_size, strides, border, relative, in_kx, a, k):
+def _map_plan(func_map, shape, kernel_size, strides, border, relative, in_kx, a, k, static=None):
     """Trace + classify + build the KxGeom / KxProgram.  Plans of argument-free window
     functions are cached on the function objects' identity (the reference re-traces under
     ``jit`` at most once per shape too), so steady-state calls cost one ctypes launch."""
-    key = _plan_key("map", func_map, shape, kernel_size, strides, border, relative, in_kx, a, k)
+    key = _plan_key("map", func_map, shape, kernel_size, strides, border, relative, in_kx, a, k, static)
     if key is not None and key in _PLAN_CACHE:
         specs, _stale_args, out_kx, prog, geom, full_shape = _PLAN_CACHE[key][1]
         # device tensors are looked up afresh: the cached plan only remembers their positions
@@ -475,12 +523,12 @@ def _map_plan(func_map, shape, kernel_size, strides, border, relative, in_kx, a,
     return plan
 
 
-def _run_map(func_map, shape, kernel_size, strides, border, relative, array, a, k):
+def _run_map(func_map, shape, kernel_size, strides, border, relative, array, a, k, static=None):
     arr = _Arr(array)
     if tuple(arr.t.shape) != tuple(shape):
         raise ValueError(f"array shape {tuple(arr.t.shape)} != declared shape {tuple(shape)}")
     specs, device_args, out_kx, prog, geom, full_shape = _map_plan(
-        func_map, shape, kernel_size, strides, border, relative, arr.kx_dtype, a, k)
+        func_map, shape, kernel_size, strides, border, relative, arr.kx_dtype, a, k, static)
     comp_dtype = _KX2TORCH[out_kx]
     coef = prog.coef_tensor(device_args, comp_dtype, arr.t.device)
     needs_grad = torch.is_grad_enabled() and (arr.t.requires_grad or (coef is not None and coef.requires_grad))
@@ -587,9 +635,10 @@ def kernel_map(func_map: dict, shape, kernel_size, strides, border, relative: bo
         piped = _try_host_pipeline(func_map, shape, kernel_size, strides, border, relative, array, a, k)
         if piped is not None:
             return piped
-        arr, out = _run_map(func_map, shape, kernel_size, strides, border, relative, array, a, k)
+        arr, out = _run_map(func_map, shape, kernel_size, strides, border, relative, array, a, k, static)
         return arr.give_back(out)
 
+    static = _static_key("map", func_map, shape, kernel_size, strides, border, relative)
     return call
 
 
