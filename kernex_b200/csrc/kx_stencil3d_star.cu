@@ -22,6 +22,9 @@
 //   + zc 64                                                           765-770     = 0.935-0.94 of the measured copy peak
 //   4 x 512 tiles 727-763, a 4-stage ring 666-705, 4 blocks / SM at 64 registers 625, one barrier per two planes 617,
 //   cp.async L2::128B / L2::256B prefetch hints: no change.  Without the groups zc 64 gives 749.
+//   Per-stage mbarriers instead of wait_group + __syncthreads (cp.async.mbarrier.arrive.noinc for "landed", one
+//   arrive per thread for "read"; a warp then waits for data only): 767 vs 770-774 on the same box -- the per-plane
+//   block barrier shows up in the stall samples but is not what limits the kernel; removed again.
 // KX_STAR_WX=1|2|4, KX_STAR_ZC=n, KX_STAR_NO_GROUPS=1 and KX_STAR_GRID3D=1 select the other variants (bit-identical
 // results; cross-checks and A/B timing).
 #include "kx_internal.cuh"
