@@ -187,6 +187,18 @@ stencil2d_kernel(const __grid_constant__ S2Args<T> a) {
     for (int i = 0; i < kCols; ++i) {
       T v;
       if constexpr (OP == kSep) {
+        if constexpr (std::is_same<T, float>::value) {
+          if (i & 1) continue;      // outputs (i, i + 1) are folded together below
+          float v0 = a.coef[kMaxK] * row[SHIFT + i], v1 = a.coef[kMaxK] * row[SHIFT + i + 1];
+#pragma unroll
+          for (int kx = 1; kx < KX; ++kx) {
+            const float wx = a.coef[kMaxK + kx];
+            ffma2(v0, v1, wx, wx, row[SHIFT + kx + i], row[SHIFT + kx + i + 1]);
+          }
+          dst[i] = v0;
+          dst[i + 1] = v1;
+          continue;
+        }
         v = a.coef[kMaxK] * row[SHIFT + i];
 #pragma unroll
         for (int kx = 1; kx < KX; ++kx) v = mad_wrap(a.coef[kMaxK + kx], row[SHIFT + kx + i], v);
@@ -244,6 +256,18 @@ stencil2d_kernel(const __grid_constant__ S2Args<T> a) {
             }
           }
         } else {
+          if constexpr (OP == kSep && std::is_same<T, float>::value) {
+            // vertical fold as packed FFMA2: two output columns per instruction, the weight is a broadcast scalar
+            // (same rounding as the scalar chain; the wide windows are issue-bound: 74 % issue-active at 15x15)
+#pragma unroll
+            for (int i = 0; i < kCols; ++i) acc[i] = a.bias;
+#pragma unroll
+            for (int ky = 0; ky < KY; ++ky) {
+              const float wy = a.coef[ky];
+              ffma2(acc[0], acc[1], wy, wy, q[u + ky][0], q[u + ky][1]);
+              ffma2(acc[2], acc[3], wy, wy, q[u + ky][2], q[u + ky][3]);
+            }
+          } else
 #pragma unroll
           for (int i = 0; i < kCols; ++i) {
             if constexpr (OP == kSep) {
