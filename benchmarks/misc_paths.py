@@ -70,7 +70,7 @@ if want("fir"):
         f = kex.kmap(kernel_size=(k,), padding="same")(fn)
         y = f(x)
         med, _ = timeit(lambda: f(x), 4)
-        rep(f"{name} on a 1-D array of 2^27 fp32" + (" (KX_FOLD_1D)" if os.environ.get("KX_FOLD_1D") else ""),
+        rep(f"{name} on a 1-D array of 2^27 fp32" + (" (one-row launch, KX_NO_FOLD_1D)" if os.environ.get("KX_NO_FOLD_1D") else ""),
             x.numel() * 8, med, y.numel())
     del x, y
     torch.cuda.empty_cache()
@@ -141,13 +141,12 @@ if want("dense3d"):
     y = f(x)
     med, _ = timeit(lambda: f(x), 4)
     rep("dense 27-point 3-D stencil (host weights) 'same' on 1024^3", x.numel() * 8, med, y.numel())
-    if os.environ.get("KX_TEST_EXPERIMENTAL"):   # opt-in plane-stationary kernel, same problem
-        os.environ["KX_DENSE3D_PLANES"] = "1"
-        y2 = f(x)
-        med, _ = timeit(lambda: f(x), 4)
-        rep("dense 27-point 3-D stencil, plane-stationary kernel (opt-in), 1024^3", x.numel() * 8, med, y2.numel())
-        print(json.dumps({"max_abs_diff_vs_default": float((y2 - y).abs().max())}), flush=True)
-        del os.environ["KX_DENSE3D_PLANES"], y2
+    os.environ["KX_NO_DENSE3D_PLANES"] = "1"      # the conv row ring with the three z planes as channels (device-weight path)
+    y2 = f(x)
+    med, _ = timeit(lambda: f(x), 4)
+    rep("dense 27-point 3-D stencil on the conv row ring (KX_NO_DENSE3D_PLANES), 1024^3", x.numel() * 8, med, y2.numel())
+    print(json.dumps({"max_abs_diff_vs_default": float((y2 - y).abs().max())}), flush=True)
+    del os.environ["KX_NO_DENSE3D_PLANES"], y2
     xb = torch.randn((256, 2048, 2048), device=dev, generator=g)
     yb = f(xb)
     med, _ = timeit(lambda: f(xb), 4)
