@@ -43,7 +43,7 @@ struct PoolArgs {
   int ly, lx, th;
   float post_div;
   T bias;
-  T coef[9];
+  T coef[16];
 };
 
 // A warp covers kWarpOut<SX> output columns: 256 for stride 1 (8 per lane, two groups of 4 consecutive
@@ -307,8 +307,12 @@ int launch_pool_geom(PoolArgs<T>& a, dim3 grid, int ky, int kx, int sy, int sx, 
   KX_POOL_CASE(2, 2, 2, 2)
   KX_POOL_CASE(3, 3, 2, 2)
   KX_POOL_CASE(3, 3, 3, 3)
+  KX_POOL_CASE(4, 4, 4, 4)
+  KX_POOL_CASE(4, 4, 2, 2)
   KX_POOL_CASE(1, 2, 1, 2)
   KX_POOL_CASE(1, 3, 1, 2)
+  KX_POOL_CASE(1, 3, 1, 3)
+  KX_POOL_CASE(1, 4, 1, 4)
   if (OP != kOpAffine) {  // stride-1 AFFINE windows are kx_stencil2d.cu's job
     KX_POOL_CASE(3, 3, 1, 1)
     KX_POOL_CASE(2, 2, 1, 1)
@@ -333,7 +337,7 @@ int run_pool(const MapArgs& m, const KxProgram& p, cudaStream_t s) {
     lead *= g.in_shape[d];
   }
   const int64_t batch = m.batch * lead;
-  if (batch > 65535 || ky * kx > 9) return KX_ERR_UNSUPPORTED;
+  if (batch > 65535 || ky * kx > 16) return KX_ERR_UNSUPPORTED;
   if (f.tap_end - f.tap_begin != ky * kx) return KX_ERR_UNSUPPORTED;          // dense windows only
   if (m.coef_dev) return KX_ERR_UNSUPPORTED;
   PoolArgs<T> a;

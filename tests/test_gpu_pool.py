@@ -29,7 +29,8 @@ def _last_kernel():
 
 
 GEOMS = [((2, 2), (2, 2)), ((3, 3), (2, 2)), ((3, 3), (3, 3)), ((3, 3), (1, 1)), ((2, 2), (1, 1)),
-         ((1, 3), (1, 2)), ((1, 2), (1, 2)), ((1, 3), (1, 1))]
+         ((1, 3), (1, 2)), ((1, 2), (1, 2)), ((1, 3), (1, 1)), ((4, 4), (4, 4)), ((4, 4), (2, 2)), ((1, 3), (1, 3)),
+         ((1, 4), (1, 4))]
 FNS = {"max": lambda v: np.max(v), "min": lambda v: np.min(v), "mean": lambda v: np.mean(v),
        "sum": lambda v: np.sum(v)}
 
