@@ -125,6 +125,17 @@ int try_convc(const MapArgs& a, const KxProgram& prog, cudaStream_t s);
 int try_conv_dense3d(const MapArgs& a, const KxProgram& prog, int64_t batch, cudaStream_t s);
 int try_stencil3d_dense(const MapArgs& a, const KxProgram& prog, int64_t batch, cudaStream_t s);
 int try_pool2d(const MapArgs& a, const KxProgram& prog, cudaStream_t s);
+// wide separable windows (kx_sep2d.cu), requested by kx_stencil2d.cu once it has factored the coefficient table
+struct Sep2dReq {
+  const float* in;
+  float* out;
+  int64_t in_batch, out_batch, batch;
+  int hin, win, hout, wout, ly, lx;
+  int KY, KX, th;
+  float bias, post_mul;
+  float cy[15], cx[15];
+};
+int try_sep2d(const Sep2dReq& req, cudaStream_t s);
 int try_pool3d(const MapArgs& a, const KxProgram& prog, cudaStream_t s);
 int64_t conv_wgrad_scratch_bytes(const KxGeom& g, const KxProgram& prog);
 int try_conv_wgrad(const KxGeom& g, const KxProgram& prog, const void* x, const void* gout, void* scratch,

@@ -123,6 +123,25 @@ int run(const MapArgs& m, const KxProgram& p, int ay, int ax, int64_t batch, cud
   }
   if (op == kAffine && !s2_has_affine(KY, KX)) return KX_ERR_UNSUPPORTED;   // dense form: windows up to 7x7, 1 x 15
   a.post_mul = f.post_div != 0.0 ? (float)(1.0 / f.post_div) : 0.f;
+  if constexpr (std::is_same<T, float>::value) {
+    if (op == kSep && vw == 4) {   // square odd windows >= 7x7: the TMA row-ring kernel (kx_sep2d.cu)
+      Sep2dReq r;
+      memset(&r, 0, sizeof(r));
+      r.in = a.in;
+      r.out = a.out;
+      r.in_batch = a.in_batch;
+      r.out_batch = a.out_batch;
+      r.batch = batch;
+      r.hin = a.hin, r.win = a.win, r.hout = a.hout, r.wout = a.wout, r.ly = a.ly, r.lx = a.lx;
+      r.KY = KY, r.KX = KX;
+      r.bias = a.bias;
+      r.post_mul = a.post_mul;
+      for (int ky = 0; ky < KY && ky < 15; ++ky) r.cy[ky] = a.coef[ky];
+      for (int kx = 0; kx < KX && kx < 15; ++kx) r.cx[kx] = a.coef[kMaxK + kx];
+      const int rc = try_sep2d(r, s);
+      if (rc != KX_ERR_UNSUPPORTED) return rc;
+    }
+  }
   return launch_t<T>(a, KY, KX, op, (int)batch, vw, s);
 }
 

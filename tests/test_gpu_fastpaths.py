@@ -140,7 +140,7 @@ def _gauss(ky, kx, rng):
 
 @pytest.mark.parametrize("ksize", [(4, 4), (5, 5), (3, 5), (5, 3), (7, 7), (9, 9), (11, 11), (13, 13), (15, 15)])
 @pytest.mark.parametrize("kind", ["gauss", "signed", "mean", "max", "sum-i32"])
-def test_stencil2d_separable_windows_up_to_15x15(kex, ksize, kind):
+def test_stencil2d_separable_windows_up_to_15x15(kex, ksize, kind, monkeypatch):
     """README.md:277-294 Gaussian blur (w = outer(g, g) / sum, any kernel size) and other outer-product tables run as
     KY + KX FMAs per output; box sums / means and max / min as row-then-column folds; vs the dense oracle."""
     ky, kx = ksize
@@ -169,8 +169,16 @@ def test_stencil2d_separable_windows_up_to_15x15(kex, ksize, kind):
         if kind == "signed":   # derivative-of-Gaussian style: sign changes in one factor (zero entries would be
             wt = np.outer(wt[:, kx // 2], np.linspace(-1, 1.37, kx)).astype(np.float32)   # dropped by the tracer)
         got = kex.kernel_map({(lambda v: np.sum(v * wt)): ()}, (h, w_), ksize, (1, 1), border, False)(x)
-        assert _last_kernel() == "stencil2d_kernel"
+        # square odd windows >= 7x7 over 16-byte aligned rows take the TMA row-ring kernel (kx_sep2d.cu)
+        ring = ky == kx and ky >= 7 and ky % 2 == 1 and w_ % 4 == 0
+        assert _last_kernel() == ("sep2d_kernel" if ring else "stencil2d_kernel")
         _check_affine(got, x, ksize, (1, 1), border, taps, [float(wt[t]) for t in taps])
+        if ring:   # ... and must agree bit for bit with stencil2d_kernel's separable path (same accumulation order)
+            monkeypatch.setenv("KX_NO_SEP2D", "1")
+            got2 = kex.kernel_map({(lambda v: np.sum(v * wt)): ()}, (h, w_), ksize, (1, 1), border, False)(x)
+            monkeypatch.delenv("KX_NO_SEP2D")
+            assert _last_kernel() == "stencil2d_kernel"
+            np.testing.assert_array_equal(got, got2)
 
 
 def test_stencil2d_dense_tables_are_not_mistaken_for_outer_products(kex):
@@ -565,3 +573,33 @@ def test_vector_valued_1d_functions_do_not_take_the_fold(kex):
     want = torch.stack([torch.cat([torch.zeros(1, dtype=torch.int32, device="cuda"), x[:-1]]), x,
                         torch.cat([x[1:], torch.zeros(1, dtype=torch.int32, device="cuda")])], dim=1)
     assert torch.equal(p, want)
+
+
+@pytest.mark.parametrize("k", [7, 9, 11, 13, 15])
+def test_sep2d_row_ring_geometry(kex, k, monkeypatch):
+    """kx_sep2d.cu on the shapes that stress its ring: several bands (zero-filled stages above / below the array), several
+    warps and column blocks with a ragged last block, every window misalignment (left x border 0..3), a bias, a batch axis,
+    the README Gaussian with a mean-style final division -- against the oracle and bit for bit against stencil2d_kernel."""
+    rng = np.random.default_rng(9700 + k)
+    g1 = np.exp(-0.5 * np.linspace(-(k - 1) / 2, (k - 1) / 2, k) ** 2 / 2.0)
+    wt = np.outer(g1, g1)
+    wt = (wt / wt.sum()).astype(np.float32)
+    taps = list(itertools.product(range(k), range(k)))
+    for (h, w_), border in [((300, 644), ((k // 2, k // 2), (0, k - 1))), ((70, 1028), ((0, 0), (1, 2))),
+                            ((1100, 516), ((k - 1, 0), (2, k // 2))), ((40, 260), ((3, 3), (3, 3)))]:
+        x = rng.standard_normal((h, w_)).astype(np.float32)
+        fn = lambda v: np.sum(v * wt) + 0.25      # noqa: E731
+        got = kex.kernel_map({fn: ()}, (h, w_), (k, k), (1, 1), border, False)(x)
+        assert _last_kernel() == "sep2d_kernel"
+        _check_affine(got, x, (k, k), (1, 1), border, taps, [float(wt[t]) for t in taps], 0.25)
+        monkeypatch.setenv("KX_NO_SEP2D", "1")
+        got2 = kex.kernel_map({(lambda v: np.sum(v * wt) + 0.25): ()}, (h, w_), (k, k), (1, 1), border, False)(x)
+        monkeypatch.delenv("KX_NO_SEP2D")
+        np.testing.assert_array_equal(got, got2)
+    xb = rng.standard_normal((3, 50, 132)).astype(np.float32)
+    f = kex.vmap(kex.kmap(kernel_size=(k, k), padding="same")(lambda v: np.sum(v * wt)))
+    gotb = f(torch.from_numpy(xb).cuda()).cpu().numpy()
+    assert _last_kernel() == "sep2d_kernel"
+    b = ko.resolve_padding("same", (k, k))
+    for c in range(3):
+        _check_affine(gotb[c], xb[c], (k, k), (1, 1), b, taps, [float(wt[t]) for t in taps])
