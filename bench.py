@@ -416,7 +416,10 @@ def run_config_suite(world, rank, dev, clocks, peak, budget_s=60.0):
         par = all_ok(within(dx[8000:8064].cpu().numpy(), want, scale))
         ms, win = timed(lambda: slab.vjp(g), 20)
         emit("C2 backward on axis-0 slabs (VJP wrt x, transposed halo exchange)", total(N * N), 8, ms, win, par,
-             kernel="stencil2d_kernel", halo_transport="nccl (cotangent halo rows are sent back and added)")
+             kernel="stencil2d_kernel",
+             halo_transport=("p2p pull-add (the cotangent rows that landed in a neighbour's halo are pulled over NVLink and "
+                             "added by one kernel)" if slab.__dict__.get("_gpeers") is not None else
+                             "nccl (cotangent halo rows are sent back and added)"))
         slab.close()
         del slab, o, g, dx
         torch.cuda.empty_cache()

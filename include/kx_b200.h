@@ -222,7 +222,8 @@ typedef struct KxHaloSide {
 
 typedef struct KxHaloPull {
   int32_t n_sides;       /* 0..2 neighbours                                                                  */
-  int32_t reserved;
+  int32_t accumulate;    /* 0: dst = src (halo exchange); 1: dst += src as fp32 (its adjoint: cotangent rows that landed in
+                            the neighbour's halo are added to my edge rows)                                  */
   uint64_t epoch;        /* strictly increasing per step, the same sequence on every rank                    */
   uint32_t* counter;     /* local scratch word, zero between launches                                        */
   KxHaloSide side[2];

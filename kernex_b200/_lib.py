@@ -83,7 +83,7 @@ class KxHaloSide(C.Structure):
 
 
 class KxHaloPull(C.Structure):
-    _fields_ = [("n_sides", C.c_int32), ("reserved", C.c_int32), ("epoch", C.c_uint64), ("counter", C.c_void_p),
+    _fields_ = [("n_sides", C.c_int32), ("accumulate", C.c_int32), ("epoch", C.c_uint64), ("counter", C.c_void_p),
                 ("side", KxHaloSide * 2)]
 
 

@@ -9,7 +9,8 @@
 //
 //   1. store `epoch` into the neighbours' READY flags        (my own rows are final: stream order + system fence)
 //   2. spin until the neighbours have stored `epoch` into mine (ld.acquire.sys on local memory, written over NVLink)
-//   3. pull the neighbours' edge rows into my halo rows        (16-byte ld.relaxed.sys over NVLink -> local stores)
+//   3. pull the neighbours' edge rows into my halo rows        (16-byte ld.relaxed.sys over NVLink -> local stores;
+//      `accumulate`: ADD them to my rows instead -- the adjoint of the exchange, for the sharded VJP)
 //   4. the last block stores `epoch` into the neighbours' DONE flags (they may overwrite those rows again)
 //
 // No host thread of another rank is involved and nothing but this kernel sits between "own rows final" and the two
@@ -80,7 +81,16 @@ __global__ void __launch_bounds__(kPullThreads) halo_pull_kernel(const __grid_co
         if (i + u * kPullThreads < n16) v[u] = ld_peer16(src + i + u * kPullThreads);
 #pragma unroll
       for (int u = 0; u < 4; ++u)
-        if (i + u * kPullThreads < n16) dst[i + u * kPullThreads] = v[u];
+        if (i + u * kPullThreads < n16) {
+          if (p.accumulate) {   // adjoint exchange: the pulled cotangent rows are ADDED to my edge rows (fp32)
+            const uint4 o = dst[i + u * kPullThreads];
+            v[u].x = __float_as_uint(__uint_as_float(o.x) + __uint_as_float(v[u].x));
+            v[u].y = __float_as_uint(__uint_as_float(o.y) + __uint_as_float(v[u].y));
+            v[u].z = __float_as_uint(__uint_as_float(o.z) + __uint_as_float(v[u].z));
+            v[u].w = __float_as_uint(__uint_as_float(o.w) + __uint_as_float(v[u].w));
+          }
+          dst[i + u * kPullThreads] = v[u];
+        }
     }
   }
   __syncthreads();

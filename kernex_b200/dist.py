@@ -256,12 +256,20 @@ class SlabStencil:
         elif why:
             raise ValueError(f"p2p transport: {why}")
         self._peers = grp
-        F = _lib.KX_PEER_FLAG_BYTES
-        self.ext = grp.tensor(F, (L.ext_rows,) + tuple(trailing))
-        pull = _lib.KxHaloPull()
-        pull.n_sides, pull.epoch = 0, 0
-        pull.counter = grp.local_ptr + peer.COUNTER_BYTE
+        self._C, self._klib, self._row_bytes = C, _lib, row_bytes
+        self.ext = grp.tensor(_lib.KX_PEER_FLAG_BYTES, (L.ext_rows,) + tuple(trailing))
         plan = {pr: (mine, theirs) for mine, pr, theirs in halo_pull_plan(self.rank, self.world, rows, k0, (L.lo, L.hi))}
+        self._pull, self._done_flags = self._build_pull(grp, plan, row_bytes)
+
+    def _build_pull(self, grp, plan, row_bytes, accumulate=False):
+        """``KxHaloPull`` for ``plan`` = {neighbour rank: (my ext rows, their ext rows)}; both neighbours that exist get a
+        side (READY / DONE flags are exchanged with both even when nothing is pulled from one of them)."""
+        from . import peer
+        _lib = self._klib
+        F = _lib.KX_PEER_FLAG_BYTES
+        pull = _lib.KxHaloPull()
+        pull.n_sides, pull.epoch, pull.accumulate = 0, 0, 1 if accumulate else 0
+        pull.counter = grp.local_ptr + peer.COUNTER_BYTE
         for nb, my_ready, their_ready, their_done in ((self.rank - 1, peer.READY_FROM_UP, peer.READY_FROM_DOWN, peer.DONE_FROM_DOWN),
                                                       (self.rank + 1, peer.READY_FROM_DOWN, peer.READY_FROM_UP, peer.DONE_FROM_UP)):
             if not (0 <= nb < self.world):
@@ -275,10 +283,29 @@ class SlabStencil:
             sd.my_ready = grp.flag_ptr(self.rank, my_ready)
             sd.peer_done = grp.flag_ptr(nb, their_done)
             pull.n_sides += 1
-        self._pull, self._C, self._klib = pull, C, _lib
-        self._done_flags = [grp.flag_ptr(self.rank, s) for nb, s in ((self.rank - 1, peer.DONE_FROM_UP),
-                                                                     (self.rank + 1, peer.DONE_FROM_DOWN))
-                            if 0 <= nb < self.world]
+        done = [grp.flag_ptr(self.rank, sl) for nb, sl in ((self.rank - 1, peer.DONE_FROM_UP), (self.rank + 1, peer.DONE_FROM_DOWN))
+                if 0 <= nb < self.world]
+        return pull, done
+
+    def _init_grad_peers(self, grad_peers=None):
+        """Second peer-mapped buffer, for the cotangent of ``ext`` (collective: every rank makes its first ``vjp`` call
+        together).  The adjoint of the halo exchange is a pull-ADD: the cotangent rows that landed in a neighbour's halo
+        are pulled over NVLink and added to my edge rows by the same kernel (``accumulate``)."""
+        from . import peer
+        L = self.layout
+        grp = grad_peers if grad_peers is not None else peer.PeerGroup.create(self._peers.nbytes, self.device, self.group)
+        self._gpeers, self._gepoch = grp, 0
+        self._dext = grp.tensor(self._klib.KX_PEER_FLAG_BYTES, tuple(self.ext.shape))
+        plan = {}
+        if not L.first and L.send_up:       # rank-1's bottom halo rows hold the cotangents of my first send_up rows
+            up = SlabLayout(self.rank - 1, self.world, L.rows, L.k0, (L.lo, L.hi))
+            b = up.halo_top + L.rows
+            plan[self.rank - 1] = (slice(L.halo_top, L.halo_top + L.send_up), slice(b, b + up.halo_bot))
+        if not L.last and L.send_down:      # rank+1's top halo rows hold the cotangents of my last send_down rows
+            dn = SlabLayout(self.rank + 1, self.world, L.rows, L.k0, (L.lo, L.hi))
+            e = L.halo_top + L.rows
+            plan[self.rank + 1] = (slice(e - L.send_down, e), slice(0, dn.halo_top))
+        self._gpull, self._gdone = self._build_pull(grp, plan, self._row_bytes, accumulate=True)
 
     def _pull_halos(self, stream):
         """One launch on ``stream``: READY -> wait -> pull over NVLink -> DONE (kx_peer.cu)."""
@@ -295,6 +322,9 @@ class SlabStencil:
                 self._klib.check(lib.kx_flag_wait(self._C.c_void_p(f), self._C.c_uint64(self._epoch), s))
 
     def close(self):
+        if self.__dict__.get("_gpeers") is not None:
+            self._gpeers.close()
+            self._gpeers = None
         if self._peers is not None:
             self._peers.close()
             self._peers = None
@@ -420,7 +450,7 @@ class SlabStencil:
         main.synchronize()
         return y_host
 
-    def vjp(self, g_local: torch.Tensor, want_input=True, want_coef=False):
+    def vjp(self, g_local: torch.Tensor, want_input=True, want_coef=False, grad_peers=None):
         """Adjoint of :meth:`step`: ``g_local`` is the cotangent of this rank's output rows.
 
         * input: every piece's flipped-tap stencil of its cotangent rows is accumulated into an
@@ -438,9 +468,16 @@ class SlabStencil:
             # ONE persistent buffer (like self.out; the returned rows are valid until the next call): a fresh 1 GB
             # tensor per call is handed to NCCL's stream by the exchange, so the caching allocator could not reuse the
             # previous one and fell back to cudaMalloc every call (1.84 ms instead of 0.40 ms per call at C2 size)
+            if self._peers is not None and self.__dict__.get("_gpeers") is None and (grad_peers is not None or dist.is_initialized()):
+                self._init_grad_peers(grad_peers)
+            gp2p = self.__dict__.get("_gpeers") is not None
             dext = self.__dict__.get("_dext")
             if dext is None or dext.shape != self.ext.shape:
                 dext = self._dext = torch.empty(self.ext.shape, dtype=torch.float32, device=self.device)
+            if gp2p and self._gepoch:      # the neighbours must have pulled the halo rows of my previous cotangent
+                st = self._C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+                for f in self._gdone:
+                    self._klib.check(self._klib.load().kx_flag_wait(self._C.c_void_p(f), self._C.c_uint64(self._gepoch), st))
             if L.halo_top:
                 dext[:L.halo_top].zero_()
             if L.halo_bot:
@@ -460,7 +497,13 @@ class SlabStencil:
                     continue
                 dext[p.in0:p.in1] += pm.vjp_input(gp)             # O(halo)-row strips
             if self.world > 1:
-                exchange_halo_grads(dext, L, self.group)
+                if gp2p:               # transposed halo exchange as ONE pull-add kernel over NVLink
+                    self._gepoch += 1
+                    self._gpull.epoch = self._gepoch
+                    st = self._C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+                    self._klib.check(self._klib.load().kx_halo_pull(self._C.byref(self._gpull), st))
+                else:
+                    exchange_halo_grads(dext, L, self.group)
             dx_own = dext[L.own]
         if want_coef:
             for p, pm in self.maps:
