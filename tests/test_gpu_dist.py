@@ -126,3 +126,48 @@ def test_peer_halo_pull_with_emulated_ranks_on_one_gpu(kex, world, fn, ksize, ro
         assert got.shape == want.shape and torch.equal(got, want), trial
     for g in groups:
         g.close()
+
+
+@pytest.mark.parametrize("world,padding", [(2, "valid"), (3, "same")])
+def test_peer_pull_add_vjp_with_emulated_ranks_on_one_gpu(kex, world, padding):
+    """The adjoint of the halo exchange on a 1-GPU box: every emulated rank accumulates the flipped-tap stencils of its
+    cotangent rows into a peer-mapped ext-shaped buffer, then ONE pull kernel in `accumulate` mode adds the rows that
+    landed in the neighbours' halos to its edge rows.  Two rounds (the second waits for the neighbours' DONE flags before
+    the buffer is rewritten); against autograd of the single-launch kmap on the whole array at the 1e-5 bound."""
+    from kernex_b200 import _lib, peer
+    from kernex_b200.dist import SlabStencil
+    from vjp_ref import assert_within, dx_reference
+    dev = torch.device("cuda", 0)
+    rows, width, ksize = 40, 132, (3, 3)
+    nbytes = _lib.KX_PEER_FLAG_BYTES + (rows + 2) * width * 4
+    groups, ggroups = peer.PeerGroup.local(world, nbytes, dev), peer.PeerGroup.local(world, nbytes, dev)
+    mains = [torch.cuda.Stream(device=dev) for _ in range(world)]
+    slabs = [SlabStencil(lap, kernel_size=ksize, relative=True, rows_per_rank=rows, width=width, device=dev, padding=padding,
+                         transport="p2p", rank=r, world=world, peers=groups[r]) for r in range(world)]
+    gen = torch.Generator(device=dev).manual_seed(9)
+    border = ko.resolve_padding(padding, ksize)
+    taps, coefs = [(2, 1), (1, 0), (1, 1), (1, 2), (0, 1)], [1.0, 1.0, -4.0, 1.0, 1.0]
+    for trial in range(2):
+        glob = torch.randn((world * rows, width), device=dev, generator=gen)
+        outs = []
+        torch.cuda.synchronize()
+        for r, s in enumerate(slabs):
+            with torch.cuda.stream(mains[r]):
+                s.set_local(glob[r * rows:(r + 1) * rows])
+                outs.append(s.step())
+        torch.cuda.synchronize()
+        g_glob = torch.randn((sum(o.shape[0] for o in outs),) + tuple(outs[0].shape[1:]), device=dev, generator=gen)
+        dxs, o0 = [], 0
+        torch.cuda.synchronize()
+        for r, s in enumerate(slabs):
+            with torch.cuda.stream(mains[r]):
+                dx, _ = s.vjp(g_glob[o0:o0 + outs[r].shape[0]], grad_peers=ggroups[r])
+                dxs.append(dx)
+            o0 += outs[r].shape[0]
+        torch.cuda.synchronize()
+        assert _lib.last_kernel() == "halo_pull_kernel"
+        got = torch.cat(dxs, dim=0).cpu().numpy()
+        want, mag = dx_reference(g_glob.cpu().numpy(), (world * rows, width), ksize, (1, 1), border, taps, coefs)
+        assert_within(got, want, mag, f"sharded dx, trial {trial}")
+    for g in groups + ggroups:
+        g.close()
