@@ -46,14 +46,16 @@ def test_ctypes_signatures_cover_the_header(lib):
 def test_struct_layouts_match_the_c_compiler(tmp_path):
     from kernex_b200 import _lib
     prog = tmp_path / "sz.c"
-    prog.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "kx_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu\\n",'
+    prog.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "kx_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n",'
                     'sizeof(KxGeom),sizeof(KxKeyItem),sizeof(KxKey),sizeof(KxFunc),sizeof(KxProgram),'
-                    'offsetof(KxProgram,tap_off),offsetof(KxProgram,coef));return 0;}\n')
+                    'offsetof(KxProgram,tap_off),offsetof(KxProgram,coef),sizeof(KxHaloSide),sizeof(KxHaloPull),'
+                    'offsetof(KxHaloPull,counter),offsetof(KxHaloPull,side));return 0;}\n')
     exe = tmp_path / "sz"
     subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(prog), "-o", str(exe)], check=True)
     out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
     want = [C.sizeof(_lib.KxGeom), C.sizeof(_lib.KxKeyItem), C.sizeof(_lib.KxKey), C.sizeof(_lib.KxFunc),
-            C.sizeof(_lib.KxProgram), _lib.KxProgram.tap_off.offset, _lib.KxProgram.coef.offset]
+            C.sizeof(_lib.KxProgram), _lib.KxProgram.tap_off.offset, _lib.KxProgram.coef.offset,
+            C.sizeof(_lib.KxHaloSide), C.sizeof(_lib.KxHaloPull), _lib.KxHaloPull.counter.offset, _lib.KxHaloPull.side.offset]
     assert [int(v) for v in out] == want
 
 
