@@ -6,9 +6,9 @@
 //
 // The channel axis is the MARCHING axis of a 2.5-D blocking (the geometry of kx_stencil3d_star.cu): a block (8 warps)
 // owns an 8-row x 256-column tile of the single output plane and walks through the C input planes; every plane tile
-// (10 rows x 264 columns) is fetched once with 16-byte cp.async.cg (zero-fill = the reference's zero padding) into a
-// 3-stage shared-memory ring two planes ahead of the math; a thread (4 columns x 2 rows) reads its 4 rows x 6 columns
-// of the plane once and accumulates the plane's 9 taps into its 8 outputs, which stay in registers until the last
+// (10 rows x 264 columns) is fetched once -- one TMA bulk copy per row segment, clipped to the row; the ring starts out
+// as zeros, which is the reference's zero padding -- into a 3-stage (small grids: 6-stage) shared-memory ring ahead of
+// the math; a thread (4 columns x 2 rows) reads its 4 rows x 6 columns of the plane once and accumulates the plane's 9 taps into its 8 outputs, which stay in registers until the last
 // plane: 4 B read per input element + 4 B written per output, (C * 4 + 4) bytes per lattice update.  fp32 uses packed
 // FFMA2 (two outputs per instruction, the weight is a broadcast scalar).  The C * 9 weights (host table or device
 // array) are staged in shared memory once per block and read back as broadcasts, 9 per plane.
@@ -16,6 +16,7 @@
 #include <type_traits>
 
 #include "kx_internal.cuh"
+#include "kx_tma.cuh"
 
 namespace kx {
 
@@ -24,7 +25,6 @@ namespace {
 constexpr int kCWX = 2, kCWarps = 8, kCRY = 2;
 constexpr int kCX = 128 * kCWX, kCY = kCWarps / kCWX * kCRY;   // tile 8 x 256
 constexpr int kCThreads = 32 * kCWarps;
-constexpr int kCStages = 3;
 constexpr int kCMaxC = KX_MAX_TAPS / 9;
 
 template <typename T>
@@ -42,14 +42,12 @@ struct ConvCArgs {
   uint32_t mask[kCMaxC];    // 9 bits per channel
 };
 
-__device__ __forceinline__ void c_cp_async16(unsigned smem_addr, const void* gmem, int src_bytes) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_addr), "l"(gmem), "r"(src_bytes)
-               : "memory");
-}
-__device__ __forceinline__ void c_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void c_cp_wait() {
-  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+template <int I, int N, typename F>
+__device__ __forceinline__ void c_static_for(F&& f) {
+  if constexpr (I < N) {
+    f(std::integral_constant<int, I>{});
+    c_static_for<I + 1, N>(f);
+  }
 }
 
 template <typename T>
@@ -61,16 +59,16 @@ __device__ __forceinline__ void c_lds4(const T* p, T (&d)[4]) {
   d[3] = reinterpret_cast<const T&>(raw.w);
 }
 
-template <typename T, int SHIFT, bool FULL>
+template <typename T, int SHIFT, bool FULL, int kCStages>
 __global__ void __launch_bounds__(kCThreads)
 convc_kernel(const __grid_constant__ ConvCArgs<T> a) {
   constexpr int NV = (SHIFT + 6 + 3) / 4;          // aligned 4-vectors covering the 6 needed columns
   constexpr int SW = kCX + 4 * NV;                  // tile width (columns), multiple of 4
   constexpr int SR = kCY + 2;
-  constexpr int CH = SW / 4;
-  constexpr int NCH = (SR * CH + kCThreads - 1) / kCThreads;   // 16-byte chunks per thread per plane
-  __shared__ __align__(16) T smem[kCStages * SR * SW];
-  __shared__ T wsm[kCMaxC * 9];
+  extern __shared__ __align__(128) unsigned char dyn_smem[];   // the ring: kCStages * SR * SW elements (dynamic: 6 stages exceed 48 KB)
+  T* smem = reinterpret_cast<T*>(dyn_smem);
+  __shared__ __align__(16) T wsm[kCMaxC * 12];       // 9 weights per plane, padded to 12: three LDS.128 per plane
+  __shared__ __align__(8) uint64_t bars[kCStages];
 
   const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * 32 + tx;
   const int b = blockIdx.x / a.ntiles;
@@ -82,42 +80,44 @@ convc_kernel(const __grid_constant__ ConvCArgs<T> a) {
   const int nplanes = a.C;
   const int64_t plane_elems = (int64_t)a.hin * a.win;
 
-  // weights -> shared memory (read back as broadcasts)
-  for (int i = tid; i < a.C * 9; i += kCThreads) wsm[i] = a.coef_dev ? a.coef_dev[i] : a.coef[i];
-
-  int src_off[NCH];        // element offset inside a plane, or -1 = outside the array (zero fill)
-  unsigned dst_off[NCH];   // byte offset inside a stage
-  {
-    const int gx0 = x0 - a.lx - SHIFT;             // global column of tile column 0 (multiple of 4)
-    const int gy0 = y0 - a.ly;
-#pragma unroll
-    for (int k = 0; k < NCH; ++k) {
-      const int i = tid + k * kCThreads;
-      const int r = i / CH, c = (i - r * CH) * 4;
-      const int gy = gy0 + r, gx = gx0 + c;
-      const bool ok = (i < SR * CH) && (gy >= 0) && (gy < a.hin) && (gx >= 0) && (gx + 3 < a.win);
-      src_off[k] = ok ? gy * a.win + gx : -1;
-      dst_off[k] = (i < SR * CH) ? (unsigned)((r * SW + c) * sizeof(T)) : 0xffffffffu;
-    }
+  // weights -> shared memory (read back as broadcasts); the ring starts out as zeros: rows above / below the array and
+  // the columns clipped off the row copies are the same in every plane, so they are never written again = zero padding
+  for (int i = tid; i < a.C * 12; i += kCThreads) {
+    const int c = i / 12, t = i - c * 12;
+    wsm[i] = t < 9 ? (a.coef_dev ? a.coef_dev[c * 9 + t] : a.coef[c * 9 + t]) : T(0);
   }
   const unsigned smem_base = (unsigned)__cvta_generic_to_shared(smem);
+  for (int i = tid; i < kCStages * SR * SW / 4; i += kCThreads) sts_zero16(smem_base + (unsigned)(i * 16));
+  const unsigned bar0 = (unsigned)__cvta_generic_to_shared(bars);
+  if (tid < kCStages) mbar_init(bar0 + tid * 8, 1);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  fence_proxy_async();
+  __syncthreads();
 
-  auto issue = [&](int pl) {
-    const T* src = in + (int64_t)pl * plane_elems;
-    const unsigned dst = smem_base + (unsigned)((pl % kCStages) * SR * SW * sizeof(T));
-#pragma unroll
-    for (int k = 0; k < NCH; ++k) {
-      if (dst_off[k] != 0xffffffffu) {
-        const bool ok = src_off[k] >= 0;
-        c_cp_async16(dst + dst_off[k], ok ? (const void*)(src + src_off[k]) : (const void*)in, ok ? 16 : 0);
-      }
+  // A plane tile = SR row segments of SW columns, each ONE TMA bulk copy (clipped to the row) issued by thread 0 and
+  // completing on the stage's mbarrier: no LDGSTS (ptxas pads every LDGSTS with three dummy LDS; ncu of the cp.async
+  // version: l1tex at 88 % of its peak, MIO throttle the top stall), no per-thread chunk bookkeeping.
+  const int gx0 = x0 - a.lx - SHIFT;               // global column of tile column 0 (multiple of 4)
+  const int gy0 = y0 - a.ly;
+  const int c_lo = max(gx0, 0), c_hi = min(gx0 + SW, a.win);
+  const unsigned row_bytes = c_hi > c_lo ? (unsigned)((c_hi - c_lo) * 4) : 0u;
+  const int r_lo = max(0, -gy0), r_hi = min(SR, a.hin - gy0);      // tile rows inside the array
+  const unsigned dst_col = (unsigned)((c_lo - gx0) * 4);
+  auto issue = [&](int pl) {                        // thread 0 only
+    const unsigned bar = bar0 + (unsigned)((pl % kCStages) * 8);
+    const unsigned st = smem_base + (unsigned)((pl % kCStages) * SR * SW * 4);
+    if (row_bytes == 0 || r_hi <= r_lo) {
+      mbar_arrive(bar);
+      return;
     }
+    mbar_expect_tx(bar, row_bytes * (unsigned)(r_hi - r_lo));
+    const T* src = in + (int64_t)pl * plane_elems + (int64_t)(gy0 + r_lo) * a.win + c_lo;
+    for (int r = r_lo; r < r_hi; ++r, src += a.win) bulk_g2s(st + (unsigned)(r * SW * 4) + dst_col, src, row_bytes, bar);
   };
-
+  if (tid == 0) {
 #pragma unroll
-  for (int s = 0; s < kCStages - 1; ++s) {
-    if (s < nplanes) issue(s);
-    c_cp_commit();
+    for (int s_ = 0; s_ < kCStages - 1; ++s_)
+      if (s_ < nplanes) issue(s_);
   }
 
   const int jx = 4 * tx + 128 * (ty % kCWX);   // thread's first output column inside the tile
@@ -134,10 +134,9 @@ convc_kernel(const __grid_constant__ ConvCArgs<T> a) {
 
   auto step = [&](auto phase, int pl) {
     constexpr int PH = decltype(phase)::value;       // pl % kCStages, compile time
-    c_cp_wait<kCStages - 2>();
-    __syncthreads();            // plane pl landed for all threads (and, first trip, the weights); the stage read last step is free
-    if (pl + kCStages - 1 < nplanes) issue(pl + kCStages - 1);
-    c_cp_commit();
+    __syncthreads();            // everybody is done reading the stage that is refilled now
+    if (tid == 0 && pl + kCStages - 1 < nplanes) issue(pl + kCStages - 1);
+    mbar_wait(bar0 + PH * 8, (unsigned)((pl / kCStages) & 1));      // plane pl has landed
     // rows iy .. iy+RY+1 of the plane tile: the 6 window columns SHIFT+jx .. SHIFT+jx+5 of each
     T P[kCRY + 2][6];
     {
@@ -156,9 +155,14 @@ convc_kernel(const __grid_constant__ ConvCArgs<T> a) {
         for (int e = 0; e < 6; ++e) P[r][e] = w[SHIFT + e];
       }
     }
-    T wk[9];
+    T wk[12];
 #pragma unroll
-    for (int t = 0; t < 9; ++t) wk[t] = wsm[pl * 9 + t];
+    for (int q = 0; q < 3; ++q) {
+      T d[4];
+      c_lds4(wsm + pl * 12 + 4 * q, d);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) wk[4 * q + e] = d[e];
+    }
     const uint32_t m = FULL ? 0x1ffu : a.mask[pl];
 #pragma unroll
     for (int r = 0; r < kCRY; ++r) {
@@ -182,13 +186,11 @@ convc_kernel(const __grid_constant__ ConvCArgs<T> a) {
   };
   int pl = 0;
 #pragma unroll 1
-  for (; pl + 2 < nplanes; pl += 3) {   // unrolled by the ring depth: stage addresses are compile-time
-    step(std::integral_constant<int, 0>{}, pl);
-    step(std::integral_constant<int, 1>{}, pl + 1);
-    step(std::integral_constant<int, 2>{}, pl + 2);
-  }
-  if (pl < nplanes) step(std::integral_constant<int, 0>{}, pl);
-  if (pl + 1 < nplanes) step(std::integral_constant<int, 1>{}, pl + 1);
+  for (; pl + kCStages <= nplanes; pl += kCStages)   // unrolled by the ring depth: stage addresses are compile-time
+    c_static_for<0, kCStages>([&](auto ph) { step(ph, pl + decltype(ph)::value); });
+  c_static_for<0, kCStages>([&](auto ph) {
+    if (pl + decltype(ph)::value < nplanes) step(ph, pl + decltype(ph)::value);
+  });
 
 #pragma unroll
   for (int r = 0; r < kCRY; ++r) {
@@ -252,9 +254,24 @@ int run_convc(const MapArgs& m, const KxProgram& p, int64_t batch, cudaStream_t 
   if (nblocks > 0x7fffffffll || nblocks < 1) return KX_ERR_UNSUPPORTED;
   dim3 grid((unsigned)nblocks), block(32, kCWarps);
   const int shift = (((-a.lx) % 4) + 4) % 4;
-#define KX_CONVC(S)                                                   \
-  if (a.full) convc_kernel<T, S, true><<<grid, block, 0, s>>>(a);     \
-  else convc_kernel<T, S, false><<<grid, block, 0, s>>>(a);
+  // ring depth: 3 stages (5 blocks / SM); 6 stages (3 blocks / SM) only when the whole grid is resident anyway -- there
+  // a block's C-plane march is one dependent chain of DRAM round trips and depth is all that hides it (measured,
+  // benchmarks/convc_probe.py: 4-10 % at <= 512^2, but 1.6x SLOWER at 1024^2 where it costs a second wave)
+  int stages = nblocks <= (int64_t)sm_count() * 3 ? 6 : 3;
+  if (const char* e = getenv("KX_CONVC_STAGES")) stages = atoi(e) == 6 ? 6 : 3;   // tuning knob
+  const int sw = kCX + 4 * ((shift + 6 + 3) / 4);
+  const size_t ring = (size_t)stages * (kCY + 2) * sw * sizeof(T);
+#define KX_CONVC2(S, FULLV, ST)                                                                                  \
+  {                                                                                                              \
+    auto kern = convc_kernel<T, S, FULLV, ST>;                                                                   \
+    if (ring > 48 * 1024) KX_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring)); \
+    kern<<<grid, block, ring, s>>>(a);                                                                           \
+  }
+#define KX_CONVC(S)                                                    \
+  if (a.full && stages == 6) KX_CONVC2(S, true, 6)                      \
+  else if (a.full) KX_CONVC2(S, true, 3)                               \
+  else if (stages == 6) KX_CONVC2(S, false, 6)                          \
+  else KX_CONVC2(S, false, 3)
   switch (shift) {
     case 0: KX_CONVC(0) break;
     case 1: KX_CONVC(1) break;
@@ -262,6 +279,7 @@ int run_convc(const MapArgs& m, const KxProgram& p, int64_t batch, cudaStream_t 
     default: KX_CONVC(3) break;
   }
 #undef KX_CONVC
+#undef KX_CONVC2
   return after_launch("convc_kernel");
 }
 
