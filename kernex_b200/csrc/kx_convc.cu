@@ -8,8 +8,8 @@
 // owns an 8-row x 256-column tile of the single output plane and walks through the C input planes; every plane tile
 // (10 rows x 264 columns) is fetched once -- one TMA bulk copy per row segment, clipped to the row; the ring starts out
 // as zeros, which is the reference's zero padding -- into a 3-stage (small grids: 6-stage) shared-memory ring ahead of
-// the math; a thread (4 columns x 2 rows) reads its 4 rows x 6 columns of the plane once and accumulates the plane's 9 taps into its 8 outputs, which stay in registers until the last
-// plane: 4 B read per input element + 4 B written per output, (C * 4 + 4) bytes per lattice update.  fp32 uses packed
+// the math; a thread (4 columns x 2 rows) reads its 4 rows x 6 columns of the plane once and accumulates the plane's
+// 9 taps into its 8 outputs, which stay in registers until the last plane: 4 B read per input element + 4 B written per output, (C * 4 + 4) bytes per lattice update.  fp32 uses packed
 // FFMA2 (two outputs per instruction, the weight is a broadcast scalar).  The C * 9 weights (host table or device
 // array) are staged in shared memory once per block and read back as broadcasts, 9 per plane.
 // Accumulation order of one output: bias, then the window in row-major (c, ky, kx) order.

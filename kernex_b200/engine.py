@@ -357,6 +357,7 @@ class _AffineMapFn(torch.autograd.Function):
 
 _PLAN_CACHE: "dict[tuple, tuple]" = {}
 _PLAN_CACHE_MAX = 128
+_PLAN_GEN = [0]
 
 
 def _arg_signature(v):
@@ -466,6 +467,7 @@ def _func_fingerprint(f, depth=0):
 def clear_plan_cache():
     """Drop every cached trace (public: ``kernex_b200.clear_plan_cache()``)."""
     _PLAN_CACHE.clear()
+    _PLAN_GEN[0] += 1       # steady-state launchers of earlier generations retire themselves
 
 
 def _static_key(tag, func_map, shape, kernel_size, strides, border, relative):
@@ -492,6 +494,21 @@ def _plan_key(tag, func_map, shape, kernel_size, strides, border, relative, in_k
     return (static, in_kx, sig, captured)
 
 
+def _fresh_device_args(a, k):
+    """Device tensors are looked up afresh on a cache hit: the cached plan only remembers their positions."""
+    fresh = {i: v for i, v in enumerate(a) if isinstance(v, torch.Tensor) and (v.is_cuda or v.requires_grad)}
+    fresh.update({("kw", n): v for n, v in (k or {}).items()
+                  if isinstance(v, torch.Tensor) and (v.is_cuda or v.requires_grad)})
+    return fresh
+
+
+def _cache_plan(key, func_map, plan):
+    if key is not None:
+        if len(_PLAN_CACHE) >= _PLAN_CACHE_MAX:
+            _PLAN_CACHE.pop(next(iter(_PLAN_CACHE)))
+        _PLAN_CACHE[key] = (tuple(func_map), plan)  # keep the functions alive: ids stay unique
+
+
 def _map_plan(func_map, shape, kernel_size, strides, border, relative, in_kx, a, k, static=None):
     """Trace + classify + build the KxGeom / KxProgram.  Plans of argument-free window
     functions are cached on the function objects' identity (the reference re-traces under
@@ -499,11 +516,7 @@ def _map_plan(func_map, shape, kernel_size, strides, border, relative, in_kx, a,
     key = _plan_key("map", func_map, shape, kernel_size, strides, border, relative, in_kx, a, k, static)
     if key is not None and key in _PLAN_CACHE:
         specs, _stale_args, out_kx, prog, geom, full_shape = _PLAN_CACHE[key][1]
-        # device tensors are looked up afresh: the cached plan only remembers their positions
-        fresh = {i: v for i, v in enumerate(a) if isinstance(v, torch.Tensor) and (v.is_cuda or v.requires_grad)}
-        fresh.update({("kw", n): v for n, v in (k or {}).items()
-                      if isinstance(v, torch.Tensor) and (v.is_cuda or v.requires_grad)})
-        return specs, fresh, out_kx, prog, geom, full_shape
+        return specs, _fresh_device_args(a, k), out_kx, prog, geom, full_shape
     specs, device_args = _trace_all(func_map, kernel_size, relative, a, k)
     groups = [tuple(v) for v in func_map.values()]
     out_shape = calculate_output_shape(shape, kernel_size, strides, border)
@@ -516,14 +529,62 @@ def _map_plan(func_map, shape, kernel_size, strides, border, relative, in_kx, a,
     geom = _geom(shape, out_shape, kernel_size, strides, border, in_kx, out_kx)
     full_shape = out_shape + (gather[0].out_shape if gather else ())
     plan = (specs, device_args, out_kx, prog, geom, full_shape)
-    if key is not None:
-        if len(_PLAN_CACHE) >= _PLAN_CACHE_MAX:
-            _PLAN_CACHE.pop(next(iter(_PLAN_CACHE)))
-        _PLAN_CACHE[key] = (tuple(func_map), plan)  # keep the functions alive: ids stay unique
+    _cache_plan(key, func_map, plan)
     return plan
 
 
-def _run_map(func_map, shape, kernel_size, strides, border, relative, array, a, k, static=None):
+class _FastMap:
+    """Steady-state launcher of one engine closure for device-resident inputs: everything the general path derives
+    per call (plan key, program, geometry, output shape) is fixed once that path has run, so a repeat call is the
+    checks below, one ``torch.empty`` and the ``kx_map`` call.  BASELINE config 1 and the reference's own benchmark
+    shapes (tests_and_benchmarks/test_benchmark_{patch,conv2d}.py) are launch-latency bound: this is their hot path
+    (benchmarks/call_layers.py).  Returns None whenever a precondition fails -> the general path decides."""
+
+    __slots__ = ("funcs", "captured", "shape", "in_dtype", "device", "dev_index", "full_shape", "out_dtype", "geom", "prog",
+                 "geom_ref", "prog_ref", "kx_map", "weight", "raw_stream", "gen")
+
+    def __init__(self, func_map, key, shape, t, w, full_shape, out_dtype, geom, prog):
+        self.funcs = tuple(func_map)
+        plans = [_capture_plan(f) for f in self.funcs]
+        trivial = all(pl.trivial and not pl.fn.__defaults__ and not pl.fn.__kwdefaults__ for pl in plans)
+        self.captured = None if trivial else key[3]     # captured VALUES are re-checked per call unless there are none
+        self.shape, self.in_dtype, self.device = tuple(shape), t.dtype, t.device
+        self.dev_index = t.device.index if t.device.index is not None else torch.cuda.current_device()
+        self.full_shape, self.out_dtype = tuple(full_shape), out_dtype
+        self.geom, self.prog = geom, prog               # keep the ctypes structures alive
+        self.geom_ref, self.prog_ref = C.byref(geom), C.byref(prog.c)
+        self.kx_map = _lib.load().kx_map
+        self.weight = None if w is None else (tuple(w.shape), w.dtype)
+        self.raw_stream = torch._C._cuda_getCurrentRawStream
+        self.gen = _PLAN_GEN[0]
+
+    def __call__(self, t, w):
+        if self.gen != _PLAN_GEN[0] or t.shape != self.shape or t.dtype is not self.in_dtype or t.device != self.device or not t.is_contiguous():
+            return None
+        coef = 0
+        if w is not None:
+            if self.weight is None or type(w) is not torch.Tensor or (tuple(w.shape), w.dtype) != self.weight \
+                    or w.device != self.device or not w.is_contiguous() or w.requires_grad:
+                return None
+            coef = w.data_ptr()
+        elif self.weight is not None:
+            return None
+        if t.requires_grad and torch.is_grad_enabled():
+            return None
+        if self.captured is not None:
+            try:
+                if tuple(_func_fingerprint(f) for f in self.funcs) != self.captured:
+                    return None
+            except Exception:
+                return None
+        out = torch.empty(self.full_shape, dtype=self.out_dtype, device=self.device)
+        rc = self.kx_map(self.geom_ref, self.prog_ref, t.data_ptr(), coef, 0, out.data_ptr(), 1, self.raw_stream(self.dev_index))
+        if rc:
+            _lib.check(rc)
+        return out
+
+
+def _run_map(func_map, shape, kernel_size, strides, border, relative, array, a, k, static=None, fast_out=None):
     arr = _Arr(array)
     if tuple(arr.t.shape) != tuple(shape):
         raise ValueError(f"array shape {tuple(arr.t.shape)} != declared shape {tuple(shape)}")
@@ -532,6 +593,15 @@ def _run_map(func_map, shape, kernel_size, strides, border, relative, array, a, 
     comp_dtype = _KX2TORCH[out_kx]
     coef = prog.coef_tensor(device_args, comp_dtype, arr.t.device)
     needs_grad = torch.is_grad_enabled() and (arr.t.requires_grad or (coef is not None and coef.requires_grad))
+    if fast_out is not None and not needs_grad and arr.t is array and not k and len(a) <= 1 and hasattr(torch._C, "_cuda_getCurrentRawStream"):
+        # the call qualifies for the steady-state launcher if its plan is cacheable and the coefficient table is
+        # either absent or the single device argument itself (sum(x * w): zero-copy identity layout)
+        w = a[0] if a else None
+        ok = (w is None and coef is None) or (isinstance(w, torch.Tensor) and coef is not None and w.is_cuda
+                                              and w.is_contiguous() and coef.data_ptr() == w.data_ptr() and coef.dtype == w.dtype)
+        key = _plan_key("map", func_map, shape, kernel_size, strides, border, relative, arr.kx_dtype, a, k, static) if ok else None
+        if key is not None and key in _PLAN_CACHE and int(np.prod(full_shape)) > 0:
+            fast_out.append(_FastMap(func_map, key, shape, arr.t, w, full_shape, comp_dtype, geom, prog))
     if needs_grad:
         if len(specs) != 1 or specs[0].kind != "affine" or out_kx != _lib.KX_F32 or arr.kx_dtype != _lib.KX_F32:
             raise UnsupportedStencilError("gradients are implemented for single-function float32 affine stencils")
@@ -627,7 +697,15 @@ def kernel_map(func_map: dict, shape, kernel_size, strides, border, relative: bo
     folded = _fold_leading_axes(func_map, shape, kernel_size, strides, border, relative)
     fold1d = _fold_1d(func_map, shape, kernel_size, strides, border, relative)
 
+    fast: dict = {}      # (input dtype, has a weight argument) -> _FastMap, installed by the first general call
+
     def call(array, *a, **k):
+        if type(array) is torch.Tensor and not k and len(a) <= 1:     # steady state, device-resident input
+            ent = fast.get((array.dtype, len(a)))
+            if ent is not None:
+                out = ent(array, a[0] if a else None)
+                if out is not None:
+                    return out
         if folded is not None:
             return folded(array, *a, **k)
         if fold1d is not None and fold1d.applies(array, a, k):
@@ -635,7 +713,10 @@ def kernel_map(func_map: dict, shape, kernel_size, strides, border, relative: bo
         piped = _try_host_pipeline(func_map, shape, kernel_size, strides, border, relative, array, a, k)
         if piped is not None:
             return piped
-        arr, out = _run_map(func_map, shape, kernel_size, strides, border, relative, array, a, k, static)
+        installed: list = []
+        arr, out = _run_map(func_map, shape, kernel_size, strides, border, relative, array, a, k, static, installed)
+        if installed and len(fast) < 8:
+            fast[(arr.t.dtype, len(a))] = installed[0]
         return arr.give_back(out)
 
     static = _static_key("map", func_map, shape, kernel_size, strides, border, relative)
@@ -790,10 +871,13 @@ def _write_back(x, res, shape, strides, offset, what):
 # --------------------------------------------------------------------------- #
 
 
-def _run_scan(func_map, shape, kernel_size, strides, border, relative, reverse, array, a, k):
-    arr = _Arr(array)
-    if tuple(arr.t.shape) != tuple(shape):
-        raise ValueError(f"array shape {tuple(arr.t.shape)} != declared shape {tuple(shape)}")
+def _scan_plan(func_map, shape, kernel_size, strides, border, relative, in_kx, a, k, static=None):
+    """Trace + KxGeom / KxProgram of a scan, cached like the map plans (same key, tag "scan"): a time-stepping loop
+    that calls one kscan per step re-traces nothing."""
+    key = _plan_key("scan", func_map, shape, kernel_size, strides, border, relative, in_kx, a, k, static)
+    if key is not None and key in _PLAN_CACHE:
+        specs, _stale_args, prog, geom, out_shape = _PLAN_CACHE[key][1]
+        return specs, _fresh_device_args(a, k), prog, geom, out_shape
     specs, device_args = _trace_all(func_map, kernel_size, relative, a, k)
     for s in specs:
         if s.kind == "gather" and s.out_shape != ():
@@ -802,7 +886,18 @@ def _run_scan(func_map, shape, kernel_size, strides, border, relative, reverse, 
     out_shape = tuple(max(o, 0) for o in calculate_output_shape(shape, kernel_size, strides, border))
     prog = _Program(specs, groups, len(shape))
     # the carried state has the array's dtype; values are cast on write (scan.py:50)
-    geom = _geom(shape, out_shape, kernel_size, strides, border, arr.kx_dtype, arr.kx_dtype)
+    geom = _geom(shape, out_shape, kernel_size, strides, border, in_kx, in_kx)
+    plan = (specs, device_args, prog, geom, out_shape)
+    _cache_plan(key, func_map, plan)
+    return plan
+
+
+def _run_scan(func_map, shape, kernel_size, strides, border, relative, reverse, array, a, k, static=None):
+    arr = _Arr(array)
+    if tuple(arr.t.shape) != tuple(shape):
+        raise ValueError(f"array shape {tuple(arr.t.shape)} != declared shape {tuple(shape)}")
+    specs, device_args, prog, geom, out_shape = _scan_plan(
+        func_map, shape, kernel_size, strides, border, relative, arr.kx_dtype, a, k, static)
     comp = torch.float32 if any(s.kind == "affine" and s.weak_float for s in specs) else arr.t.dtype
     coef = prog.coef_tensor(device_args, comp, arr.t.device)
     lib = _lib.load()
@@ -835,9 +930,10 @@ def kernel_scan(func_map: dict, shape, kernel_size, strides, border, relative: b
     _validate(shape, kernel_size, strides, border)
 
     def call(array, *a, **k):
-        arr, out = _run_scan(func_map, shape, kernel_size, strides, border, relative, reverse, array, a, k)
+        arr, out = _run_scan(func_map, shape, kernel_size, strides, border, relative, reverse, array, a, k, static)
         return arr.give_back(out)
 
+    static = _static_key("scan", func_map, shape, kernel_size, strides, border, relative)
     return call
 
 
@@ -851,7 +947,8 @@ def offset_kernel_scan(func_map: dict, shape, kernel_size, strides, offset, rela
     _validate(shape, kernel_size, strides, border)
 
     def call(array, *a, **k):
-        arr, res = _run_scan(func_map, shape, kernel_size, strides, border, relative, reverse, array, a, k)
+        arr, res = _run_scan(func_map, shape, kernel_size, strides, border, relative, reverse, array, a, k, static)
         return arr.give_back(_write_back(arr.t, res, shape, strides, offset, "scan"))
 
+    static = _static_key("scan", func_map, shape, kernel_size, strides, border, relative)
     return call

@@ -92,3 +92,23 @@ def test_fingerprint_is_cheap():
     for _ in range(2000):
         _key(f)
     assert (time.perf_counter() - t0) / 2000 < 50e-6
+
+
+def test_scan_plans_are_cached_per_captured_value():
+    """kernel_scan keeps its traced program per (function, geometry, captured values) like kernel_map does: the second
+    lookup returns the SAME program object, a changed closure value a new one (scan.py:84-113 re-traces per call)."""
+    E.clear_plan_cache()
+    c = 0.5
+    f = lambda u: u[0, 0] - c * (u[0, 0] - u[0, -1])      # noqa: E731
+    args = ({f: ()}, (6, 16), (1, 3), (1, 1), ((0, 0), (1, 1)), True, _lib.KX_F32, (), {})
+    p1 = E._scan_plan(*args)
+    p2 = E._scan_plan(*args)
+    assert p1[2] is p2[2] and p1[3] is p2[3]
+    c = 0.25
+    p3 = E._scan_plan(*args)
+    assert p3[2] is not p1[2]
+    assert abs(p3[2].c.coef[0] - p1[2].c.coef[0]) > 0 or any(
+        p3[2].c.coef[i] != p1[2].c.coef[i] for i in range(p1[2].c.n_taps))
+    # a map of the same function and geometry is a different entry (tag), not a collision
+    m = E._map_plan(*args)
+    assert m[3] is not p3[2]
