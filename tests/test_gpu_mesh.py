@@ -177,3 +177,34 @@ def test_two_pass_mesh_equals_one_pass_bit_for_bit(kex, dtype, monkeypatch):
             if strided:
                 edge &= ~((rr % 64 == 0) & (cc % 2 == 0))
             np.testing.assert_array_equal(g[edge], xh[1:-1, 1:-1][edge])
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_mesh_block_order_covers_every_tile(kex, seed, monkeypatch):
+    """stencil2d_mesh_kernel dispatches the tile columns / row bands a region edge runs through FIRST (linear grid, the
+    rest follows band by band).  Whatever the edges -- none, a few, more than the priority tables hold (17+ distinct
+    tile columns: natural order) -- every tile must be computed exactly once: the result equals the generic kernel's
+    and the run in natural order (KX_MESH_NO_PRIO=1) bit for bit."""
+    rng = np.random.default_rng(900 + seed)
+    n0, n1 = int(rng.integers(100, 700)), 4 * int(rng.integers(300, 1400))
+    x = torch.from_numpy(rng.integers(-50, 50, (n0, n1)).astype(np.int32)).cuda()
+    F = kex.kmap(kernel_size=(3, 3), padding="same", relative=True)
+    F[:, :] = lambda v: v[0, 0]
+    F[1:-1, 1:-1] = lambda v: v[1, 0] + v[0, -1] - 4 * v[0, 0] + v[0, 1] + v[-1, 0]
+    fns = [lambda v: 2 * v[0, 0] + 1, lambda v: v[0, 1] - v[0, -1], lambda v: 3 * v[-1, 0], lambda v: v[1, 1] + 7]
+    n_rect = [0, 1, 3, 9, 12, 2][seed]          # 9+ rectangles: more than 16 distinct edge columns are likely
+    for i in range(n_rect):
+        r0, c0 = int(rng.integers(0, n0 - 2)), int(rng.integers(0, n1 - 2))
+        r1, c1 = int(rng.integers(r0 + 1, n0)), int(rng.integers(c0 + 1, n1))
+        F[r0:r1, c0:c1] = fns[i % len(fns)]
+    got = F(x)
+    assert _last_kernel() == "stencil2d_mesh_kernel"
+    monkeypatch.setenv("KX_MESH_NO_PRIO", "1")
+    natural = F(x)
+    monkeypatch.delenv("KX_MESH_NO_PRIO")
+    monkeypatch.setenv("KX_NO_MESH", "1")
+    want = F(x)
+    assert _last_kernel() == "generic_map_kernel"
+    monkeypatch.delenv("KX_NO_MESH")
+    assert torch.equal(got, natural)
+    assert torch.equal(got, want)
