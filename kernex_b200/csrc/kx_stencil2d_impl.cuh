@@ -113,8 +113,27 @@ __device__ __forceinline__ T s2_fold(T acc, T v) {
   }
 }
 
+#include "kx_stencil2d_minb.inc"
+// Which instantiations carry the INNER path (and the register cap that goes with it).  Measured on B200, 16384^2 fp32,
+// fraction of the HBM roofline without -> with (profiles/r2e_s2_inner.txt): 1x7 moving average 0.70 -> 0.92, 5x5 box blur
+// 0.90 -> 0.92, 5x5 max filter 0.92 -> 0.94, dense 7x7 0.37 -> 0.44; but the small windows LOSE: 3x3 5-point (C2)
+// 1.02 -> 0.99 and its 8-byte aligned backward pass 1.01 -> 0.91 (the cap alone: spills where ptxas used to
+// rematerialise), 3x3 max filter 1.02 -> 0.89, separable 4x4 0.92 -> 0.83.  So: row windows of 5 taps and more and
+// windows of 25 taps and more; every other instantiation compiles exactly as before (minBlocks 0 = not specified;
+// minBlocks 1 is NOT the same: ptxas then stops rematerialising and the 3x3 kernels take 85-92 registers instead of 54).
+__host__ __device__ constexpr bool s2_inner_path(int KY, int KX, int VW, int OP) {
+  return VW == 4 && ((KY == 1 && KX >= 5) || KY * KX >= 25);
+}
+
+constexpr int s2_minb(bool is_float, int KY, int KX, int SHIFT, int VW, int U, int OP) {
+  const unsigned key = (((((((is_float ? 1u : 0u) * 16 + KY) * 16 + KX) * 4 + SHIFT) * 8 + VW) * 8 + U) * 8 + OP);
+  for (unsigned i = 0; i < sizeof(kS2MinB) / sizeof(kS2MinB[0]); ++i)
+    if (kS2MinB[i][0] == key) return (int)kS2MinB[i][1];
+  return 1;   // an instantiation the table does not know: no cap
+}
+
 template <typename T, int KY, int KX, int SHIFT, int VW, int U, int OP>
-__global__ void __launch_bounds__(kTX)
+__global__ void __launch_bounds__(kTX, s2_inner_path(KY, KX, VW, OP) ? s2_minb(std::is_same<T, float>::value, KY, KX, SHIFT, VW, U, OP) : 0)
 stencil2d_kernel(const __grid_constant__ S2Args<T> a) {
   constexpr int NV = (SHIFT + KX + kCols - 1 + VW - 1) / VW;  // aligned vectors per row per thread
   constexpr int NE = NV * VW;
@@ -139,44 +158,12 @@ stencil2d_kernel(const __grid_constant__ S2Args<T> a) {
     for (int i = 0; i < KY * KX; ++i) coef[i] = a.coef[i];
   }
 
-  auto load_row = [&](int iy, T(&dst)[NE]) {
-    const bool row_ok = (iy >= 0) && (iy < a.hin);
-    const T* rp = in + (int64_t)iy * a.win;
-    if (VW == 4) {
-#pragma unroll
-      for (int v = 0; v < NV; ++v) {
-        const int c = xa + 4 * v;
-        if (row_ok && c >= 0 && c + 3 < a.win) {  // win % 4 == 0: a vector is all in or all out
-          const Vec4<T> t = ld_vec4(rp + c);
-#pragma unroll
-          for (int e = 0; e < 4; ++e) dst[4 * v + e] = t.v[e];
-        } else {
-#pragma unroll
-          for (int e = 0; e < 4; ++e) dst[4 * v + e] = T(0);
-        }
-      }
-    } else if (VW == 2) {
-#pragma unroll
-      for (int v = 0; v < NV; ++v) {
-        const int c = xa + 2 * v;
-        if (row_ok && c >= 0 && c + 1 < a.win) {  // win % 2 == 0: a pair is all in or all out
-          const int2 raw = __ldg(reinterpret_cast<const int2*>(rp + c));
-          dst[2 * v] = reinterpret_cast<const T&>(raw.x);
-          dst[2 * v + 1] = reinterpret_cast<const T&>(raw.y);
-        } else {
-          dst[2 * v] = T(0);
-          dst[2 * v + 1] = T(0);
-        }
-      }
-    } else {
-#pragma unroll
-      for (int e = 0; e < KX + kCols - 1; ++e) {
-        const int c = xa + e;
-        dst[e] = (row_ok && c >= 0 && c < a.win) ? __ldg(rp + c) : T(0);
-      }
-    }
-  };
-
+  // INNER (warp-uniform, see below): every row and every aligned vector the warp reads exists -> one 64-bit multiply-add
+  // and NV unconditional 128-bit loads per row.  With the bounds tests the compiler re-derives column index, batch
+  // offset and predicates per vector (about 12 instructions per loaded vector, measured on the mesh kernel: 48 per row
+  // load against 20 FMAs), which is what made smap, the 1-D FIR filters and the small grids issue-bound (75-80 % issue
+  // active at 0.71-0.94 of the roofline).
+  const T* __restrict__ colp = in + xa;            // element 0 of the thread's row buffer in row 0 (dereferenced only where valid)
   // Separable operators (whole-window max / min, and sums with one common coefficient) queue the HORIZONTAL fold
   // of every input row (4 values per thread) instead of the row itself: KX-1 + KY-1 operations per output
   // instead of KY*KX-1, and a queue of 4-wide rows.
@@ -211,101 +198,179 @@ stencil2d_kernel(const __grid_constant__ S2Args<T> a) {
     }
   };
 
-  T q[KY - 1 + U][QW];
+  T* __restrict__ outp = out + j0;
+  const bool st_al = (a.wout % 4 == 0) && (a.out_batch % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.out) & 15) == 0);   // every output row 16-byte aligned
+  auto march = [&](auto inner_c) {
+    constexpr bool INNER = decltype(inner_c)::value;
+    auto load_row = [&](int iy, T(&dst)[NE]) {
+      const bool row_ok = (iy >= 0) && (iy < a.hin);
+      const T* rp = in + (int64_t)iy * a.win;
+      if constexpr (INNER && VW == 4) {
+        const T* ip = colp + (int64_t)iy * a.win;
 #pragma unroll
-  for (int ky = 0; ky < KY - 1; ++ky) {
-    if constexpr (!SEP) {
-      load_row(r0 - a.ly + ky, q[ky]);
-    } else {
-      T row[NE];
-      load_row(r0 - a.ly + ky, row);
-      hfold(row, q[ky]);
-    }
-  }
-
-  for (int r = r0; r < r1; r += U) {
-    if constexpr (!SEP) {
+        for (int v = 0; v < NV; ++v) {
+          const Vec4<T> t = ld_vec4(ip + 4 * v);
 #pragma unroll
-      for (int u = 0; u < U; ++u)
-        if (r + u < r1) load_row(r + u - a.ly + KY - 1, q[KY - 1 + u]);
-    } else {
-      T raw[U][NE];   // all U rows are requested before the first fold waits for one
+          for (int e = 0; e < 4; ++e) dst[(4 * v + e) % NE] = t.v[e];
+        }
+      } else if (VW == 4) {
 #pragma unroll
-      for (int u = 0; u < U; ++u)
-        if (r + u < r1) load_row(r + u - a.ly + KY - 1, raw[u]);
+        for (int v = 0; v < NV; ++v) {
+          const int c = xa + 4 * v;
+          if (row_ok && c >= 0 && c + 3 < a.win) {  // win % 4 == 0: a vector is all in or all out
+            const Vec4<T> t = ld_vec4(rp + c);
 #pragma unroll
-      for (int u = 0; u < U; ++u)
-        if (r + u < r1) hfold(raw[u], q[KY - 1 + u]);
-    }
+            for (int e = 0; e < 4; ++e) dst[4 * v + e] = t.v[e];
+          } else {
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      if (r + u < r1) {
-        T acc[kCols];
-        if constexpr (!SEP) {
-#pragma unroll
-          for (int i = 0; i < kCols; ++i) acc[i] = a.bias;
-#pragma unroll
-          for (int ky = 0; ky < KY; ++ky) {
-#pragma unroll
-            for (int kx = 0; kx < KX; ++kx) {
-              if ((ky * KX + kx < 32) ? (a.mask & (1u << ((ky * KX + kx) & 31))) : (a.mask_hi & (1u << ((ky * KX + kx) & 31)))) {
-#pragma unroll
-                for (int i = 0; i < kCols; ++i)
-                  acc[i] = mad_wrap(coef[ky * KX + kx], q[u + ky][SHIFT + kx + i], acc[i]);
-              }
-            }
+            for (int e = 0; e < 4; ++e) dst[4 * v + e] = T(0);
           }
-        } else {
-          if constexpr (OP == kSep && std::is_same<T, float>::value) {
-            // vertical fold as packed FFMA2: two output columns per instruction, the weight is a broadcast scalar
-            // (same rounding as the scalar chain; the wide windows are issue-bound: 74 % issue-active at 15x15)
+        }
+      } else if (VW == 2) {
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+          const int c = xa + 2 * v;
+          if (row_ok && c >= 0 && c + 1 < a.win) {  // win % 2 == 0: a pair is all in or all out
+            const int2 raw = __ldg(reinterpret_cast<const int2*>(rp + c));
+            dst[2 * v] = reinterpret_cast<const T&>(raw.x);
+            dst[2 * v + 1] = reinterpret_cast<const T&>(raw.y);
+          } else {
+            dst[2 * v] = T(0);
+            dst[2 * v + 1] = T(0);
+          }
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < KX + kCols - 1; ++e) {
+          const int c = xa + e;
+          dst[e] = (row_ok && c >= 0 && c < a.win) ? __ldg(rp + c) : T(0);
+        }
+      }
+    };
+  
+    T q[KY - 1 + U][QW];
+#pragma unroll
+    for (int ky = 0; ky < KY - 1; ++ky) {
+      if constexpr (!SEP) {
+        load_row(r0 - a.ly + ky, q[ky]);
+      } else {
+        T row[NE];
+        load_row(r0 - a.ly + ky, row);
+        hfold(row, q[ky]);
+      }
+    }
+  
+    for (int r = r0; r < r1; r += U) {
+      if constexpr (!SEP) {
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+          if (r + u < r1) load_row(r + u - a.ly + KY - 1, q[KY - 1 + u]);
+      } else {
+        T raw[U][NE];   // all U rows are requested before the first fold waits for one
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+          if (r + u < r1) load_row(r + u - a.ly + KY - 1, raw[u]);
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+          if (r + u < r1) hfold(raw[u], q[KY - 1 + u]);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (r + u < r1) {
+          T acc[kCols];
+          if constexpr (!SEP) {
 #pragma unroll
             for (int i = 0; i < kCols; ++i) acc[i] = a.bias;
 #pragma unroll
             for (int ky = 0; ky < KY; ++ky) {
-              const float wy = a.coef[ky];
-              ffma2(acc[0], acc[1], wy, wy, q[u + ky][0], q[u + ky][1]);
-              ffma2(acc[2], acc[3], wy, wy, q[u + ky][2], q[u + ky][3]);
+#pragma unroll
+              for (int kx = 0; kx < KX; ++kx) {
+                if ((ky * KX + kx < 32) ? (a.mask & (1u << ((ky * KX + kx) & 31))) : (a.mask_hi & (1u << ((ky * KX + kx) & 31)))) {
+#pragma unroll
+                  for (int i = 0; i < kCols; ++i)
+                    acc[i] = mad_wrap(coef[ky * KX + kx], q[u + ky][SHIFT + kx + i], acc[i]);
+                }
+              }
             }
-          } else
+          } else {
+            if constexpr (OP == kSep && std::is_same<T, float>::value) {
+              // vertical fold as packed FFMA2: two output columns per instruction, the weight is a broadcast scalar
+              // (same rounding as the scalar chain; the wide windows are issue-bound: 74 % issue-active at 15x15)
 #pragma unroll
-          for (int i = 0; i < kCols; ++i) {
-            if constexpr (OP == kSep) {
-              T v = a.bias;
+              for (int i = 0; i < kCols; ++i) acc[i] = a.bias;
 #pragma unroll
-              for (int ky = 0; ky < KY; ++ky) v = mad_wrap(a.coef[ky], q[u + ky][i], v);
-              acc[i] = v;
+              for (int ky = 0; ky < KY; ++ky) {
+                const float wy = a.coef[ky];
+                ffma2(acc[0], acc[1], wy, wy, q[u + ky][0], q[u + ky][1]);
+                ffma2(acc[2], acc[3], wy, wy, q[u + ky][2], q[u + ky][3]);
+              }
             } else {
-              T v = q[u][i];
 #pragma unroll
-              for (int ky = 1; ky < KY; ++ky) v = s2_fold<T, OP>(v, q[u + ky][i]);
-              acc[i] = (OP == kBox) ? mad_wrap(a.coef[0], v, a.bias) : v;
+              for (int i = 0; i < kCols; ++i) {
+                if constexpr (OP == kSep) {
+                  T v = a.bias;
+#pragma unroll
+                  for (int ky = 0; ky < KY; ++ky) v = mad_wrap(a.coef[ky], q[u + ky][i], v);
+                  acc[i] = v;
+                } else {
+                  T v = q[u][i];
+#pragma unroll
+                  for (int ky = 1; ky < KY; ++ky) v = s2_fold<T, OP>(v, q[u + ky][i]);
+                  acc[i] = (OP == kBox) ? mad_wrap(a.coef[0], v, a.bias) : v;
+                }
+              }
             }
           }
-        }
-        if (std::is_same<T, float>::value && (OP == kAffine || OP == kBox || OP == kSep) && a.post_mul != 0.f) {
-          // block-uniform: window mean.  One multiply by the host-rounded reciprocal (<= 1.5 ulp from the true
-          // quotient, exact for power-of-two windows) instead of ~10 instructions of IEEE division per output:
-          // the 5x5 box blur went from 0.74 to 0.9x of peak
+          if (std::is_same<T, float>::value && (OP == kAffine || OP == kBox || OP == kSep) && a.post_mul != 0.f) {
+            // block-uniform: window mean.  One multiply by the host-rounded reciprocal (<= 1.5 ulp from the true
+            // quotient, exact for power-of-two windows) instead of ~10 instructions of IEEE division per output:
+            // the 5x5 box blur went from 0.74 to 0.9x of peak
 #pragma unroll
-          for (int i = 0; i < kCols; ++i) acc[i] = (T)((float)acc[i] * a.post_mul);
-        }
-        if constexpr (!SEP) {
-          if (a.use_box) {  // block-uniform: smap / offset_kernel_map fused into one pass
-            const bool rin = (r + u >= a.by0) && (r + u < a.by1);
+            for (int i = 0; i < kCols; ++i) acc[i] = (T)((float)acc[i] * a.post_mul);
+          }
+          if constexpr (!SEP) {
+            if (a.use_box) {  // block-uniform: smap / offset_kernel_map fused into one pass
+              const bool rin = (r + u >= a.by0) && (r + u < a.by1);
 #pragma unroll
-            for (int i = 0; i < kCols; ++i)
-              if (!(rin && j0 + i >= a.bx0 && j0 + i < a.bx1)) acc[i] = q[u + (KY - 1) / 2][SHIFT + (KX - 1) / 2 + i];
+              for (int i = 0; i < kCols; ++i)
+                if (!(rin && j0 + i >= a.bx0 && j0 + i < a.bx1)) acc[i] = q[u + (KY - 1) / 2][SHIFT + (KX - 1) / 2 + i];
+            }
+          }
+          if constexpr (INNER) {
+            T* o = outp + (int64_t)(r + u) * a.wout;
+            if (st_al) {
+              int4 raw4;
+              raw4.x = reinterpret_cast<const int&>(acc[0]);
+              raw4.y = reinterpret_cast<const int&>(acc[1]);
+              raw4.z = reinterpret_cast<const int&>(acc[2]);
+              raw4.w = reinterpret_cast<const int&>(acc[3]);
+              __stcs(reinterpret_cast<int4*>(o), raw4);
+            } else {
+              st_row4(o, acc, 4);
+            }
+          } else {
+            st_row4(out + (int64_t)(r + u) * a.wout + j0, acc, n_valid);
           }
         }
-        st_row4(out + (int64_t)(r + u) * a.wout + j0, acc, n_valid);
+      }
+#pragma unroll
+      for (int ky = 0; ky < KY - 1; ++ky) {
+#pragma unroll
+        for (int e = 0; e < QW; ++e) q[ky][e] = q[U + ky][e];
       }
     }
-#pragma unroll
-    for (int ky = 0; ky < KY - 1; ++ky) {
-#pragma unroll
-      for (int e = 0; e < QW; ++e) q[ky][e] = q[U + ky][e];
-    }
+  };
+  // warp-uniform: the rows r0 - ly .. r1 - 1 - ly + KY - 1 exist, so do the aligned vectors of lanes 0 and 31, and every
+  // lane owns 4 output columns
+  const int jw = (blockIdx.x * kTX + (threadIdx.x & ~31)) * kCols;
+  const int xw = jw - a.lx - SHIFT;
+  const bool inner = VW == 4 && (r0 - a.ly >= 0) && (r1 - 1 - a.ly + KY - 1 < a.hin) && (xw >= 0) &&
+                     (xw + 31 * kCols + NE <= a.win) && (jw + 32 * kCols <= a.wout);
+  if constexpr (s2_inner_path(KY, KX, VW, OP)) {
+    if (inner) march(std::true_type{});
+    else march(std::false_type{});
+  } else {
+    march(std::false_type{});
   }
 }
 
