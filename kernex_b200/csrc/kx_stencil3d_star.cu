@@ -25,6 +25,8 @@
 //   Per-stage mbarriers instead of wait_group + __syncthreads (cp.async.mbarrier.arrive.noinc for "landed", one
 //   arrive per thread for "read"; a warp then waits for data only): 767 vs 770-774 on the same box -- the per-plane
 //   block barrier shows up in the stall samples but is not what limits the kernel; removed again.
+//   Deeper rings in dynamic shared memory (3 blocks / SM kept): 3 stages 764, 4 stages 695, 5 stages 708, 6 stages 697 --
+//   MORE bytes in flight are slower, so the limit is not latency but what DRAM / L2 make of the access stream.
 // KX_STAR_WX=1|2|4, KX_STAR_ZC=n, KX_STAR_NO_GROUPS=1 and KX_STAR_GRID3D=1 select the other variants (bit-identical
 // results; cross-checks and A/B timing).
 #include "kx_internal.cuh"
