@@ -13,6 +13,11 @@
 // FFMA2 (two outputs per instruction, the weight is a broadcast scalar).  The C * 9 weights (host table or device
 // array) are staged in shared memory once per block and read back as broadcasts, 9 per plane.
 // Accumulation order of one output: bias, then the window in row-major (c, ky, kx) order.
+// ncu at (16, 4096^2), 0.77 of the HBM roofline: the shared-memory pipe is the limiter (l1tex 92 % of its peak, short
+// scoreboard + MIO throttle the top stalls: 12 LDS.128 of plane data + 3 of weights per plane and thread).  Measured and
+// rejected: one own vector per row + the neighbours' columns by __shfl_up / __shfl_down (edge lanes read the adjacent
+// vector): 4 MIO instructions per row instead of 3 -> 0.585; 8 contiguous columns per lane would halve the LDS count
+// but puts lanes 32 B apart (2-way bank conflicts on LDS.128).
 #include <type_traits>
 
 #include "kx_internal.cuh"
