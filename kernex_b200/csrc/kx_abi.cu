@@ -1,5 +1,7 @@
 // extern "C" entry points of libkx_b200 (declared in include/kx_b200.h): validation and
 // dispatch to the kernel templates.  Every entry point only enqueues on `stream`.
+#include <algorithm>
+#include <vector>
 #include "kx_internal.cuh"
 
 using namespace kx;
@@ -72,6 +74,158 @@ void fill_map_args(MapArgs& a, const KxGeom& g, const KxProgram& p, const void* 
   a.out_base = 0;
 }
 
+int dispatch_map(const MapArgs& a, const KxProgram& prog, cudaStream_t s);
+
+// Multi-function meshes that none of the fast templates takes (3-D windows -- a heat equation with Dirichlet faces --,
+// window reductions, wide windows, more than 8 functions): `F[slice] = fn` regions are boxes, so the function that
+// covers the bulk of the domain runs as a SINGLE-function map over every window (on whatever fast template takes it:
+// 0.8-1.0 of the HBM roofline instead of the generic kernel's 0.05), and the boxes of the OTHER functions' keys are
+// recomputed afterwards by the generic kernel with the full region selection of kernex/_src/utils.py:338-382 (so key
+// priority and overlaps need no special care: a recomputed cell always gets the function the reference selects).
+// Declines (-> one generic launch over everything) for strided keys, vector-valued functions, device coefficients,
+// batches, when a window could match no key while the bulk function is not function 0, or when the boxes are more
+// than 30 % of the domain.  KX_NO_DECOMPOSE=1 switches it off (cross-check).
+int try_mesh_decompose(const MapArgs& a, const KxProgram& p, cudaStream_t s) {
+  const KxGeom& g = a.g;
+  const int nd = g.ndim;
+  if (p.n_funcs < 2 || a.batch != 1 || a.fn_elems != 1 || a.use_box || a.coef_dev || a.in_bcast) return KX_ERR_UNSUPPORTED;
+  if (getenv("KX_NO_DECOMPOSE")) return KX_ERR_UNSUPPORTED;
+  for (int f = 0; f < p.n_funcs; ++f)
+    if (p.func[f].kind == KX_GATHER) return KX_ERR_UNSUPPORTED;
+  struct Box {
+    int64_t j0[KX_MAX_DIMS], j1[KX_MAX_DIMS];
+    int64_t vol;
+    bool whole;
+  };
+  auto ceil_div = [](int64_t n, int64_t d) { return n >= 0 ? (n + d - 1) / d : -((-n) / d); };
+  static thread_local Box box[KX_MAX_KEYS];
+  const int64_t kFar = (int64_t)1 << 40;
+  for (int k = 0; k < p.n_keys; ++k) {
+    Box& b = box[k];
+    b.vol = 1;
+    b.whole = true;
+    for (int d = 0; d < nd; ++d) {
+      int64_t lo_j = 0, hi_j = g.out_shape[d];
+      if (d < p.key[k].n_items && p.key[k].item[d].kind != KX_KEY_ANY) {
+        const KxKeyItem& it = p.key[k].item[d];
+        if (it.kind == KX_KEY_RANGE_STEP && it.step != 1 && it.step != -1) return KX_ERR_UNSUPPORTED;   // c % 1 == 0 always
+        int64_t ca = it.a, cb = it.kind == KX_KEY_EQ ? it.a + 1 : it.b;     // window centres c with ca <= c < cb
+        ca = std::max(ca, -kFar);
+        cb = std::min(cb, kFar);
+        // c(j) = j * stride - lo + (k - 1) / 2
+        const int64_t sh = (int64_t)g.lo[d] - (g.ksize[d] - 1) / 2, st = g.stride[d];
+        lo_j = std::max(lo_j, ceil_div(ca + sh, st));
+        hi_j = std::min(hi_j, ceil_div(cb + sh, st));
+      }
+      if (hi_j < lo_j) hi_j = lo_j;
+      b.j0[d] = lo_j;
+      b.j1[d] = hi_j;
+      b.vol *= hi_j - lo_j;
+      b.whole = b.whole && lo_j == 0 && hi_j == g.out_shape[d];
+    }
+  }
+  // the bulk function: the one the reference selects for the window in the middle of the domain
+  int dom = 0;
+  {
+    int64_t centre[KX_MAX_DIMS];
+    for (int d = 0; d < nd; ++d) centre[d] = (g.out_shape[d] / 2) * g.stride[d] - g.lo[d] + (g.ksize[d] - 1) / 2;
+    for (int k = p.n_keys - 1; k >= 0; --k) {
+      bool ok = true;
+      for (int d = 0; d < p.key[k].n_items && d < nd; ++d) {
+        const KxKeyItem& it = p.key[k].item[d];
+        if (it.kind == KX_KEY_EQ) ok = ok && centre[d] == it.a;
+        else if (it.kind == KX_KEY_RANGE || it.kind == KX_KEY_RANGE_STEP) ok = ok && it.a <= centre[d] && centre[d] < it.b;
+      }
+      if (ok) {
+        dom = p.key[k].func;
+        break;
+      }
+    }
+  }
+  bool covered = dom == 0;           // a window no key matches gets function 0 (utils.py:379)
+  for (int k = 0; k < p.n_keys; ++k) covered = covered || box[k].whole;
+  if (!covered) return KX_ERR_UNSUPPORTED;
+  // cells to recompute: the box of every key of another function, minus the boxes of the LATER-inserted keys of the
+  // bulk function (they win there: `F[:, :, :] = bc` followed by `F[1:-1, 1:-1, 1:-1] = step` leaves the six faces)
+  struct Cut {
+    int64_t j0[KX_MAX_DIMS], j1[KX_MAX_DIMS];
+  };
+  std::vector<Cut> todo, cur, nxt;
+  for (int k = 0; k < p.n_keys; ++k) {
+    if (p.key[k].func == dom || box[k].vol == 0) continue;
+    cur.clear();
+    Cut c0;
+    for (int d = 0; d < KX_MAX_DIMS; ++d) c0.j0[d] = d < nd ? box[k].j0[d] : 0, c0.j1[d] = d < nd ? box[k].j1[d] : 1;
+    cur.push_back(c0);
+    for (int q = k + 1; q < p.n_keys && !cur.empty(); ++q) {
+      if (p.key[q].func != dom || box[q].vol == 0) continue;
+      nxt.clear();
+      for (const Cut& b : cur) {
+        bool overlap = true;
+        for (int d = 0; d < nd; ++d) overlap = overlap && box[q].j0[d] < b.j1[d] && box[q].j1[d] > b.j0[d];
+        if (!overlap) {
+          nxt.push_back(b);
+          continue;
+        }
+        Cut r = b;                                   // peel off the slabs of b outside box q, axis by axis
+        for (int d = 0; d < nd; ++d) {
+          if (r.j0[d] < box[q].j0[d]) {
+            Cut lo = r;
+            lo.j1[d] = box[q].j0[d];
+            nxt.push_back(lo);
+            r.j0[d] = box[q].j0[d];
+          }
+          if (r.j1[d] > box[q].j1[d]) {
+            Cut hi = r;
+            hi.j0[d] = box[q].j1[d];
+            nxt.push_back(hi);
+            r.j1[d] = box[q].j1[d];
+          }
+        }
+      }
+      cur.swap(nxt);
+      if (cur.size() > 256) return KX_ERR_UNSUPPORTED;
+    }
+    todo.insert(todo.end(), cur.begin(), cur.end());
+    if (todo.size() > 256) return KX_ERR_UNSUPPORTED;
+  }
+  int64_t patch = 0;
+  for (const Cut& b : todo) {
+    int64_t v = 1;
+    for (int d = 0; d < nd; ++d) v *= b.j1[d] - b.j0[d];
+    patch += v;
+  }
+  if (patch * 10 > a.n_win * 3) return KX_ERR_UNSUPPORTED;
+
+  static thread_local KxProgram p1;
+  memset(&p1, 0, sizeof(p1));
+  p1.n_funcs = 1;
+  p1.func[0] = p.func[dom];
+  p1.n_taps = p.func[dom].tap_end - p.func[dom].tap_begin;
+  p1.func[0].tap_begin = 0;
+  p1.func[0].tap_end = p1.n_taps;
+  for (int t = 0; t < p1.n_taps; ++t) {
+    for (int d = 0; d < KX_MAX_DIMS; ++d) p1.tap_off[t][d] = p.tap_off[p.func[dom].tap_begin + t][d];
+    p1.coef[t] = p.coef[p.func[dom].tap_begin + t];
+  }
+  int rc = dispatch_map(a, p1, s);
+  if (rc) return rc;
+  for (const Cut& b : todo) {
+    MapArgs ab = a;
+    ab.n_win = 1;
+    for (int d = 0; d < nd; ++d) {
+      ab.g.out_shape[d] = b.j1[d] - b.j0[d];
+      ab.n_win *= ab.g.out_shape[d];
+      ab.g.lo[d] = (int32_t)(g.lo[d] - b.j0[d] * g.stride[d]);          // window j of the box = window j0 + j of the map
+      ab.out_base += b.j0[d] * a.out_pitch[d];
+    }
+    if (ab.n_win == 0) continue;
+    rc = launch_generic_map(ab, p, s);
+    if (rc) return rc;
+  }
+  return KX_OK;
+}
+
 // fast templates first, the generic kernel as the universal backstop
 int dispatch_map(const MapArgs& a, const KxProgram& prog, cudaStream_t s) {
   int rc = try_stencil2d(a, prog, s);
@@ -91,6 +245,8 @@ int dispatch_map(const MapArgs& a, const KxProgram& prog, cudaStream_t s) {
   rc = try_pool2d(a, prog, s);
   if (rc != KX_ERR_UNSUPPORTED) return rc;
   rc = try_pool3d(a, prog, s);
+  if (rc != KX_ERR_UNSUPPORTED) return rc;
+  rc = try_mesh_decompose(a, prog, s);
   if (rc != KX_ERR_UNSUPPORTED) return rc;
   return launch_generic_map(a, prog, s);
 }

@@ -100,9 +100,11 @@ def test_interface_mesh_large_matches_generic_kernel(kex, monkeypatch):
     got = F(x)
     assert _last_kernel() == "stencil2d_mesh_kernel"
     monkeypatch.setenv("KX_NO_MESH", "1")
+    monkeypatch.setenv("KX_NO_DECOMPOSE", "1")      # ONE generic launch over everything
     want = F(x)
     assert _last_kernel() == "generic_map_kernel"
     monkeypatch.delenv("KX_NO_MESH")
+    monkeypatch.delenv("KX_NO_DECOMPOSE")
     # same taps and coefficients; the generic kernel accumulates in expression order, this one in window order
     torch.testing.assert_close(got, want, rtol=1e-5, atol=1e-5)
     # independent check of the three rectangular regions
@@ -203,8 +205,10 @@ def test_mesh_block_order_covers_every_tile(kex, seed, monkeypatch):
     natural = F(x)
     monkeypatch.delenv("KX_MESH_NO_PRIO")
     monkeypatch.setenv("KX_NO_MESH", "1")
+    monkeypatch.setenv("KX_NO_DECOMPOSE", "1")      # ONE generic launch over everything
     want = F(x)
     assert _last_kernel() == "generic_map_kernel"
     monkeypatch.delenv("KX_NO_MESH")
+    monkeypatch.delenv("KX_NO_DECOMPOSE")
     assert torch.equal(got, natural)
     assert torch.equal(got, want)
