@@ -28,6 +28,12 @@ if case in ("ma7", "box5", "max5", "w4", "lap", "d7", "smap", "lap8k"):
                        "max5": ((5, 5), lambda v: np.max(v), False), "w4": ((4, 4), lambda v: np.sum(v * rw[:4, :4]), False),
                        "lap": ((3, 3), lap, True), "lap8k": ((3, 3), lap, True), "d7": ((7, 7), lambda v: np.sum(v * rw), False)}[case]
         f = kex.kmap(kernel_size=ks, padding="same", relative=rel)(fn)
+elif case in ("patch5", "patch7", "patch5_old"):
+    import os as _os
+    k = 7 if case == "patch7" else 5
+    n = 4096
+    x = torch.randn((n, n), device=dev, generator=g)
+    f = kex.kmap(kernel_size=(k, k), padding="same")(lambda v: v)
 elif case == "fir15":
     x = torch.randn((1 << 27,), device=dev, generator=g)
     taps = np.hanning(15).astype(np.float32)

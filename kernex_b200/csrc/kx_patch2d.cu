@@ -253,6 +253,70 @@ int launch_p2_warp(const P2Args& a, int64_t batch, cudaStream_t s) {
   return after_launch("patch2d_kernel");
 }
 
+// ---------------------------------------------------------------------------------------------
+// Larger windows (5x5, 7x7, 4x4, 1x7, ...): 4 windows x KY*KX outputs no longer fit a thread's registers (5x5: 100), so
+// nothing is staged -- the block walks the row segment's output words in ORDER (fully coalesced 128-bit streaming
+// stores) and picks every word out of the shared-memory row ring: word i of the segment is tap i % NT of window i / NT
+// (compile-time divisors).  Write-bound like the small windows: 4 B read + 4 KY KX B written per window; before this
+// kernel these shapes ran on patch_kernel (flat gather through L1: 0.15 of the HBM roofline).
+template <int KY, int KX, bool ROLLED>
+__global__ void __launch_bounds__(kPT)
+patch2d_direct_kernel(const __grid_constant__ P2Args a) {
+  constexpr int NT = KY * KX;
+  constexpr int TW = 256;                           // windows per block row
+  constexpr int PW = TW + ((KX - 1 + 3) / 4) * 4;
+  __shared__ __align__(16) uint32_t rows[KY][PW];
+  const int tid = threadIdx.x;
+  const int x0 = blockIdx.x * TW;
+  const int r0 = blockIdx.y * a.th, r1 = min(r0 + a.th, a.hout);
+  const uint32_t* __restrict__ in = a.in + (int64_t)blockIdx.z * a.in_batch;
+  uint32_t* __restrict__ out = a.out + (int64_t)blockIdx.z * a.out_batch;
+  const int nwin = min(TW, a.wout - x0);
+  const int count = nwin * NT;
+  auto load_row = [&](int iy, int slot) {
+    const bool row_ok = (iy >= 0) && (iy < a.hin);
+    const uint32_t* rp = in + (int64_t)iy * a.win;
+    for (int c = tid; c < TW + KX - 1; c += kPT) {
+      const int gx = x0 - a.lx + c;
+      rows[slot][c] = (row_ok && gx >= 0 && gx < a.win) ? __ldg(rp + gx) : 0u;
+    }
+  };
+  auto word = [&](int i, int rb) -> uint32_t {      // output word i of the row segment; rb = r % KY
+    const int w = i / NT, t = i - w * NT;
+    const int ty = t / KX, tx = t - ty * KX;
+    // rolled layout: patch index (ty,tx) holds window element ((ty+cy)%KY, (tx+cx)%KX)
+    const int sy = ROLLED ? (ty + (KY - 1) / 2) % KY : ty;
+    const int sx = ROLLED ? (tx + (KX - 1) / 2) % KX : tx;
+    int slot = rb + sy;
+    if (slot >= KY) slot -= KY;
+    return rows[slot][w + sx];
+  };
+#pragma unroll 1
+  for (int ky = 0; ky < KY - 1; ++ky) load_row(r0 - a.ly + ky, (r0 + ky) % KY);
+  for (int r = r0; r < r1; ++r) {
+    load_row(r - a.ly + KY - 1, (r + KY - 1) % KY);
+    __syncthreads();
+    const int rb = r % KY;
+    uint32_t* dst = out + ((int64_t)r * a.wout + x0) * NT;
+    if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+      for (int v = tid; 4 * v + 3 < count; v += kPT)
+        __stcs(reinterpret_cast<uint4*>(dst) + v, make_uint4(word(4 * v, rb), word(4 * v + 1, rb), word(4 * v + 2, rb), word(4 * v + 3, rb)));
+      for (int i = (count & ~3) + tid; i < count; i += kPT) dst[i] = word(i, rb);
+    } else {
+      for (int i = tid; i < count; i += kPT) dst[i] = word(i, rb);
+    }
+    __syncthreads();                                 // the oldest row's slot is refilled next
+  }
+}
+
+template <int KY, int KX>
+int launch_p2_direct(const P2Args& a, bool rolled, int64_t batch, cudaStream_t s) {
+  dim3 grid((a.wout + 255) / 256, (a.hout + a.th - 1) / a.th, (unsigned)batch);
+  if (rolled) patch2d_direct_kernel<KY, KX, true><<<grid, kPT, 0, s>>>(a);
+  else patch2d_direct_kernel<KY, KX, false><<<grid, kPT, 0, s>>>(a);
+  return after_launch("patch2d_direct_kernel");
+}
+
 template <int KY, int KX>
 int launch_p2(const P2Args& a, bool rolled, int64_t batch, cudaStream_t s) {
   if (KX <= 3 && a.aligned && a.lx >= 0 && a.lx <= KX - 1 && !getenv("KX_PATCH_BLOCK")) {
@@ -320,6 +384,17 @@ int try_patch2d(const MapArgs& m, const KxProgram& p, cudaStream_t s) {
   if (KY == 1 && KX == 3) return launch_p2<1, 3>(a, roll, batch, s);
   if (KY == 2 && KX == 2) return launch_p2<2, 2>(a, roll, batch, s);
   if (KY == 1 && KX == 5) return launch_p2<1, 5>(a, roll, batch, s);
+  if (KY == 5 && KX == 5) return launch_p2_direct<5, 5>(a, roll, batch, s);
+  if (KY == 7 && KX == 7) return launch_p2_direct<7, 7>(a, roll, batch, s);
+  if (KY == 4 && KX == 4) return launch_p2_direct<4, 4>(a, roll, batch, s);
+  if (KY == 3 && KX == 5) return launch_p2_direct<3, 5>(a, roll, batch, s);
+  if (KY == 5 && KX == 3) return launch_p2_direct<5, 3>(a, roll, batch, s);
+  if (KY == 2 && KX == 3) return launch_p2_direct<2, 3>(a, roll, batch, s);
+  if (KY == 3 && KX == 2) return launch_p2_direct<3, 2>(a, roll, batch, s);
+  if (KY == 1 && KX == 2) return launch_p2_direct<1, 2>(a, roll, batch, s);
+  if (KY == 1 && KX == 4) return launch_p2_direct<1, 4>(a, roll, batch, s);
+  if (KY == 1 && KX == 7) return launch_p2_direct<1, 7>(a, roll, batch, s);
+  if (KY == 1 && KX == 9) return launch_p2_direct<1, 9>(a, roll, batch, s);
   return KX_ERR_UNSUPPORTED;
 }
 
