@@ -370,8 +370,143 @@ int launch_generic_map(const MapArgs& a, const KxProgram& prog, cudaStream_t s) 
   return fail(KX_ERR_UNSUPPORTED, "dtype combination in=%d out=%d is not supported", in, out);
 }
 
+// ---------------------------------------------------- VJP (input), strided windows ----
+// Cotangent of the input of a STRIDED dense window (average / sum pooling, strided weighted windows): the gradient of
+// the README's avg-pool example.  generic_vjp_input_kernel tests every tap of every input element with 64-bit divisions
+// (0.013-0.018 of the HBM roofline on 3x3 stride-2 pooling of 8192^2); here a thread owns 4 consecutive input elements
+// of a row and walks ONLY the windows that contain them: input coordinate c of axis d lies in window j at tap t iff
+// j * S + t = c + lo, so t runs over (c + lo) mod S, +S, ... < K while j runs down from (c + lo) / S -- at most
+// ceil(K / S) windows per axis, 32-bit arithmetic throughout.  Same accumulation as the generic kernel (taps in
+// row-major order, one FMA each, the forward's final division last), so the two agree bit for bit.
+constexpr int kPVMaxTaps = 128;
+struct PVArgs {
+  const float* g;
+  float* dx;
+  int in_shape[3], out_shape[3], K[3], S[3], lo[3];   // trailing three axes (missing leading ones: size 1, K = S = 1)
+  int64_t in_elems, out_elems;                        // per batch item
+  float post_div;
+  float coef[kPVMaxTaps];                             // dense [K0][K1][K2]
+};
+
+// SS > 0: the stride of the last two axes is the compile-time constant SS (division = shifts / a multiply); 0: run time
+template <int VEC, int SS>
+__global__ void __launch_bounds__(kThreads)
+strided_vjp_input_kernel(const __grid_constant__ PVArgs a) {
+  const int S1 = SS > 0 ? SS : a.S[1], S2 = SS > 0 ? SS : a.S[2];
+  const int W = a.in_shape[2], H = a.in_shape[1];
+  const unsigned nvec = (unsigned)(a.in_elems / VEC);
+  const float* __restrict__ g = a.g + (int64_t)blockIdx.y * a.out_elems;
+  float* __restrict__ dx = a.dx + (int64_t)blockIdx.y * a.in_elems;
+  for (unsigned v = blockIdx.x * kThreads + threadIdx.x; v < nvec; v += gridDim.x * kThreads) {
+    const unsigned r = v * VEC;
+    const int x = (int)(r % (unsigned)W);
+    const unsigned yz = r / (unsigned)W;
+    const int y = (int)(yz % (unsigned)H), z = (int)(yz / (unsigned)H);
+    float acc[VEC];
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) acc[e] = 0.f;
+    const int qz = z + a.lo[0], qy = y + a.lo[1];
+    if (qz >= 0 && qy >= 0) {
+      const int tz0 = a.S[0] == 1 ? 0 : qz % a.S[0], jz0 = a.S[0] == 1 ? qz : qz / a.S[0];
+      for (int tz = tz0, jz = jz0; tz < a.K[0] && jz >= 0; tz += a.S[0], --jz) {
+        if (jz >= a.out_shape[0]) continue;
+        for (int ty = qy % S1, jy = qy / S1; ty < a.K[1] && jy >= 0; ty += S1, --jy) {
+          if (jy >= a.out_shape[1]) continue;
+          const float* grow = g + ((int64_t)jz * a.out_shape[1] + jy) * a.out_shape[2];
+          const float* crow = a.coef + (tz * a.K[1] + ty) * a.K[2];
+#pragma unroll
+          for (int e = 0; e < VEC; ++e) {
+            const int qx = x + e + a.lo[2];
+            if (qx < 0) continue;
+            for (int tx = qx % S2, jx = qx / S2; tx < a.K[2] && jx >= 0; tx += S2, --jx)
+              if (jx < a.out_shape[2]) acc[e] = fmaf(crow[tx], __ldg(grow + jx), acc[e]);
+          }
+        }
+      }
+    }
+    if (a.post_div != 0.f) {
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) acc[e] = acc[e] / a.post_div;
+    }
+    if (VEC == 4) {
+      __stcs(reinterpret_cast<float4*>(dx + r), make_float4(acc[0], acc[1], acc[2], acc[3]));
+    } else {
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) dx[r + e] = acc[e];
+    }
+  }
+}
+
+// dense host-coefficient windows over the trailing <= 3 axes, pure batch axes in front; anything else -> generic kernel
+int try_strided_vjp_input(const KxGeom& g, const KxProgram& p, const void* gout, const void* coef_dev, void* dx,
+                          cudaStream_t s) {
+  if (coef_dev || p.n_funcs != 1 || p.func[0].kind != KX_AFFINE || getenv("KX_NO_STRIDED_VJP")) return KX_ERR_UNSUPPORTED;
+  const int nd = g.ndim, nw = nd < 3 ? nd : 3, lead = nd - nw;
+  int64_t batch = 1;
+  for (int d = 0; d < lead; ++d) {
+    if (g.ksize[d] != 1 || g.stride[d] != 1 || g.lo[d] != 0 || g.hi[d] != 0) return KX_ERR_UNSUPPORTED;
+    batch *= g.in_shape[d];
+  }
+  static thread_local PVArgs a;
+  memset(&a, 0, sizeof(a));
+  int64_t ntap = 1;
+  a.in_elems = a.out_elems = 1;
+  for (int i = 0; i < 3; ++i) {
+    const int d = lead + i - (3 - nw);
+    if (i < 3 - nw) {
+      a.in_shape[i] = a.out_shape[i] = a.K[i] = a.S[i] = 1;
+      a.lo[i] = 0;
+    } else {
+      if (g.in_shape[d] > 0x3fffffff || g.out_shape[d] > 0x3fffffff) return KX_ERR_UNSUPPORTED;
+      a.in_shape[i] = (int)g.in_shape[d];
+      a.out_shape[i] = (int)g.out_shape[d];
+      a.K[i] = g.ksize[d];
+      a.S[i] = g.stride[d];
+      a.lo[i] = g.lo[d];
+    }
+    ntap *= a.K[i];
+    a.in_elems *= a.in_shape[i];
+    a.out_elems *= a.out_shape[i];
+  }
+  const KxFunc& f = p.func[0];
+  if (ntap > kPVMaxTaps || f.tap_end - f.tap_begin != ntap) return KX_ERR_UNSUPPORTED;      // dense windows only
+  if (a.in_elems <= 0 || a.in_elems > 0xfffffff0ll || batch > 65535 || batch < 1) return KX_ERR_UNSUPPORTED;
+  for (int t = f.tap_begin; t < f.tap_end; ++t) {
+    int idx = 0;
+    for (int i = 3 - nw; i < 3; ++i) idx = idx * a.K[i] + p.tap_off[t][lead + i - (3 - nw)];
+    if (t - f.tap_begin != idx) return KX_ERR_UNSUPPORTED;   // row-major tap order = the generic kernel's accumulation order
+    a.coef[idx] = (float)p.coef[t];
+  }
+  a.g = (const float*)gout;
+  a.dx = (float*)dx;
+  a.post_div = (float)f.post_div;
+  if (a.out_elems == 0) {
+    KX_CUDA_CHECK(cudaMemsetAsync(dx, 0, (size_t)(a.in_elems * batch) * 4, s));
+    return KX_OK;
+  }
+  const bool vec = a.in_shape[2] % 4 == 0 && (reinterpret_cast<uintptr_t>(dx) & 15) == 0;
+  const int64_t nvec = a.in_elems / (vec ? 4 : 1);
+  int64_t blocks = (nvec + kThreads - 1) / kThreads;
+  const int64_t cap = (int64_t)sm_count() * 32;
+  if (blocks > cap) blocks = cap;
+  dim3 grid((unsigned)blocks, (unsigned)batch);
+  const int ss = (a.S[1] == a.S[2] || a.in_shape[1] == 1) ? a.S[2] : 0;   // 1-D windows: axis 1 has one row, any stride does
+  if (a.in_shape[1] == 1) a.S[1] = a.S[2];
+  if (vec && ss == 2) strided_vjp_input_kernel<4, 2><<<grid, kThreads, 0, s>>>(a);
+  else if (vec && ss == 3) strided_vjp_input_kernel<4, 3><<<grid, kThreads, 0, s>>>(a);
+  else if (vec && ss == 4) strided_vjp_input_kernel<4, 4><<<grid, kThreads, 0, s>>>(a);
+  else if (vec) strided_vjp_input_kernel<4, 0><<<grid, kThreads, 0, s>>>(a);
+  else if (ss == 2) strided_vjp_input_kernel<1, 2><<<grid, kThreads, 0, s>>>(a);
+  else strided_vjp_input_kernel<1, 0><<<grid, kThreads, 0, s>>>(a);
+  return after_launch("strided_vjp_input_kernel");
+}
+
 int launch_generic_vjp_input(const KxGeom& g, const KxProgram& prog, const void* gout, const void* coef_dev,
                              void* dx, cudaStream_t s) {
+  {
+    const int rc = try_strided_vjp_input(g, prog, gout, coef_dev, dx, s);
+    if (rc != KX_ERR_UNSUPPORTED) return rc;
+  }
   static thread_local DevProgram<float> dp;
   make_dev_program<float>(prog, g.ndim, dp);
   const int64_t n_in = prod(g.in_shape, g.ndim);

@@ -62,10 +62,14 @@ def test_input_vjp_matches_transpose(kex, case):
 
 @pytest.mark.parametrize("fn_name", ["sum", "mean", "weighted"])
 @pytest.mark.parametrize("geom", [((17, 20), (3, 3), (2, 2), "same"), ((31, 44), (2, 2), (2, 2), "valid"),
-                                  ((12, 9, 14), (2, 3, 2), (2, 1, 2), "same"), ((101,), (4,), (3,), ((2, 1),))])
-def test_strided_input_vjp_generic_kernel(kex, fn_name, geom):
-    """Strided windows take generic_vjp_input_kernel; `mean` carries the forward's final division
-    (KxFunc.post_div) into the cotangent -- the average-pool gradient of README.md:327-337."""
+                                  ((12, 9, 14), (2, 3, 2), (2, 1, 2), "same"), ((101,), (4,), (3,), ((2, 1),)),
+                                  ((64, 260), (3, 3), (2, 2), ((1, 1), (1, 1))), ((40, 128), (4, 4), (4, 4), "valid"),
+                                  ((33, 64), (3, 3), (3, 3), ((-1, 2), (0, -2))), ((9, 20, 36), (3, 3, 3), (2, 2, 2), "same"),
+                                  ((5, 24, 40), (1, 3, 3), (1, 2, 2), ((0, 0), (1, 0), (0, 1)))])
+def test_strided_input_vjp_generic_kernel(kex, fn_name, geom, monkeypatch):
+    """Strided dense windows take strided_vjp_input_kernel (a thread walks only the windows that contain its input
+    elements); `mean` carries the forward's final division (KxFunc.post_div) into the cotangent -- the average-pool
+    gradient of README.md:327-337.  Same accumulation order as generic_vjp_input_kernel: bit-identical to it."""
     from kernex_b200 import _lib
     shape, ksize, strides, pad = geom
     rng = np.random.default_rng(5)
@@ -82,10 +86,14 @@ def test_strided_input_vjp_generic_kernel(kex, fn_name, geom):
     x = torch.from_numpy(rng.standard_normal(shape).astype(np.float32)).cuda().requires_grad_()
     y = kex.kmap(kernel_size=ksize, strides=strides, padding=pad)(fn)(x)
     g = torch.from_numpy(rng.standard_normal(tuple(y.shape)).astype(np.float32)).cuda()
-    (dx,) = torch.autograd.grad(y, x, g)
-    assert _lib.last_kernel() == "generic_vjp_input_kernel"
+    (dx,) = torch.autograd.grad(y, x, g, retain_graph=True)
+    assert _lib.last_kernel() == "strided_vjp_input_kernel"
     want, mag = dx_reference(g.cpu().numpy(), shape, ksize, strides, border, taps, coefs, div)
     assert_within(dx.cpu().numpy(), want, mag, f"dx[{fn_name}]")
+    monkeypatch.setenv("KX_NO_STRIDED_VJP", "1")
+    (dx2,) = torch.autograd.grad(y, x, g)
+    assert _lib.last_kernel() == "generic_vjp_input_kernel"
+    assert torch.equal(dx, dx2)
 
 
 @pytest.mark.parametrize("strides", [(1, 1), (2, 2)])
