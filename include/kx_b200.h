@@ -142,6 +142,12 @@ int kx_map(const KxGeom* geom, const KxProgram* prog, const void* in, const void
  * launcher either runs one fused pass (stride 1, single AFFINE function: every cell is produced by
  * the stencil kernel, cells outside the interior copy their input value) or enqueues the
  * device-to-device copy itself followed by the strided write-back kernel. */
+/* int32 -> float32 conversion of a whole device array (16-byte aligned), round to nearest even.  JAX converts an int32
+ * window before it applies a float-valued function (weak-type promotion, SURVEY 9.8 R: jnp.mean of integers, Python
+ * float coefficients; kernex/_src/map.py:46 gathers the patch, the user function promotes it), so the host side
+ * converts once and runs the float32 templates. */
+int kx_cast_i32_f32(const void* in, void* out, int64_t n, void* stream);
+
 int kx_map_offset(const KxGeom* geom, const KxProgram* prog, const void* in, const void* coef_dev,
                   const int32_t* off0, void* out, void* stream);
 

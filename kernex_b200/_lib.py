@@ -94,6 +94,7 @@ _SIGNATURES = {
     "kx_last_kernel": (C.c_char_p, []),
     "kx_map": (C.c_int, [C.POINTER(KxGeom), C.POINTER(KxProgram), C.c_void_p, C.c_void_p, C.c_int64,
                          C.c_void_p, C.c_int64, C.c_void_p]),
+    "kx_cast_i32_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "kx_map_offset": (C.c_int, [C.POINTER(KxGeom), C.POINTER(KxProgram), C.c_void_p, C.c_void_p,
                                 C.POINTER(C.c_int32), C.c_void_p, C.c_void_p]),
     "kx_map_vjp_input": (C.c_int, [C.POINTER(KxGeom), C.POINTER(KxProgram), C.c_void_p, C.c_void_p,

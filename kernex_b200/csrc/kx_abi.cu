@@ -349,7 +349,31 @@ int vjp_input_full_depth(const KxGeom& g, const KxProgram& p, int C, int NT, con
 
 }  // namespace
 
+__global__ void __launch_bounds__(256) cast_i32_f32_kernel(const int32_t* __restrict__ in, float* __restrict__ out, int64_t n) {
+  const int64_t nv = n >> 2;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < nv; i += (int64_t)gridDim.x * 256) {
+    const int4 v = __ldg(reinterpret_cast<const int4*>(in) + i);
+    __stcs(reinterpret_cast<float4*>(out) + i, make_float4((float)v.x, (float)v.y, (float)v.z, (float)v.w));
+  }
+  for (int64_t i = (nv << 2) + (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) out[i] = (float)in[i];
+}
+
 extern "C" {
+
+// int32 -> float32, round to nearest even like XLA's convert: the first thing JAX does to an int32 window when the
+// function's result is float (jnp.mean of integers, a Python-float coefficient): lets those calls take the float32 fast
+// templates instead of the generic kernel (engine.py _run_map).  in / out: device, 16-byte aligned, n elements.
+int kx_cast_i32_f32(const void* in, void* out, int64_t n, void* stream) {
+  if (n <= 0) return KX_OK;
+  if (!in || !out) return fail(KX_ERR_INVALID, "null device pointer");
+  if ((reinterpret_cast<uintptr_t>(in) & 15) || (reinterpret_cast<uintptr_t>(out) & 15)) return fail(KX_ERR_INVALID, "unaligned buffer");
+  DeviceGuard guard(out);
+  int64_t blocks = ((n >> 2) + 255) / 256 + 1;
+  const int64_t cap = (int64_t)sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  cast_i32_f32_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const int32_t*)in, (float*)out, n);
+  return after_launch("cast_i32_f32_kernel");
+}
 
 int kx_abi_version(void) { return KX_ABI_VERSION; }
 const char* kx_last_error(void) { return err_buf(); }

@@ -357,6 +357,7 @@ class _AffineMapFn(torch.autograd.Function):
 
 _PLAN_CACHE: "dict[tuple, tuple]" = {}
 _PLAN_CACHE_MAX = 128
+_PROMOTE_MIN = 1 << 16      # int32 arrays with a float32 result: convert first from this many elements on
 _PLAN_GEN = [0]
 
 
@@ -590,6 +591,16 @@ def _run_map(func_map, shape, kernel_size, strides, border, relative, array, a, 
         raise ValueError(f"array shape {tuple(arr.t.shape)} != declared shape {tuple(shape)}")
     specs, device_args, out_kx, prog, geom, full_shape = _map_plan(
         func_map, shape, kernel_size, strides, border, relative, arr.kx_dtype, a, k, static)
+    if arr.kx_dtype == _lib.KX_I32 and out_kx == _lib.KX_F32 and arr.t.numel() >= _PROMOTE_MIN \
+            and all(s.kind == "affine" for s in specs):
+        # int32 array, float result (jnp.mean of integers, a Python-float coefficient): JAX converts the window to
+        # float32 before the arithmetic, so convert the ARRAY once (kx_cast_i32_f32) and run the float32 templates; the
+        # mixed-dtype form exists only in the generic kernel (0.04-0.06 of the HBM roofline on 8192^2)
+        t32 = torch.empty(arr.t.shape, dtype=torch.float32, device=arr.t.device)
+        _lib.check(_lib.load().kx_cast_i32_f32(_ptr(arr.t), _ptr(t32), arr.t.numel(), _stream_ptr(arr.t.device)))
+        arr.t, arr.kx_dtype = t32, _lib.KX_F32
+        specs, device_args, out_kx, prog, geom, full_shape = _map_plan(
+            func_map, shape, kernel_size, strides, border, relative, _lib.KX_F32, a, k, static)
     comp_dtype = _KX2TORCH[out_kx]
     coef = prog.coef_tensor(device_args, comp_dtype, arr.t.device)
     needs_grad = torch.is_grad_enabled() and (arr.t.requires_grad or (coef is not None and coef.requires_grad))
