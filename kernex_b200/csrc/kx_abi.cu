@@ -240,6 +240,8 @@ int dispatch_map(const MapArgs& a, const KxProgram& prog, cudaStream_t s) {
   if (rc != KX_ERR_UNSUPPORTED) return rc;
   rc = try_patch2d(a, prog, s);
   if (rc != KX_ERR_UNSUPPORTED) return rc;
+  rc = try_patch3d(a, prog, s);
+  if (rc != KX_ERR_UNSUPPORTED) return rc;
   rc = try_patch(a, prog, s);
   if (rc != KX_ERR_UNSUPPORTED) return rc;
   rc = try_pool2d(a, prog, s);

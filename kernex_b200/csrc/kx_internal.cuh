@@ -120,6 +120,7 @@ int try_stencil3d(const MapArgs& a, const KxProgram& prog, cudaStream_t s);
 int try_stencil3d_star(const MapArgs& a, const KxProgram& prog, int64_t batch, cudaStream_t s);
 int try_patch(const MapArgs& a, const KxProgram& prog, cudaStream_t s);
 int try_patch2d(const MapArgs& a, const KxProgram& prog, cudaStream_t s);
+int try_patch3d(const MapArgs& a, const KxProgram& prog, cudaStream_t s);
 int try_conv2d(const MapArgs& a, const KxProgram& prog, cudaStream_t s);
 int try_convc(const MapArgs& a, const KxProgram& prog, cudaStream_t s);
 int try_conv_dense3d(const MapArgs& a, const KxProgram& prog, int64_t batch, cudaStream_t s);

@@ -334,6 +334,129 @@ int launch_p2(const P2Args& a, bool rolled, int64_t batch, cudaStream_t s) {
   return after_launch("patch2d_kernel");
 }
 
+// ---------------------------------------------------------------------------------------------
+// 3-D windows (3x3x3, 2x2x2 patches of a volume: 4 B read + 4 KZ KY KX B written per window): patch2d_direct_kernel with
+// KZ planes in the ring -- a block owns 256 windows of an output row, marches down a band of rows of ONE output plane
+// and fetches KZ new input row segments (one per window plane) per output row; the rows of neighbouring output planes
+// are re-read by their own blocks (L2 hits, and 3 x 4 B against 108 B written per window for 3x3x3).
+template <int KZ, int KY, int KX, bool ROLLED>
+__global__ void __launch_bounds__(kPT)
+patch3d_direct_kernel(const __grid_constant__ P2Args a, int din, int dout, int lz) {
+  constexpr int NT = KZ * KY * KX;
+  constexpr int TW = 256;
+  constexpr int PW = TW + ((KX - 1 + 3) / 4) * 4;
+  __shared__ __align__(16) uint32_t rows[KZ][KY][PW];
+  const int tid = threadIdx.x;
+  const int x0 = blockIdx.x * TW;
+  const int r0 = blockIdx.y * a.th, r1 = min(r0 + a.th, a.hout);
+  const int b = blockIdx.z / dout, z = blockIdx.z - b * dout;
+  const uint32_t* __restrict__ in = a.in + (int64_t)b * a.in_batch;
+  uint32_t* __restrict__ out = a.out + (int64_t)b * a.out_batch + (int64_t)z * a.hout * a.wout * NT;
+  const int nwin = min(TW, a.wout - x0);
+  const int count = nwin * NT;
+  const int64_t plane = (int64_t)a.hin * a.win;
+  auto load_rows = [&](int iy, int slot) {           // input row iy of the KZ window planes -> ring slot
+    const bool row_ok = (iy >= 0) && (iy < a.hin);
+#pragma unroll
+    for (int kz = 0; kz < KZ; ++kz) {
+      const int iz = z - lz + kz;
+      const bool ok = row_ok && iz >= 0 && iz < din;
+      const uint32_t* rp = in + (int64_t)iz * plane + (int64_t)iy * a.win;
+      for (int c = tid; c < TW + KX - 1; c += kPT) {
+        const int gx = x0 - a.lx + c;
+        rows[kz][slot][c] = (ok && gx >= 0 && gx < a.win) ? __ldg(rp + gx) : 0u;
+      }
+    }
+  };
+  auto word = [&](int i, int rb) -> uint32_t {
+    const int w = i / NT, t = i - w * NT;
+    const int tz = t / (KY * KX), t2 = t - tz * (KY * KX);
+    const int ty = t2 / KX, tx = t2 - ty * KX;
+    const int sz = ROLLED ? (tz + (KZ - 1) / 2) % KZ : tz;
+    const int sy = ROLLED ? (ty + (KY - 1) / 2) % KY : ty;
+    const int sx = ROLLED ? (tx + (KX - 1) / 2) % KX : tx;
+    int slot = rb + sy;
+    if (slot >= KY) slot -= KY;
+    return rows[sz][slot][w + sx];
+  };
+#pragma unroll 1
+  for (int ky = 0; ky < KY - 1; ++ky) load_rows(r0 - a.ly + ky, (r0 + ky) % KY);
+  for (int r = r0; r < r1; ++r) {
+    load_rows(r - a.ly + KY - 1, (r + KY - 1) % KY);
+    __syncthreads();
+    const int rb = r % KY;
+    uint32_t* dst = out + ((int64_t)r * a.wout + x0) * NT;
+    if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+      for (int v = tid; 4 * v + 3 < count; v += kPT)
+        __stcs(reinterpret_cast<uint4*>(dst) + v, make_uint4(word(4 * v, rb), word(4 * v + 1, rb), word(4 * v + 2, rb), word(4 * v + 3, rb)));
+      for (int i = (count & ~3) + tid; i < count; i += kPT) dst[i] = word(i, rb);
+    } else {
+      for (int i = tid; i < count; i += kPT) dst[i] = word(i, rb);
+    }
+    __syncthreads();
+  }
+}
+
+template <int KZ, int KY, int KX>
+int launch_p3_direct(const P2Args& a, int din, int dout, int lz, bool rolled, int64_t batch, cudaStream_t s) {
+  dim3 grid((a.wout + 255) / 256, (a.hout + a.th - 1) / a.th, (unsigned)(batch * dout));
+  if (rolled) patch3d_direct_kernel<KZ, KY, KX, true><<<grid, kPT, 0, s>>>(a, din, dout, lz);
+  else patch3d_direct_kernel<KZ, KY, KX, false><<<grid, kPT, 0, s>>>(a, din, dout, lz);
+  return after_launch("patch3d_direct_kernel");
+}
+
+}  // namespace
+
+// dense patch extraction over the last THREE axes (stride 1), plain or rolled tap order
+int try_patch3d(const MapArgs& m, const KxProgram& p, cudaStream_t s) {
+  const KxGeom& g = m.g;
+  const int nd = g.ndim;
+  if (nd < 3 || p.n_funcs != 1 || p.func[0].kind != KX_GATHER || g.in_dtype != g.out_dtype) return KX_ERR_UNSUPPORTED;
+  const int az = nd - 3, ay = nd - 2, ax = nd - 1;
+  int64_t lead = 1;
+  for (int d = 0; d < az; ++d) {
+    if (g.ksize[d] != 1 || g.stride[d] != 1 || g.lo[d] != 0 || g.hi[d] != 0) return KX_ERR_UNSUPPORTED;
+    lead *= g.in_shape[d];
+  }
+  if (g.stride[az] != 1 || g.stride[ay] != 1 || g.stride[ax] != 1) return KX_ERR_UNSUPPORTED;
+  const int KZ = g.ksize[az], KY = g.ksize[ay], KX = g.ksize[ax];
+  if (KZ < 2) return KX_ERR_UNSUPPORTED;                       // 2-D windows: try_patch2d
+  const KxFunc& f = p.func[0];
+  if (f.tap_end - f.tap_begin != KZ * KY * KX) return KX_ERR_UNSUPPORTED;
+  bool plain = true, rolled = true;
+  for (int t = 0; t < KZ * KY * KX; ++t) {
+    const int tz = t / (KY * KX), ty = (t / KX) % KY, tx = t % KX;
+    const int oz = p.tap_off[f.tap_begin + t][az], oy = p.tap_off[f.tap_begin + t][ay], ox = p.tap_off[f.tap_begin + t][ax];
+    if (oz != tz || oy != ty || ox != tx) plain = false;
+    if (oz != (tz + (KZ - 1) / 2) % KZ || oy != (ty + (KY - 1) / 2) % KY || ox != (tx + (KX - 1) / 2) % KX) rolled = false;
+    for (int d = 0; d < az; ++d)
+      if (p.tap_off[f.tap_begin + t][d] != 0) return KX_ERR_UNSUPPORTED;
+  }
+  if (!plain && !rolled) return KX_ERR_UNSUPPORTED;
+  const int64_t batch = m.batch * lead;
+  if (g.in_shape[ax] > 0x3fffffff || g.in_shape[ay] > 0x3fffffff || g.in_shape[az] > 0x3fffffff) return KX_ERR_UNSUPPORTED;
+  if (batch * g.out_shape[az] > 65535) return KX_ERR_UNSUPPORTED;
+  P2Args a;
+  memset(&a, 0, sizeof(a));
+  a.in = (const uint32_t*)m.in;
+  a.out = (uint32_t*)m.out;
+  a.hin = (int)g.in_shape[ay];
+  a.win = (int)g.in_shape[ax];
+  a.hout = (int)g.out_shape[ay];
+  a.wout = (int)g.out_shape[ax];
+  a.ly = g.lo[ay];
+  a.lx = g.lo[ax];
+  a.in_batch = (int64_t)g.in_shape[az] * a.hin * a.win;
+  a.out_batch = (int64_t)g.out_shape[az] * a.hout * a.wout * KZ * KY * KX;
+  a.th = a.hout >= 64 ? 16 : 4;
+  while ((a.hout + a.th - 1) / a.th > 65535) a.th *= 2;
+  const int din = (int)g.in_shape[az], dout = (int)g.out_shape[az], lz = g.lo[az];
+  if (KZ == 3 && KY == 3 && KX == 3) return launch_p3_direct<3, 3, 3>(a, din, dout, lz, !plain, batch, s);
+  if (KZ == 2 && KY == 2 && KX == 2) return launch_p3_direct<2, 2, 2>(a, din, dout, lz, !plain, batch, s);
+  return KX_ERR_UNSUPPORTED;
+}
+
+namespace {
 }  // namespace
 
 int try_patch2d(const MapArgs& m, const KxProgram& p, cudaStream_t s) {

@@ -63,3 +63,31 @@ def test_wide_patches_batched_and_large(kex):
     assert _last_kernel() == "patch2d_direct_kernel"
     win = np.lib.stride_tricks.sliding_window_view(x, (1, 5, 5), axis=(0, 1, 2))
     np.testing.assert_array_equal(got, win)
+
+
+@pytest.mark.parametrize("ksize", [(3, 3, 3), (2, 2, 2)])
+@pytest.mark.parametrize("relative", [False, True])
+def test_patches_3d_match_oracle(kex, ksize, relative):
+    """3-D windows (patch3d_direct_kernel): 'same', 'valid' and mixed borders, ragged widths, int32 and float32."""
+    rng = np.random.default_rng(sum(ksize) + relative)
+    for case, (shape, border) in enumerate([
+            ((9, 14, 300), tuple(((k - 1) // 2, k // 2) for k in ksize)),
+            ((7, 11, 261), ((0, 0), (0, 0), (0, 0))),
+            ((6, 20, 64), ((1, 0), (0, 1), (2, 1)))]):
+        x = rng.integers(-1000, 1000, shape).astype(np.int32) if case % 2 else rng.standard_normal(shape).astype(np.float32)
+        fmap = {(lambda v: v): ()}
+        want = ko.kernel_map(fmap, shape, ksize, (1, 1, 1), border, relative)(x)
+        got = kex.kernel_map(fmap, shape, ksize, (1, 1, 1), border, relative)(x)
+        assert _last_kernel() == "patch3d_direct_kernel", (ksize, case, _last_kernel())
+        assert got.shape == want.shape and got.dtype == want.dtype
+        np.testing.assert_array_equal(got, want)
+
+
+def test_patches_3d_batched(kex):
+    rng = np.random.default_rng(4)
+    x = rng.standard_normal((2, 20, 30, 260)).astype(np.float32)
+    f = kex.kmap(kernel_size=(1, 3, 3, 3), padding=("valid", "valid", "valid", "valid"))(lambda v: v)
+    got = f(torch.from_numpy(x).cuda()).cpu().numpy()
+    assert _last_kernel() == "patch3d_direct_kernel"
+    win = np.lib.stride_tricks.sliding_window_view(x, (1, 3, 3, 3), axis=(0, 1, 2, 3))
+    np.testing.assert_array_equal(got, win)
