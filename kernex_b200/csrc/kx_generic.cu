@@ -389,10 +389,13 @@ struct PVArgs {
 };
 
 // SS > 0: the stride of the last two axes is the compile-time constant SS (division = shifts / a multiply); 0: run time
-template <int VEC, int SS>
+// KK > 0 (needs SS > 0): the window of the last two axes is KK x KK: the tap loops unroll into ceil(KK / SS) predicated steps
+template <int VEC, int SS, int KK>
 __global__ void __launch_bounds__(kThreads)
 strided_vjp_input_kernel(const __grid_constant__ PVArgs a) {
   const int S1 = SS > 0 ? SS : a.S[1], S2 = SS > 0 ? SS : a.S[2];
+  const int K1 = KK > 0 ? KK : a.K[1], K2 = KK > 0 ? KK : a.K[2];
+  constexpr int NI = (KK > 0 && SS > 0) ? (KK + SS - 1) / SS : 1;
   const int W = a.in_shape[2], H = a.in_shape[1];
   const unsigned nvec = (unsigned)(a.in_elems / VEC);
   const float* __restrict__ g = a.g + (int64_t)blockIdx.y * a.out_elems;
@@ -410,16 +413,38 @@ strided_vjp_input_kernel(const __grid_constant__ PVArgs a) {
       const int tz0 = a.S[0] == 1 ? 0 : qz % a.S[0], jz0 = a.S[0] == 1 ? qz : qz / a.S[0];
       for (int tz = tz0, jz = jz0; tz < a.K[0] && jz >= 0; tz += a.S[0], --jz) {
         if (jz >= a.out_shape[0]) continue;
-        for (int ty = qy % S1, jy = qy / S1; ty < a.K[1] && jy >= 0; ty += S1, --jy) {
-          if (jy >= a.out_shape[1]) continue;
-          const float* grow = g + ((int64_t)jz * a.out_shape[1] + jy) * a.out_shape[2];
-          const float* crow = a.coef + (tz * a.K[1] + ty) * a.K[2];
+        if constexpr (KK > 0 && SS > 0) {
+          const int ty0 = qy % SS, jy0 = qy / SS;
 #pragma unroll
-          for (int e = 0; e < VEC; ++e) {
-            const int qx = x + e + a.lo[2];
-            if (qx < 0) continue;
-            for (int tx = qx % S2, jx = qx / S2; tx < a.K[2] && jx >= 0; tx += S2, --jx)
-              if (jx < a.out_shape[2]) acc[e] = fmaf(crow[tx], __ldg(grow + jx), acc[e]);
+          for (int iy = 0; iy < NI; ++iy) {
+            const int ty = ty0 + iy * SS, jy = jy0 - iy;
+            if (ty >= KK || jy < 0 || jy >= a.out_shape[1]) continue;
+            const float* grow = g + ((int64_t)jz * a.out_shape[1] + jy) * a.out_shape[2];
+            const float* crow = a.coef + (tz * KK + ty) * KK;
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) {
+              const int qx = x + e + a.lo[2];
+              if (qx < 0) continue;
+              const int tx0 = qx % SS, jx0 = qx / SS;
+#pragma unroll
+              for (int ix = 0; ix < NI; ++ix) {
+                const int tx = tx0 + ix * SS, jx = jx0 - ix;
+                if (tx < KK && jx >= 0 && jx < a.out_shape[2]) acc[e] = fmaf(crow[tx], __ldg(grow + jx), acc[e]);
+              }
+            }
+          }
+        } else {
+          for (int ty = qy % S1, jy = qy / S1; ty < K1 && jy >= 0; ty += S1, --jy) {
+            if (jy >= a.out_shape[1]) continue;
+            const float* grow = g + ((int64_t)jz * a.out_shape[1] + jy) * a.out_shape[2];
+            const float* crow = a.coef + (tz * K1 + ty) * K2;
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) {
+              const int qx = x + e + a.lo[2];
+              if (qx < 0) continue;
+              for (int tx = qx % S2, jx = qx / S2; tx < K2 && jx >= 0; tx += S2, --jx)
+                if (jx < a.out_shape[2]) acc[e] = fmaf(crow[tx], __ldg(grow + jx), acc[e]);
+            }
           }
         }
       }
@@ -492,12 +517,18 @@ int try_strided_vjp_input(const KxGeom& g, const KxProgram& p, const void* gout,
   dim3 grid((unsigned)blocks, (unsigned)batch);
   const int ss = (a.S[1] == a.S[2] || a.in_shape[1] == 1) ? a.S[2] : 0;   // 1-D windows: axis 1 has one row, any stride does
   if (a.in_shape[1] == 1) a.S[1] = a.S[2];
-  if (vec && ss == 2) strided_vjp_input_kernel<4, 2><<<grid, kThreads, 0, s>>>(a);
-  else if (vec && ss == 3) strided_vjp_input_kernel<4, 3><<<grid, kThreads, 0, s>>>(a);
-  else if (vec && ss == 4) strided_vjp_input_kernel<4, 4><<<grid, kThreads, 0, s>>>(a);
-  else if (vec) strided_vjp_input_kernel<4, 0><<<grid, kThreads, 0, s>>>(a);
-  else if (ss == 2) strided_vjp_input_kernel<1, 2><<<grid, kThreads, 0, s>>>(a);
-  else strided_vjp_input_kernel<1, 0><<<grid, kThreads, 0, s>>>(a);
+  const int kk = (a.K[1] == a.K[2] && a.in_shape[1] > 1) ? a.K[2] : 0;
+  if (vec && ss == 2 && kk == 2) strided_vjp_input_kernel<4, 2, 2><<<grid, kThreads, 0, s>>>(a);
+  else if (vec && ss == 2 && kk == 3) strided_vjp_input_kernel<4, 2, 3><<<grid, kThreads, 0, s>>>(a);
+  else if (vec && ss == 2 && kk == 4) strided_vjp_input_kernel<4, 2, 4><<<grid, kThreads, 0, s>>>(a);
+  else if (vec && ss == 3 && kk == 3) strided_vjp_input_kernel<4, 3, 3><<<grid, kThreads, 0, s>>>(a);
+  else if (vec && ss == 4 && kk == 4) strided_vjp_input_kernel<4, 4, 4><<<grid, kThreads, 0, s>>>(a);
+  else if (vec && ss == 2) strided_vjp_input_kernel<4, 2, 0><<<grid, kThreads, 0, s>>>(a);
+  else if (vec && ss == 3) strided_vjp_input_kernel<4, 3, 0><<<grid, kThreads, 0, s>>>(a);
+  else if (vec && ss == 4) strided_vjp_input_kernel<4, 4, 0><<<grid, kThreads, 0, s>>>(a);
+  else if (vec) strided_vjp_input_kernel<4, 0, 0><<<grid, kThreads, 0, s>>>(a);
+  else if (ss == 2) strided_vjp_input_kernel<1, 2, 0><<<grid, kThreads, 0, s>>>(a);
+  else strided_vjp_input_kernel<1, 0, 0><<<grid, kThreads, 0, s>>>(a);
   return after_launch("strided_vjp_input_kernel");
 }
 
