@@ -182,6 +182,15 @@ int64_t kx_scan_state_bytes(const KxGeom* geom);
 int kx_scan(const KxGeom* geom, const KxProgram* prog, const void* in, const void* coef_dev,
             void* state, void* out, int32_t reverse, void* stream);
 
+/* Offset scan (sscan) in ONE call: replaces offset_kernel_scan (kernex/_src/scan.py:118-147) -- kernel_scan over the
+ * offset interior followed by `.at[set_indices].set(result)` into a copy of the input.  `out` has geom.in_shape; off0[d]
+ * is the low offset of axis d (geom.lo / geom.hi carry the borders _offset_to_padding derives from the offsets).
+ * Implemented for 3-D time-marching scans (one AFFINE function reading only the plane above the cell it writes,
+ * tests/test_interface.py:28-97): one fused 2-D pass per plane.  Anything else returns KX_ERR_UNSUPPORTED and the
+ * caller composes kx_scan with a strided write-back. */
+int kx_scan_offset(const KxGeom* geom, const KxProgram* prog, const void* in, const void* coef_dev, const int32_t* off0,
+                   void* out, void* stream);
+
 /* Axis-1 shard of a row-marching kscan (time-marching stencils, README.md:231-266): produces
  * columns [col_base, col_base + geom.in_shape[1]) of the scan kernel_scan would run on a
  * (geom.in_shape[0], global_nx) array; region keys and the zero pad are in GLOBAL columns.

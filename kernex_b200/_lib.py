@@ -105,6 +105,8 @@ _SIGNATURES = {
     "kx_scan_state_bytes": (C.c_int64, [C.POINTER(KxGeom)]),
     "kx_scan": (C.c_int, [C.POINTER(KxGeom), C.POINTER(KxProgram), C.c_void_p, C.c_void_p, C.c_void_p,
                           C.c_void_p, C.c_int32, C.c_void_p]),
+    "kx_scan_offset": (C.c_int, [C.POINTER(KxGeom), C.POINTER(KxProgram), C.c_void_p, C.c_void_p, C.POINTER(C.c_int32),
+                                 C.c_void_p, C.c_void_p]),
     "kx_scan_rowmarch_shard": (C.c_int, [C.POINTER(KxGeom), C.POINTER(KxProgram), C.c_int64, C.c_int64,
                                          C.c_void_p, C.c_void_p]),
     "kx_scan_rowmarch_rows_per_launch": (C.c_int, []),

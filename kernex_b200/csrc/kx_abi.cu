@@ -351,6 +351,232 @@ int vjp_input_full_depth(const KxGeom& g, const KxProgram& p, int C, int NT, con
 
 }  // namespace
 
+// rows x width 32-bit words, pitches in words (cudaMemcpy2D / 3D device-to-device copies of unaligned pitched rows ran at
+// ~0.3 TB/s here)
+__global__ void __launch_bounds__(256) copy2d_kernel(uint32_t* __restrict__ dst, int64_t dpitch, const uint32_t* __restrict__ src,
+                                                     int64_t spitch, int width, int64_t rows) {
+  const int64_t total = rows * width;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
+    const int64_t r = i / width;
+    const int c = (int)(i - r * width);
+    dst[r * dpitch + c] = __ldg(src + r * spitch + c);
+  }
+}
+
+int copy2d(void* dst, int64_t dpitch, const void* src, int64_t spitch, int64_t width, int64_t rows, cudaStream_t s) {
+  if (width <= 0 || rows <= 0) return KX_OK;
+  if (dpitch == width && spitch == width) {
+    KX_CUDA_CHECK(cudaMemcpyAsync(dst, src, (size_t)(rows * width) * 4, cudaMemcpyDeviceToDevice, s));
+    return KX_OK;
+  }
+  int64_t blocks = (rows * width + 255) / 256;
+  const int64_t cap = (int64_t)sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  copy2d_kernel<<<(unsigned)blocks, 256, 0, s>>>((uint32_t*)dst, dpitch, (const uint32_t*)src, spitch, (int)width, rows);
+  return after_launch("copy2d_kernel");
+}
+
+// the cells of an H x W plane OUTSIDE the box [y0, y1) x [x0, x1): dst <- src (the ring an offset scan leaves untouched)
+__global__ void __launch_bounds__(256) ring_copy_kernel(uint32_t* __restrict__ dst, const uint32_t* __restrict__ src, int H, int W,
+                                                        int y0, int y1, int x0, int x1) {
+  const int ring_w = x0 + (W - x1);                      // ring cells of a row that crosses the box
+  const int64_t full_rows = (int64_t)y0 + (H - y1);
+  const int64_t total = full_rows * W + (int64_t)(y1 - y0) * ring_w;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
+    int64_t r, c;
+    if (i < full_rows * W) {
+      r = i / W;
+      c = i - r * W;
+      if (r >= y0) r += y1 - y0;
+    } else {
+      const int64_t k = i - full_rows * W;
+      r = y0 + k / ring_w;
+      c = k - (k / ring_w) * ring_w;
+      if (c >= x0) c += x1 - x0;
+    }
+    dst[r * W + c] = __ldg(src + r * W + c);
+  }
+}
+
+// kscan / sscan over a 3-D array whose function reads only the PLANE ABOVE the cell it writes (axis-0 offset -1 from the
+// window centre): explicit time marching with two space axes -- the reference's own diffusion test
+// (tests/test_interface.py:28-97, an sscan with kernel (3, 3, 3)), the 3-D analogue of BASELINE config 4.  Window
+// plane n reads state plane n + c0 - 1 and writes the window centres of state plane n + c0, so output plane n is a 2-D
+// kmap of a plane that is complete before the step starts: ONE launch of the 2-D templates per plane (stencil2d_kernel
+// at 0.9-1.0 of the HBM roofline) instead of the wavefront kernel's plane-per-grid-barrier sweep (26 GLUP/s on 2048^2
+// planes).  When the window centres cover the whole plane ('same'-style borders) the source of step n is simply the
+// zero-padded output plane n - 1; otherwise (offset scans: the border cells keep their input values) the padded state
+// array of the generic scan is kept up to date with one strided copy of the output plane per step.
+int try_scan_planemarch(const KxGeom& g, const KxProgram& p, const void* in, const void* coef_dev, void* state, void* out,
+                        int reverse, cudaStream_t s) {
+  if (getenv("KX_NO_PLANEMARCH") || reverse || coef_dev || g.ndim != 3 || p.n_funcs != 1) return KX_ERR_UNSUPPORTED;
+  const KxFunc& f = p.func[0];
+  if (f.kind != KX_AFFINE || f.tap_end <= f.tap_begin) return KX_ERR_UNSUPPORTED;
+  if (g.in_dtype == KX_I32 && !f.coef_is_int) return KX_ERR_UNSUPPORTED;
+  for (int d = 0; d < 3; ++d)
+    if (g.stride[d] != 1 || g.lo[d] < 0 || g.hi[d] < 0) return KX_ERR_UNSUPPORTED;
+  const int c0 = (g.ksize[0] - 1) / 2, c1 = (g.ksize[1] - 1) / 2, c2 = (g.ksize[2] - 1) / 2;
+  for (int t = f.tap_begin; t < f.tap_end; ++t)
+    if (p.tap_off[t][0] != c0 - 1) return KX_ERR_UNSUPPORTED;
+  const int64_t D = g.in_shape[0], H = g.in_shape[1], W = g.in_shape[2];
+  const int64_t P0 = D + g.lo[0] + g.hi[0], P1 = H + g.lo[1] + g.hi[1], P2 = W + g.lo[2] + g.hi[2];
+  const int64_t o0 = g.out_shape[0], o1 = g.out_shape[1], o2 = g.out_shape[2];
+  if (o0 < 1 || o1 < 1 || o2 < 1) return KX_ERR_UNSUPPORTED;
+  if (o1 * o2 < 128 * 128) return KX_ERR_UNSUPPORTED;          // tiny planes: two launches per plane cost more than the sweep
+  (void)P0;
+  static thread_local KxProgram p2;
+  memset(&p2, 0, sizeof(p2));
+  p2.n_funcs = 1;
+  p2.func[0] = f;
+  p2.n_taps = f.tap_end - f.tap_begin;
+  p2.func[0].tap_begin = 0;
+  p2.func[0].tap_end = p2.n_taps;
+  for (int t = 0; t < p2.n_taps; ++t) {
+    p2.tap_off[t][0] = p.tap_off[f.tap_begin + t][1];
+    p2.tap_off[t][1] = p.tap_off[f.tap_begin + t][2];
+    p2.coef[t] = p.coef[f.tap_begin + t];
+  }
+  KxGeom g2;
+  memset(&g2, 0, sizeof(g2));
+  g2.ndim = 2;
+  g2.in_dtype = g2.out_dtype = g.in_dtype;
+  g2.ksize[0] = g.ksize[1], g2.ksize[1] = g.ksize[2];
+  g2.stride[0] = g2.stride[1] = 1;
+  g2.out_shape[0] = o1, g2.out_shape[1] = o2;
+  const size_t esz = 4;
+  char* outp = (char*)out;
+  const bool full_cover = o1 == H && o2 == W && g.lo[1] == c1 && g.lo[2] == c2;
+  if (full_cover) {
+    // source of step n: the zero-padded output plane n - 1 (step 0: input plane c0 - 1 - lo0, or the zero pad)
+    g2.in_shape[0] = H, g2.in_shape[1] = W;
+    g2.lo[0] = g.lo[1], g2.hi[0] = g.hi[1], g2.lo[1] = g.lo[2], g2.hi[1] = g.hi[2];
+    for (int64_t n = 0; n < o0; ++n) {
+      const void* src;
+      if (n > 0) {
+        src = outp + (size_t)(n - 1) * o1 * o2 * esz;
+      } else {
+        const int64_t pl = c0 - 1 - g.lo[0];
+        if (pl >= 0 && pl < D) {
+          src = (const char*)in + (size_t)pl * H * W * esz;
+        } else {
+          KX_CUDA_CHECK(cudaMemsetAsync(state, 0, (size_t)H * W * esz, s));
+          src = state;
+        }
+      }
+      MapArgs a;
+      fill_map_args(a, g2, p2, src, nullptr, 0, outp + (size_t)n * o1 * o2 * esz, 1);
+      const int rc = dispatch_map(a, p2, s);
+      if (rc) return rc;
+    }
+    return KX_OK;
+  }
+  // general borders: keep the padded state array (pad cells and uncovered cells stay as they are)
+  char* st = (char*)state;
+  if (P1 != H || P2 != W || P0 != D) KX_CUDA_CHECK(cudaMemsetAsync(state, 0, (size_t)P0 * P1 * P2 * esz, s));
+  for (int64_t z = 0; z < D; ++z) {                   // in -> the interior of the padded state (one strided copy per plane
+    const int rc = copy2d(st + ((size_t)((z + g.lo[0]) * P1 + g.lo[1]) * P2 + g.lo[2]) * esz, P2,   // unless nothing is padded)
+                          (const char*)in + (size_t)z * H * W * esz, W, W, H, s);
+    if (rc) return rc;
+    if (P1 == H && P2 == W) {                         // contiguous: the rest in one copy
+      KX_CUDA_CHECK(cudaMemcpyAsync(st + (size_t)(g.lo[0] + 1) * P1 * P2 * esz, (const char*)in + (size_t)H * W * esz,
+                                    (size_t)(D - 1) * H * W * esz, cudaMemcpyDeviceToDevice, s));
+      break;
+    }
+  }
+  g2.in_shape[0] = P1, g2.in_shape[1] = P2;          // 'valid' windows over the padded plane
+  for (int64_t n = 0; n < o0; ++n) {
+    const void* src = st + (size_t)(n + c0 - 1) * P1 * P2 * esz;
+    char* dst = outp + (size_t)n * o1 * o2 * esz;
+    MapArgs a;
+    fill_map_args(a, g2, p2, src, nullptr, 0, dst, 1);
+    const int rc = dispatch_map(a, p2, s);
+    if (rc) return rc;
+    if (n + 1 < o0) {    // the window centres of state plane n + c0: read by the next step
+      const int rc2 = copy2d(st + ((size_t)((n + c0) * P1 + c1) * P2 + c2) * esz, P2, dst, o2, o2, o1, s);
+      if (rc2) return rc2;
+    }
+  }
+  return KX_OK;
+}
+
+// sscan (offset scan: the result is a copy of the input whose offset interior is overwritten, kernex/_src/scan.py:118-147)
+// of the same time-marching shape: result plane u = the 2-D offset map of result plane u - 1, fused into ONE pass per
+// plane -- stencil2d_kernel in its smap form ('same' geometry, cells outside the offset interior copy the window
+// centre) writes straight into the result array, and the ring outside the interior, which must keep the INPUT values
+// of plane u rather than those of plane u - 1, is patched by ring_copy_kernel.  8 B per cell, no state array, no
+// write-back.  Returns KX_ERR_UNSUPPORTED for anything else (the caller runs kx_scan + the strided write-back).
+int scan_offset_planemarch(const KxGeom& g, const KxProgram& p, const void* in, const void* coef_dev, const int32_t* off_lo,
+                           void* out_full, cudaStream_t s) {
+  if (getenv("KX_NO_PLANEMARCH") || coef_dev || g.ndim != 3 || p.n_funcs != 1) return KX_ERR_UNSUPPORTED;
+  const KxFunc& f = p.func[0];
+  if (f.kind != KX_AFFINE || f.tap_end <= f.tap_begin || f.post_div != 0.0) return KX_ERR_UNSUPPORTED;
+  if (g.in_dtype != g.out_dtype || (g.in_dtype == KX_I32 && !f.coef_is_int)) return KX_ERR_UNSUPPORTED;
+  int c[3], off_hi[3];
+  for (int d = 0; d < 3; ++d) {
+    c[d] = (g.ksize[d] - 1) / 2;
+    if (g.stride[d] != 1 || g.lo[d] != c[d] - off_lo[d] || g.lo[d] < 0 || g.hi[d] < 0) return KX_ERR_UNSUPPORTED;
+    off_hi[d] = g.ksize[d] - 1 - c[d] - g.hi[d];                     // windows end off_hi cells before the array does
+    if (off_lo[d] < 0 || off_hi[d] < 0) return KX_ERR_UNSUPPORTED;
+  }
+  if (off_lo[0] < 1) return KX_ERR_UNSUPPORTED;                      // the first written plane reads a real plane
+  for (int t = f.tap_begin; t < f.tap_end; ++t)
+    if (p.tap_off[t][0] != c[0] - 1) return KX_ERR_UNSUPPORTED;
+  const int64_t D = g.in_shape[0], H = g.in_shape[1], W = g.in_shape[2];
+  if (H * W < 128 * 128 || H > 0x3fffffff || W > 0x3fffffff) return KX_ERR_UNSUPPORTED;
+  const int64_t u0 = off_lo[0], u1 = D - off_hi[0];                  // written planes [u0, u1)
+  const int y0 = off_lo[1], y1 = (int)H - off_hi[1], x0 = off_lo[2], x1 = (int)W - off_hi[2];
+  if (u1 <= u0 || y1 <= y0 || x1 <= x0) return KX_ERR_UNSUPPORTED;
+  static thread_local KxProgram p2;
+  memset(&p2, 0, sizeof(p2));
+  p2.n_funcs = 1;
+  p2.func[0] = f;
+  p2.n_taps = f.tap_end - f.tap_begin;
+  p2.func[0].tap_begin = 0;
+  p2.func[0].tap_end = p2.n_taps;
+  for (int t = 0; t < p2.n_taps; ++t) {
+    p2.tap_off[t][0] = p.tap_off[f.tap_begin + t][1];
+    p2.tap_off[t][1] = p.tap_off[f.tap_begin + t][2];
+    p2.coef[t] = p.coef[f.tap_begin + t];
+  }
+  KxGeom g2;
+  memset(&g2, 0, sizeof(g2));
+  g2.ndim = 2;
+  g2.in_dtype = g2.out_dtype = g.in_dtype;
+  for (int d = 0; d < 2; ++d) {
+    g2.in_shape[d] = g2.out_shape[d] = g.in_shape[d + 1];
+    g2.ksize[d] = g.ksize[d + 1];
+    g2.stride[d] = 1;
+    g2.lo[d] = c[d + 1];
+    g2.hi[d] = g.ksize[d + 1] - 1 - c[d + 1];
+  }
+  const size_t plane = (size_t)H * W * 4;
+  char* res = (char*)out_full;
+  const char* src_in = (const char*)in;
+  const bool ring = y0 > 0 || x0 > 0 || y1 < H || x1 < W;
+  int64_t ring_cells = (int64_t)(y0 + (H - y1)) * W + (int64_t)(y1 - y0) * (x0 + (W - x1));
+  for (int64_t u = u0; u < u1; ++u) {
+    MapArgs a;
+    fill_map_args(a, g2, p2, u == u0 ? (const void*)(src_in + (size_t)(u - 1) * plane) : (const void*)(res + (size_t)(u - 1) * plane),
+                  nullptr, 0, res + (size_t)u * plane, 1);
+    a.use_box = 1;
+    a.box_lo[0] = y0, a.box_hi[0] = y1, a.box_lo[1] = x0, a.box_hi[1] = x1;
+    const int rc = try_stencil2d(a, p2, s);
+    if (rc) return rc;                               // KX_ERR_UNSUPPORTED at the first plane: nothing was launched yet
+    if (ring) {
+      int64_t blocks = (ring_cells + 255) / 256;
+      if (blocks > 2048) blocks = 2048;
+      ring_copy_kernel<<<(unsigned)blocks, 256, 0, s>>>((uint32_t*)(res + (size_t)u * plane), (const uint32_t*)(src_in + (size_t)u * plane),
+                                                         (int)H, (int)W, y0, y1, x0, x1);
+      const int rc2 = after_launch("ring_copy_kernel");
+      if (rc2) return rc2;
+    }
+  }
+  // the planes an offset scan never writes keep the input
+  if (u0 > 0) KX_CUDA_CHECK(cudaMemcpyAsync(res, src_in, (size_t)u0 * plane, cudaMemcpyDeviceToDevice, s));
+  if (u1 < D) KX_CUDA_CHECK(cudaMemcpyAsync(res + (size_t)u1 * plane, src_in + (size_t)u1 * plane, (size_t)(D - u1) * plane, cudaMemcpyDeviceToDevice, s));
+  return KX_OK;
+}
+
 __global__ void __launch_bounds__(256) cast_i32_f32_kernel(const int32_t* __restrict__ in, float* __restrict__ out, int64_t n) {
   const int64_t nv = n >> 2;
   for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < nv; i += (int64_t)gridDim.x * 256) {
@@ -560,11 +786,24 @@ int kx_scan(const KxGeom* geom, const KxProgram* prog, const void* in, const voi
   cudaStream_t s = (cudaStream_t)stream;
   rc = try_scan_rowmarch(*geom, *prog, in, coef_dev, out, reverse, s);
   if (rc != KX_ERR_UNSUPPORTED) return rc;
+  rc = try_scan_planemarch(*geom, *prog, in, coef_dev, state, out, reverse, s);
+  if (rc != KX_ERR_UNSUPPORTED) return rc;
   if (!getenv("KX_SCAN_SEQUENTIAL")) {  // cross-check switch: the one-thread sweep of kx_generic.cu
     rc = launch_scan_wavefront(*geom, *prog, in, coef_dev, state, out, reverse, s);
     if (rc != KX_ERR_UNSUPPORTED) return rc;
   }
   return launch_generic_scan(*geom, *prog, in, coef_dev, state, out, reverse, s);
+}
+
+int kx_scan_offset(const KxGeom* geom, const KxProgram* prog, const void* in, const void* coef_dev, const int32_t* off0,
+                   void* out, void* stream) {
+  int rc = validate(geom, prog);
+  if (rc) return rc;
+  if (!in || !out || !off0) return fail(KX_ERR_INVALID, "null pointer");
+  DeviceGuard guard(out);
+  rc = scan_offset_planemarch(*geom, *prog, in, coef_dev, off0, out, (cudaStream_t)stream);
+  if (rc == KX_ERR_UNSUPPORTED) return fail(KX_ERR_UNSUPPORTED, "no fused offset-scan template: run kx_scan and write the values back");
+  return rc;
 }
 
 int kx_scan_rowmarch_shard(const KxGeom* geom, const KxProgram* prog, int64_t col_base, int64_t global_nx, void* out,

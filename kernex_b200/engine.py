@@ -921,6 +921,31 @@ def _run_scan(func_map, shape, kernel_size, strides, border, relative, reverse, 
     return arr, out
 
 
+def _try_fused_offset_scan(func_map, shape, kernel_size, strides, border, offset, relative, array, a, k, static):
+    """sscan in ONE C call (``kx_scan_offset``: 3-D time-marching scans, a fused 2-D pass per plane that writes straight
+    into the result).  Returns None when the library has no fused template for the call: the caller then composes
+    ``kx_scan`` with the strided write-back."""
+    if len(shape) != 3 or len(func_map) != 1 or any(s != 1 for s in strides):
+        return None
+    arr = _Arr(array)
+    if tuple(arr.t.shape) != tuple(shape):
+        return None
+    specs, device_args, prog, geom, out_shape = _scan_plan(
+        func_map, shape, kernel_size, strides, border, relative, arr.kx_dtype, a, k, static)
+    if device_args or specs[0].kind != "affine" or not all(out_shape):
+        return None
+    if arr.kx_dtype == _lib.KX_I32 and specs[0].weak_float:
+        return None
+    lib = _lib.load()
+    out = torch.empty_like(arr.t)
+    off0 = (C.c_int32 * len(shape))(*[int(o[0]) for o in offset])
+    rc = lib.kx_scan_offset(C.byref(geom), C.byref(prog.c), _ptr(arr.t), 0, off0, _ptr(out), _stream_ptr(arr.t.device))
+    if rc == 2:          # KX_ERR_UNSUPPORTED: nothing was launched
+        return None
+    _lib.check(rc)
+    return arr.give_back(out)
+
+
 def _scan_kwargs(scan_kind, scan_kwargs):
     if scan_kind not in (None, "scan"):
         raise KeyError(scan_kind)
@@ -958,6 +983,9 @@ def offset_kernel_scan(func_map: dict, shape, kernel_size, strides, offset, rela
     _validate(shape, kernel_size, strides, border)
 
     def call(array, *a, **k):
+        fused = None if reverse else _try_fused_offset_scan(func_map, shape, kernel_size, strides, border, offset, relative, array, a, k, static)
+        if fused is not None:
+            return fused
         arr, res = _run_scan(func_map, shape, kernel_size, strides, border, relative, reverse, array, a, k, static)
         return arr.give_back(_write_back(arr.t, res, shape, strides, offset, "scan"))
 
