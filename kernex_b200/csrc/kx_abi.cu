@@ -409,33 +409,74 @@ __global__ void __launch_bounds__(256) ring_copy_kernel(uint32_t* __restrict__ d
 // array of the generic scan is kept up to date with one strided copy of the output plane per step.
 int try_scan_planemarch(const KxGeom& g, const KxProgram& p, const void* in, const void* coef_dev, void* state, void* out,
                         int reverse, cudaStream_t s) {
-  if (getenv("KX_NO_PLANEMARCH") || reverse || coef_dev || g.ndim != 3 || p.n_funcs != 1) return KX_ERR_UNSUPPORTED;
-  const KxFunc& f = p.func[0];
-  if (f.kind != KX_AFFINE || f.tap_end <= f.tap_begin) return KX_ERR_UNSUPPORTED;
-  if (g.in_dtype == KX_I32 && !f.coef_is_int) return KX_ERR_UNSUPPORTED;
+  if (getenv("KX_NO_PLANEMARCH") || reverse || coef_dev || g.ndim != 3 || p.n_funcs < 1) return KX_ERR_UNSUPPORTED;
   for (int d = 0; d < 3; ++d)
     if (g.stride[d] != 1 || g.lo[d] < 0 || g.hi[d] < 0) return KX_ERR_UNSUPPORTED;
   const int c0 = (g.ksize[0] - 1) / 2, c1 = (g.ksize[1] - 1) / 2, c2 = (g.ksize[2] - 1) / 2;
-  for (int t = f.tap_begin; t < f.tap_end; ++t)
-    if (p.tap_off[t][0] != c0 - 1) return KX_ERR_UNSUPPORTED;
+  // every function: AFFINE, taps (if any: constants are boundary / initial conditions) in the plane above the centre
+  bool any_tap = false;
+  for (int fi = 0; fi < p.n_funcs; ++fi) {
+    const KxFunc& f = p.func[fi];
+    if (f.kind != KX_AFFINE) return KX_ERR_UNSUPPORTED;
+    if (g.in_dtype == KX_I32 && !f.coef_is_int) return KX_ERR_UNSUPPORTED;
+    for (int t = f.tap_begin; t < f.tap_end; ++t) {
+      if (p.tap_off[t][0] != c0 - 1) return KX_ERR_UNSUPPORTED;
+      any_tap = true;
+    }
+  }
+  if (!any_tap) return KX_ERR_UNSUPPORTED;
   const int64_t D = g.in_shape[0], H = g.in_shape[1], W = g.in_shape[2];
   const int64_t P0 = D + g.lo[0] + g.hi[0], P1 = H + g.lo[1] + g.hi[1], P2 = W + g.lo[2] + g.hi[2];
   const int64_t o0 = g.out_shape[0], o1 = g.out_shape[1], o2 = g.out_shape[2];
   if (o0 < 1 || o1 < 1 || o2 < 1) return KX_ERR_UNSUPPORTED;
   if (o1 * o2 < 128 * 128) return KX_ERR_UNSUPPORTED;          // tiny planes: two launches per plane cost more than the sweep
+  const bool full_cover = o1 == H && o2 == W && g.lo[1] == c1 && g.lo[2] == c2;
+  // region keys are window-centre coordinates of the UNPADDED array: the 2-D maps below keep them only when their
+  // geometry is the unpadded plane's ('same'-style borders), so meshes take the full-cover form only
+  if (p.n_funcs > 1 && !full_cover) return KX_ERR_UNSUPPORTED;
   (void)P0;
+  // the 2-D program: every function with its taps projected onto the plane; the keys are filled in per plane
   static thread_local KxProgram p2;
   memset(&p2, 0, sizeof(p2));
-  p2.n_funcs = 1;
-  p2.func[0] = f;
-  p2.n_taps = f.tap_end - f.tap_begin;
-  p2.func[0].tap_begin = 0;
-  p2.func[0].tap_end = p2.n_taps;
-  for (int t = 0; t < p2.n_taps; ++t) {
-    p2.tap_off[t][0] = p.tap_off[f.tap_begin + t][1];
-    p2.tap_off[t][1] = p.tap_off[f.tap_begin + t][2];
-    p2.coef[t] = p.coef[f.tap_begin + t];
+  p2.n_funcs = p.n_funcs;
+  p2.n_taps = p.n_taps;
+  for (int fi = 0; fi < p.n_funcs; ++fi) p2.func[fi] = p.func[fi];
+  for (int t = 0; t < p.n_taps; ++t) {
+    p2.tap_off[t][0] = p.tap_off[t][1];
+    p2.tap_off[t][1] = p.tap_off[t][2];
+    p2.coef[t] = p.coef[t];
   }
+  // keys of plane n: those whose axis-0 item matches the plane's window-centre coordinate, with that item dropped
+  // (utils.py:302-335: a key matches iff every item present matches; zip truncation: absent items match)
+  uint32_t cur_mask = 0xffffffffu;
+  bool have_mask = false;
+  auto set_plane_keys = [&](int64_t n) {
+    if (p.n_funcs == 1) return;
+    const int64_t cen = n - g.lo[0] + c0;
+    uint32_t mask = 0;
+    for (int k = 0; k < p.n_keys; ++k) {
+      bool m = true;
+      if (p.key[k].n_items >= 1) {
+        const KxKeyItem& it = p.key[k].item[0];
+        if (it.kind == KX_KEY_EQ) m = cen == it.a;
+        else if (it.kind == KX_KEY_RANGE) m = it.a <= cen && cen < it.b;
+        else if (it.kind == KX_KEY_RANGE_STEP) m = it.a <= cen && cen < it.b && (it.step == 0 ? false : cen % it.step == 0);
+      }
+      if (m) mask |= 1u << k;
+    }
+    if (have_mask && mask == cur_mask) return;
+    have_mask = true;
+    cur_mask = mask;
+    p2.n_keys = 0;
+    for (int k = 0; k < p.n_keys; ++k) {
+      if (!(mask & (1u << k))) continue;
+      KxKey& q = p2.key[p2.n_keys++];
+      memset(&q, 0, sizeof(q));
+      q.func = p.key[k].func;
+      q.n_items = p.key[k].n_items > 0 ? p.key[k].n_items - 1 : 0;
+      for (int d = 0; d < q.n_items; ++d) q.item[d] = p.key[k].item[d + 1];
+    }
+  };
   KxGeom g2;
   memset(&g2, 0, sizeof(g2));
   g2.ndim = 2;
@@ -445,7 +486,6 @@ int try_scan_planemarch(const KxGeom& g, const KxProgram& p, const void* in, con
   g2.out_shape[0] = o1, g2.out_shape[1] = o2;
   const size_t esz = 4;
   char* outp = (char*)out;
-  const bool full_cover = o1 == H && o2 == W && g.lo[1] == c1 && g.lo[2] == c2;
   if (full_cover) {
     // source of step n: the zero-padded output plane n - 1 (step 0: input plane c0 - 1 - lo0, or the zero pad)
     g2.in_shape[0] = H, g2.in_shape[1] = W;
@@ -463,6 +503,7 @@ int try_scan_planemarch(const KxGeom& g, const KxProgram& p, const void* in, con
           src = state;
         }
       }
+      set_plane_keys(n);
       MapArgs a;
       fill_map_args(a, g2, p2, src, nullptr, 0, outp + (size_t)n * o1 * o2 * esz, 1);
       const int rc = dispatch_map(a, p2, s);

@@ -86,3 +86,46 @@ def test_planemarch_sscan_diffusion_matches_numpy_fdm(kex):
     np.testing.assert_array_equal(got[:, 0, :], U[:, 0, :])       # border cells keep their input values
     np.testing.assert_array_equal(got[:, :, -1], U[:, :, -1])
     np.testing.assert_allclose(got, ref, rtol=1e-5, atol=1e-5)
+
+
+def test_planemarch_mesh_2d_convection_with_boundary_conditions(kex, monkeypatch):
+    """The README's linear-convection mesh (README.md:231-266) with TWO space axes: `F[slice] = fn` boundary / initial
+    conditions + an upwind update that reads the plane above, as a 3-D kscan with 'same'-style borders.  Every plane is a
+    2-D multi-function kmap (mesh kernel); int32 coefficients make the comparison with the wavefront kernel exact."""
+    nt, ny, nx = 6, 140, 260
+
+    def mesh(factory, integer):
+        F = factory(kernel_size=(3, 3, 3), padding=((1, 1), (1, 1), (1, 1)), relative=True)
+        F[:, 0, :] = F[:, -1, :] = lambda u: 1                    # boundary conditions
+        F[:, :, 0] = F[:, :, -1] = lambda u: 1
+        F[0, 1:-1, 1:-1] = lambda u: 1                             # initial conditions
+        F[0, 40:80, 60:120] = lambda u: 2
+        if integer:
+            F[1:, 1:-1, 1:-1] = lambda u: 3 * u[-1, 0, 0] - u[-1, -1, 0] - u[-1, 0, -1]
+        else:
+            F[1:, 1:-1, 1:-1] = lambda u: u[-1, 0, 0] - 0.3 * (u[-1, 0, 0] - u[-1, -1, 0]) - 0.2 * (u[-1, 0, 0] - u[-1, 0, -1])
+        return F
+
+    for integer in (True, False):
+        x = (np.ones((nt, ny, nx), dtype=np.int32) if integer else np.ones((nt, ny, nx), dtype=np.float32))
+        got = mesh(kex.kscan, integer)(torch.from_numpy(x).cuda()).cpu().numpy()
+        assert _last_kernel() in ("stencil2d_mesh_kernel", "generic_map_kernel", "stencil2d_kernel"), _last_kernel()
+        monkeypatch.setenv("KX_NO_PLANEMARCH", "1")
+        wave = mesh(kex.kscan, integer)(torch.from_numpy(x).cuda()).cpu().numpy()
+        assert _last_kernel().startswith("scan_")
+        monkeypatch.delenv("KX_NO_PLANEMARCH")
+        # NumPy reference of the same scheme
+        ref = np.ones((nt, ny, nx), dtype=np.float64)
+        ref[0, 40:80, 60:120] = 2
+        for n in range(1, nt):
+            p = ref[n - 1]
+            if integer:
+                ref[n, 1:-1, 1:-1] = 3 * p[1:-1, 1:-1] - p[:-2, 1:-1] - p[1:-1, :-2]
+            else:
+                ref[n, 1:-1, 1:-1] = p[1:-1, 1:-1] - 0.3 * (p[1:-1, 1:-1] - p[:-2, 1:-1]) - 0.2 * (p[1:-1, 1:-1] - p[1:-1, :-2])
+        if integer:
+            np.testing.assert_array_equal(got, wave)
+            np.testing.assert_array_equal(got, ref.astype(np.int32))
+        else:
+            np.testing.assert_allclose(got, wave, rtol=1e-5, atol=1e-5)
+            np.testing.assert_allclose(got, ref, rtol=1e-5, atol=1e-5)
