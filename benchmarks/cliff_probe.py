@@ -53,3 +53,8 @@ x2 = torch.randn((8192, 8191), device=dev, generator=g)
 f = kex.kmap(kernel_size=(3, 3), padding="same", relative=True)(lambda v: v[1,0]+v[-1,0]+v[0,1]+v[0,-1]-4*v[0,0])
 y = f(x2); med, _ = timeit(lambda: f(x2), 4)
 rep("2-D 5-pt on 8192x8191 (odd width)", x2.numel() * 8, med)
+# 7. smap over a 3-D volume (a Jacobi step)
+x3 = torch.randn((768, 768, 768), device=dev, generator=g)
+f = kex.smap(kernel_size=(3, 3, 3), offset=1, relative=True)(lambda v: (v[1,0,0]+v[-1,0,0]+v[0,1,0]+v[0,-1,0]+v[0,0,1]+v[0,0,-1]) / 6.0)
+y = f(x3); med, _ = timeit(lambda: f(x3), 4)
+rep("smap 3-D 6-neighbour Jacobi step on 768^3", x3.numel() * 8, med)

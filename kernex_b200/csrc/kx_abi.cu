@@ -376,6 +376,57 @@ int copy2d(void* dst, int64_t dpitch, const void* src, int64_t spitch, int64_t w
   return after_launch("copy2d_kernel");
 }
 
+// dst <- src on the box [lo, hi) of a C-contiguous array of rank <= 4 (missing leading axes: extent 1)
+struct BoxCopy {
+  int64_t lo[4], ext[4], pitch[4];
+};
+__global__ void __launch_bounds__(256) box_copy_kernel(uint32_t* __restrict__ dst, const uint32_t* __restrict__ src,
+                                                       const __grid_constant__ BoxCopy b) {
+  const int64_t total = b.ext[0] * b.ext[1] * b.ext[2] * b.ext[3];
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
+    int64_t r = i, off = 0;
+#pragma unroll
+    for (int d = 3; d >= 0; --d) {
+      const int64_t j = r % b.ext[d];
+      r /= b.ext[d];
+      off += (b.lo[d] + j) * b.pitch[d];
+    }
+    dst[off] = __ldg(src + off);
+  }
+}
+
+// every cell OUTSIDE the box [lo, hi) of an nd-dimensional array: dst <- src, as 2 nd slabs (axis d: below / above the
+// box, restricted to the box on the axes before d so that no cell is copied twice)
+int copy_outside_box(void* dst, const void* src, const int64_t* shape, int nd, const int64_t* lo, const int64_t* hi, cudaStream_t s) {
+  for (int d = 0; d < nd; ++d) {
+    for (int side = 0; side < 2; ++side) {
+      BoxCopy b;
+      int64_t pitch = 1, total = 1;
+      for (int q = 3; q >= 0; --q) {
+        const int a = q - (4 - nd);                 // array axis of slot q (negative: padding slot)
+        if (a < 0) {
+          b.lo[q] = 0, b.ext[q] = 1, b.pitch[q] = 0;
+          continue;
+        }
+        b.pitch[q] = pitch;
+        pitch *= shape[a];
+        if (a < d) b.lo[q] = lo[a], b.ext[q] = hi[a] - lo[a];
+        else if (a == d) b.lo[q] = side == 0 ? 0 : hi[a], b.ext[q] = side == 0 ? lo[a] : shape[a] - hi[a];
+        else b.lo[q] = 0, b.ext[q] = shape[a];
+        total *= b.ext[q];
+      }
+      if (total <= 0) continue;
+      int64_t blocks = (total + 255) / 256;
+      const int64_t cap = (int64_t)sm_count() * 16;
+      if (blocks > cap) blocks = cap;
+      box_copy_kernel<<<(unsigned)blocks, 256, 0, s>>>((uint32_t*)dst, (const uint32_t*)src, b);
+      const int rc = after_launch("box_copy_kernel");
+      if (rc) return rc;
+    }
+  }
+  return KX_OK;
+}
+
 // the cells of an H x W plane OUTSIDE the box [y0, y1) x [x0, x1): dst <- src (the ring an offset scan leaves untouched)
 __global__ void __launch_bounds__(256) ring_copy_kernel(uint32_t* __restrict__ dst, const uint32_t* __restrict__ src, int H, int W,
                                                         int y0, int y1, int x0, int x1) {
@@ -698,6 +749,19 @@ int kx_map_offset(const KxGeom* geom, const KxProgram* prog, const void* in, con
     }
     rc = try_stencil2d(a, *prog, s);
     if (rc != KX_ERR_UNSUPPORTED) return rc;
+    // Other windows (3-D stencils: a Jacobi step written as smap): the SAME map over every cell on whatever fast
+    // template takes it -- the cells outside the offset interior come out as zero-padded window values -- and the
+    // ring outside the interior is then restored from the input, slab by slab.  8 B per cell + the ring instead of
+    // copy + generic kernel + strided write-back (0.05 of the HBM roofline).
+    if (!getenv("KX_NO_FUSED_OFFSET") && in_elems >= (1 << 16)) {
+      MapArgs a2;
+      fill_map_args(a2, gs, *prog, in, coef_dev, 0, out, 1);
+      rc = dispatch_map(a2, *prog, s);
+      if (rc) return rc;
+      int64_t blo[KX_MAX_DIMS], bhi[KX_MAX_DIMS];
+      for (int d = 0; d < geom->ndim; ++d) blo[d] = off0[d], bhi[d] = off0[d] + geom->out_shape[d];
+      return copy_outside_box(out, in, geom->in_shape, geom->ndim, blo, bhi, s);
+    }
   }
   KX_CUDA_CHECK(cudaMemcpyAsync(out, in, (size_t)in_elems * 4, cudaMemcpyDeviceToDevice, s));
   MapArgs a;

@@ -84,3 +84,42 @@ def test_smap_max_and_mean_use_the_write_back_path(kex):
     got = kex.smap(kernel_size=(3, 3), offset=1)(g)(xf)
     want = ko.offset_kernel_map({g: ()}, x.shape, (3, 3), (1, 1), ((1, 1), (1, 1)), False)(xf)
     np.testing.assert_allclose(got, want, rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("case", [
+    ((40, 50, 64), (3, 3, 3), ((1, 1), (1, 1), (1, 1))),        # a Jacobi step: 7-point stencil, one-cell ring kept
+    ((36, 44, 68), (3, 3, 3), ((1, 0), (0, 1), (1, 1))),        # one-sided offsets: zero-padded windows on the open sides
+    ((70, 33, 36), (3, 3, 3), ((1, 1), (1, 1), (1, 1))),        # rows not 16-byte aligned
+    ((300, 260), (5, 5), ((2, 2), (1, 2))),                     # 2-D, 5x5
+    ((2, 20, 40, 48), (1, 3, 3, 3), ((0, 0), (1, 1), (1, 1), (1, 1))),   # leading batch axis
+])
+@pytest.mark.parametrize("integer", [False, True])
+def test_fused_offset_map_beyond_2d(kex, case, integer, monkeypatch):
+    """smap over 3-D windows (and anything else the 2-D fused pass declines): the map over EVERY cell on the fast
+    templates + the ring outside the offset interior restored from the input (kx_map_offset) -- against the literal
+    oracle and the copy + generic kernel + strided write-back path (KX_NO_FUSED_OFFSET=1)."""
+    import itertools
+    shape, ksize, offset = case
+    rng = np.random.default_rng(sum(shape) + integer)
+    taps = [t for t in itertools.product(*[range(k) for k in ksize]) if sum(abs(a - (k - 1) // 2) for a, k in zip(t, ksize)) <= 1]
+    coefs = rng.integers(-3, 4, len(taps)) if integer else rng.standard_normal(len(taps))
+
+    def fn(v):
+        acc = 0 if integer else 0.0
+        for t, c in zip(taps, coefs):
+            acc = acc + (int(c) if integer else float(c)) * v[t]
+        return acc
+
+    x = rng.integers(-9, 10, shape).astype(np.int32) if integer else rng.standard_normal(shape).astype(np.float32)
+    st = (1,) * len(shape)
+    want = ko.offset_kernel_map({fn: ()}, shape, ksize, st, offset, False)(x)
+    got = kex.offset_kernel_map({fn: ()}, shape, ksize, st, offset, False)(x)
+    monkeypatch.setenv("KX_NO_FUSED_OFFSET", "1")
+    plain = kex.offset_kernel_map({fn: ()}, shape, ksize, st, offset, False)(x)
+    assert got.shape == want.shape and got.dtype == want.dtype
+    if integer:
+        np.testing.assert_array_equal(got, want)
+        np.testing.assert_array_equal(plain, want)
+    else:
+        np.testing.assert_allclose(got, want, rtol=1e-5, atol=1e-5)
+        np.testing.assert_allclose(plain, want, rtol=1e-5, atol=1e-5)
