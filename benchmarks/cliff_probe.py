@@ -58,3 +58,8 @@ x3 = torch.randn((768, 768, 768), device=dev, generator=g)
 f = kex.smap(kernel_size=(3, 3, 3), offset=1, relative=True)(lambda v: (v[1,0,0]+v[-1,0,0]+v[0,1,0]+v[0,-1,0]+v[0,0,1]+v[0,0,-1]) / 6.0)
 y = f(x3); med, _ = timeit(lambda: f(x3), 4)
 rep("smap 3-D 6-neighbour Jacobi step on 768^3", x3.numel() * 8, med)
+# 8. 3-D max filter
+x3 = torch.randn((512, 512, 512), device=dev, generator=g)
+f = kex.kmap(kernel_size=(3, 3, 3), padding="same")(lambda v: np.max(v))
+y = f(x3); med, _ = timeit(lambda: f(x3), 4)
+rep("3-D max filter 3x3x3 same on 512^3", x3.numel() * 8, med)

@@ -55,3 +55,25 @@ def test_int_results_stay_int(kex):
     xp = np.pad(x.astype(np.int64), 1)
     want = sum(xp[a:a + 300, b:b + 1024] for a in range(3) for b in range(3)).astype(np.int32)
     np.testing.assert_array_equal(got.cpu().numpy(), want)
+
+
+@pytest.mark.parametrize("case", [
+    ((40, 44, 64), (3, 3, 3), "same"), ((33, 50, 72), (3, 3, 3), "valid"), ((24, 40, 68), (2, 3, 5), ((1, 0), (0, 2), (2, 2))), ((20, 40, 68), (3, 5, 7), ((1, 0), (0, 2), (3, 3))),
+    ((2, 30, 36, 64), (1, 3, 3, 3), ((0, 0), (1, 1), (1, 1), (1, 1))),
+])
+@pytest.mark.parametrize("op", ["max", "min"])
+def test_separable_3d_reduction_is_exact(kex, case, op):
+    """3-D max / min filters run as three passes of the 2-D row-march kernel (engine._separable_reduce_3d): bit for bit
+    the literal oracle's zero-padded 3-D window reduction, int32 and float32."""
+    shape, ksize, pad = case
+    border = ko.resolve_padding(pad, ksize)
+    rng = np.random.default_rng(sum(shape))
+    fn = (lambda v: np.max(v)) if op == "max" else (lambda v: np.min(v))
+    for integer in (False, True):
+        x = rng.integers(-50, 50, shape).astype(np.int32) if integer else rng.standard_normal(shape).astype(np.float32)
+        want = ko.kernel_map({fn: ()}, shape, ksize, (1,) * len(shape), border, False)(x)
+        got = kex.kernel_map({fn: ()}, shape, ksize, (1,) * len(shape), border, False)(torch.from_numpy(x).cuda())
+        if tuple(ksize[-3:]) == (3, 3, 3):
+            assert _last_kernel() == "stencil2d_kernel", _last_kernel()
+        assert tuple(got.shape) == want.shape
+        np.testing.assert_array_equal(got.cpu().numpy(), want)
