@@ -43,7 +43,7 @@ struct PoolArgs {
   int ly, lx, th;
   float post_div;
   T bias;
-  T coef[16];
+  T coef[32];
 };
 
 // A warp covers kWarpOut<SX> output columns: 256 for stride 1 (8 per lane, two groups of 4 consecutive
@@ -59,6 +59,14 @@ struct RowW {
   static constexpr int value = (((WarpOut<SX>::value - 1) * SX + 3 + 3) + 3) / 4 * 4 + 4;   // span + shift, rounded, + slack vector
 };
 
+template <int I, int N, typename F>
+__device__ __forceinline__ void p_static_for(F&& f) {
+  if constexpr (I < N) {
+    f(std::integral_constant<int, I>{});
+    p_static_for<I + 1, N>(f);
+  }
+}
+
 template <typename T, int OP>
 __device__ __forceinline__ T fold(T acc, T c, T v) {
   if (OP == kOpAffine) return mad_wrap(c, v, acc);
@@ -71,7 +79,7 @@ __global__ void __launch_bounds__(kPT)
 pool2d_kernel(const __grid_constant__ PoolArgs<T> a) {
   constexpr int NACC = (KY + SY - 1) / SY;               // output rows an input row can belong to
   constexpr int PERIOD = SY * NACC;
-  constexpr int U = (PERIOD == 1 || PERIOD == 3) ? 3 : 4;  // unroll = ring depth, a multiple of PERIOD
+  constexpr int U = (PERIOD == 1 || PERIOD == 3) ? 3 : (PERIOD == 6 ? 6 : 4);  // unroll = ring depth, a multiple of PERIOD
   constexpr int RW = RowW<SX>::value;                    // floats per ring row
   constexpr int NE = SHIFT + 3 * SX + KX;                // ring columns a lane needs, from its aligned base
   constexpr int NV = (NE + 3) / 4;
@@ -230,26 +238,19 @@ pool2d_kernel(const __grid_constant__ PoolArgs<T> a) {
     }
   };
 
-#pragma unroll
-  for (int k = 0; k < U - 1; ++k) {
-    // prologue: rows iy0 .. iy0 + U - 2 into stages 0 .. U - 2
-    if (k == 0) issue(std::integral_constant<int, 0>{}, iy0);
-    if (k == 1) issue(std::integral_constant<int, 1 % U>{}, iy0 + 1);
-    if (k == 2) issue(std::integral_constant<int, 2 % U>{}, iy0 + 2);
-  }
+  // prologue: rows iy0 .. iy0 + U - 2 into stages 0 .. U - 2
+  p_static_for<0, U - 1>([&](auto k) { issue(k, iy0 + decltype(k)::value); });
 
   const int nrows = iy1 - iy0 + 1;
 #pragma unroll 1
   for (int n = 0; n < nrows; n += U) {
-    step(std::integral_constant<int, 0>{}, n);
-    if (n + 1 >= nrows) break;
-    step(std::integral_constant<int, 1>{}, n + 1);
-    if (n + 2 >= nrows) break;
-    step(std::integral_constant<int, 2>{}, n + 2);
-    if (U == 4) {
-      if (n + 3 >= nrows) break;
-      step(std::integral_constant<int, 3 % U>{}, n + 3);
-    }
+    bool done = false;
+    p_static_for<0, U>([&](auto ph) {
+      constexpr int PHv = decltype(ph)::value;
+      if (!done && n + PHv < nrows) step(ph, n + PHv);
+      else done = true;
+    });
+    if (done) break;
     parity ^= 1u;
   }
 }
@@ -313,6 +314,8 @@ int launch_pool_geom(PoolArgs<T>& a, dim3 grid, int ky, int kx, int sy, int sx, 
   KX_POOL_CASE(1, 3, 1, 2)
   KX_POOL_CASE(1, 3, 1, 3)
   KX_POOL_CASE(1, 4, 1, 4)
+  KX_POOL_CASE(5, 5, 2, 2)
+  KX_POOL_CASE(1, 5, 1, 2)
   if (OP != kOpAffine) {  // stride-1 AFFINE windows are kx_stencil2d.cu's job
     KX_POOL_CASE(3, 3, 1, 1)
     KX_POOL_CASE(2, 2, 1, 1)
@@ -337,7 +340,7 @@ int run_pool(const MapArgs& m, const KxProgram& p, cudaStream_t s) {
     lead *= g.in_shape[d];
   }
   const int64_t batch = m.batch * lead;
-  if (batch > 65535 || ky * kx > 16) return KX_ERR_UNSUPPORTED;
+  if (batch > 65535 || ky * kx > 32) return KX_ERR_UNSUPPORTED;
   if (f.tap_end - f.tap_begin != ky * kx) return KX_ERR_UNSUPPORTED;          // dense windows only
   if (m.coef_dev) return KX_ERR_UNSUPPORTED;
   PoolArgs<T> a;

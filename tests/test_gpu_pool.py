@@ -30,7 +30,7 @@ def _last_kernel():
 
 GEOMS = [((2, 2), (2, 2)), ((3, 3), (2, 2)), ((3, 3), (3, 3)), ((3, 3), (1, 1)), ((2, 2), (1, 1)),
          ((1, 3), (1, 2)), ((1, 2), (1, 2)), ((1, 3), (1, 1)), ((4, 4), (4, 4)), ((4, 4), (2, 2)), ((1, 3), (1, 3)),
-         ((1, 4), (1, 4))]
+         ((1, 4), (1, 4)), ((5, 5), (2, 2)), ((1, 5), (1, 2))]
 FNS = {"max": lambda v: np.max(v), "min": lambda v: np.min(v), "mean": lambda v: np.mean(v),
        "sum": lambda v: np.sum(v)}
 
@@ -76,10 +76,10 @@ def test_pool2d_matches_oracle(kex, gi, op, case, legacy, monkeypatch):
         np.testing.assert_allclose(got, want, rtol=0, atol=tol)
 
 
-@pytest.mark.parametrize("seed", range(6))
+@pytest.mark.parametrize("seed", range(8))
 def test_strided_weighted_window(kex, seed):
     rng = np.random.default_rng(7700 + seed)
-    ksize, strides = [((3, 3), (2, 2)), ((2, 2), (2, 2)), ((3, 3), (3, 3))][seed % 3]
+    ksize, strides = [((3, 3), (2, 2)), ((2, 2), (2, 2)), ((3, 3), (3, 3)), ((5, 5), (2, 2))][seed % 4]
     h, w = int(rng.integers(40, 150)), 4 * int(rng.integers(40, 300))
     border = ((int(rng.integers(0, 2)), int(rng.integers(0, 2))), (int(rng.integers(0, 4)), 1))
     taps = list(itertools.product(range(ksize[0]), range(ksize[1])))
