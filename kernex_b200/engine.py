@@ -973,14 +973,11 @@ def _run_scan(func_map, shape, kernel_size, strides, border, relative, reverse, 
     return arr, out
 
 
-def _try_fused_offset_scan(func_map, shape, kernel_size, strides, border, offset, relative, array, a, k, static):
+def _try_fused_offset_scan(func_map, shape, kernel_size, strides, border, offset, relative, arr, a, k, static):
     """sscan in ONE C call (``kx_scan_offset``: 3-D time-marching scans, a fused 2-D pass per plane that writes straight
     into the result).  Returns None when the library has no fused template for the call: the caller then composes
     ``kx_scan`` with the strided write-back."""
-    if len(shape) != 3 or len(func_map) != 1 or any(s != 1 for s in strides):
-        return None
-    arr = _Arr(array)
-    if tuple(arr.t.shape) != tuple(shape):
+    if len(shape) != 3 or len(func_map) != 1 or any(s != 1 for s in strides) or tuple(arr.t.shape) != tuple(shape):
         return None
     specs, device_args, prog, geom, out_shape = _scan_plan(
         func_map, shape, kernel_size, strides, border, relative, arr.kx_dtype, a, k, static)
@@ -995,7 +992,7 @@ def _try_fused_offset_scan(func_map, shape, kernel_size, strides, border, offset
     if rc == 2:          # KX_ERR_UNSUPPORTED: nothing was launched
         return None
     _lib.check(rc)
-    return arr.give_back(out)
+    return out
 
 
 def _scan_kwargs(scan_kind, scan_kwargs):
@@ -1035,11 +1032,12 @@ def offset_kernel_scan(func_map: dict, shape, kernel_size, strides, offset, rela
     _validate(shape, kernel_size, strides, border)
 
     def call(array, *a, **k):
-        fused = None if reverse else _try_fused_offset_scan(func_map, shape, kernel_size, strides, border, offset, relative, array, a, k, static)
+        arr0 = _Arr(array)      # uploaded once, whichever path runs
+        fused = None if reverse else _try_fused_offset_scan(func_map, shape, kernel_size, strides, border, offset, relative, arr0, a, k, static)
         if fused is not None:
-            return fused
-        arr, res = _run_scan(func_map, shape, kernel_size, strides, border, relative, reverse, array, a, k, static)
-        return arr.give_back(_write_back(arr.t, res, shape, strides, offset, "scan"))
+            return arr0.give_back(fused)
+        arr, res = _run_scan(func_map, shape, kernel_size, strides, border, relative, reverse, arr0.t, a, k, static)
+        return arr0.give_back(_write_back(arr.t, res, shape, strides, offset, "scan"))
 
     static = _static_key("scan", func_map, shape, kernel_size, strides, border, relative)
     return call
