@@ -730,10 +730,11 @@ int kx_map_offset(const KxGeom* geom, const KxProgram* prog, const void* in, con
   // Fused pass: with stride 1 the offset map is a 'same'-padded map over EVERY cell in which the
   // cells outside [off0, off0 + out_shape) keep their input value (window centre), so the copy of
   // the input and the strided write-back disappear (8 B per cell instead of 16).
-  bool unit = prog->n_funcs == 1 && prog->func[0].kind == KX_AFFINE;
+  bool geo_ok = true;                     // stride 1 and borders that are exactly what the offsets imply
   for (int d = 0; d < geom->ndim; ++d)
-    if (geom->stride[d] != 1 || geom->lo[d] != (geom->ksize[d] - 1) / 2 - off0[d]) unit = false;
-  if (unit) {
+    if (geom->stride[d] != 1 || geom->lo[d] != (geom->ksize[d] - 1) / 2 - off0[d]) geo_ok = false;
+  const bool unit = geo_ok && prog->n_funcs == 1 && prog->func[0].kind == KX_AFFINE;   // the one-pass smap form of stencil2d
+  if (geo_ok) {
     KxGeom gs = *geom;
     MapArgs a;
     for (int d = 0; d < geom->ndim; ++d) {
@@ -747,9 +748,9 @@ int kx_map_offset(const KxGeom* geom, const KxProgram* prog, const void* in, con
       a.box_lo[d] = off0[d];
       a.box_hi[d] = off0[d] + geom->out_shape[d];
     }
-    rc = try_stencil2d(a, *prog, s);
+    rc = unit ? try_stencil2d(a, *prog, s) : KX_ERR_UNSUPPORTED;
     if (rc != KX_ERR_UNSUPPORTED) return rc;
-    // Other windows (3-D stencils: a Jacobi step written as smap): the SAME map over every cell on whatever fast
+    // Other windows and programs (3-D stencils: a Jacobi step written as smap; window reductions; `F[slice] = fn` meshes): the SAME map over every cell on whatever fast
     // template takes it -- the cells outside the offset interior come out as zero-padded window values -- and the
     // ring outside the interior is then restored from the input, slab by slab.  8 B per cell + the ring instead of
     // copy + generic kernel + strided write-back (0.05 of the HBM roofline).

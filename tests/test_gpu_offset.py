@@ -123,3 +123,24 @@ def test_fused_offset_map_beyond_2d(kex, case, integer, monkeypatch):
     else:
         np.testing.assert_allclose(got, want, rtol=1e-5, atol=1e-5)
         np.testing.assert_allclose(plain, want, rtol=1e-5, atol=1e-5)
+
+
+def test_fused_offset_map_reductions_and_meshes(kex, monkeypatch):
+    """The general fused offset pass takes any scalar program: a window reduction (smap max filter) and a two-function
+    `F[slice] = fn` mesh, against the literal oracle and the write-back path."""
+    rng = np.random.default_rng(77)
+    shape = (300, 512)
+    x = rng.integers(-50, 50, shape).astype(np.int32)
+    f = lambda v: np.max(v)                                          # noqa: E731
+    want = ko.offset_kernel_map({f: ()}, shape, (3, 3), (1, 1), ((1, 1), (1, 1)), False)(x)
+    got = kex.offset_kernel_map({f: ()}, shape, (3, 3), (1, 1), ((1, 1), (1, 1)), False)(x)
+    np.testing.assert_array_equal(got, want)
+    f0 = lambda v: 2 * v[1, 1] + 1                                   # noqa: E731
+    f1 = lambda v: v[0, 1] + v[2, 1] - v[1, 0] - v[1, 2]             # noqa: E731
+    fmap = {f0: [[]], f1: [[(50, 250), (100, 400)]]}
+    want = ko.offset_kernel_map(fmap, shape, (3, 3), (1, 1), ((1, 1), (1, 1)), False)(x)
+    got = kex.offset_kernel_map(fmap, shape, (3, 3), (1, 1), ((1, 1), (1, 1)), False)(x)
+    monkeypatch.setenv("KX_NO_FUSED_OFFSET", "1")
+    plain = kex.offset_kernel_map(fmap, shape, (3, 3), (1, 1), ((1, 1), (1, 1)), False)(x)
+    np.testing.assert_array_equal(got, want)
+    np.testing.assert_array_equal(plain, want)
