@@ -812,6 +812,10 @@ int kx_map_vjp_input(const KxGeom* geom, const KxProgram* prog, const void* g, c
 int64_t kx_vjp_coef_scratch_bytes(const KxGeom* geom, const KxProgram* prog) {
   if (!geom || !prog) return 0;
   int64_t a = generic_vjp_coef_scratch_bytes(*geom, *prog), b = conv_wgrad_scratch_bytes(*geom, *prog);
+  {
+    const int64_t c = wgrad_rows_scratch_bytes(*geom, *prog);
+    a = c > a ? c : a;
+  }
   int C = 0, NT = 0;
   if (prog->n_funcs == 1 && full_depth_conv(*geom, *prog, C, NT) && C > 4 && NT == 9) {   // groups of 4 channels, one at a time
     KxGeom gs = *geom;
@@ -871,6 +875,8 @@ int kx_map_vjp_coef(const KxGeom* geom, const KxProgram* prog, const void* x, co
       if (rc != KX_ERR_UNSUPPORTED) return rc;
     }
   }
+  rc = try_wgrad_rows(*geom, *prog, x, g, scratch, dcoef, (cudaStream_t)stream);
+  if (rc != KX_ERR_UNSUPPORTED) return rc;
   return launch_generic_vjp_coef(*geom, *prog, x, g, scratch, dcoef, (cudaStream_t)stream);
 }
 

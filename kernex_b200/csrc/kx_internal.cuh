@@ -121,6 +121,10 @@ int try_stencil3d_star(const MapArgs& a, const KxProgram& prog, int64_t batch, c
 int try_patch(const MapArgs& a, const KxProgram& prog, cudaStream_t s);
 int try_patch2d(const MapArgs& a, const KxProgram& prog, cudaStream_t s);
 int try_patch3d(const MapArgs& a, const KxProgram& prog, cudaStream_t s);
+// general stride-1 weight gradient (kx_wgrad.cu)
+int64_t wgrad_rows_scratch_bytes(const KxGeom& g, const KxProgram& prog);
+int try_wgrad_rows(const KxGeom& g, const KxProgram& prog, const void* x, const void* gout, void* scratch, void* dcoef,
+                   cudaStream_t s);
 int try_conv2d(const MapArgs& a, const KxProgram& prog, cudaStream_t s);
 int try_convc(const MapArgs& a, const KxProgram& prog, cudaStream_t s);
 int try_conv_dense3d(const MapArgs& a, const KxProgram& prog, int64_t batch, cudaStream_t s);

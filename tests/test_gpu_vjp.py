@@ -141,3 +141,36 @@ def test_conv_weight_gradient_matches_oracle(kex, C, H, W):
     dw_want, mag = dw_reference(x, g, (C, 3, 3), (1, 1, 1), border, taps)
     assert_within(dw.cpu().numpy().reshape(-1), dw_want, mag, "dW")
     np.testing.assert_allclose(ko.weight_grad(x, g, (C, 3, 3), (1, 1, 1), border).reshape(-1), dw_want, rtol=1e-12)
+
+
+@pytest.mark.parametrize("case", [
+    ((70, 200), (5, 5), "same"), ((65, 129), (5, 5), "valid"), ((130, 260), (7, 7), "same"), ((40, 300), (2, 2), "same"),
+    ((50, 64), (4, 4), ((1, 2), (0, 3))), ((20, 40, 68), (3, 3, 3), "same"), ((9, 70, 130), (3, 3, 3), "valid"),
+    ((2, 30, 36, 64), (1, 3, 3, 3), ((0, 0), (1, 1), (1, 1), (1, 1))), ((3, 60, 132), (1, 5, 5), ((0, 0), (2, 2), (2, 2))),
+])
+@pytest.mark.parametrize("mean", [False, True])
+def test_wgrad_rows_any_window(kex, case, mean, monkeypatch):
+    """Weight gradient of stride-1 windows beyond 3x3 (5x5, 7x7, 2x2, 4x4, 3x3x3, with batch axes): wgrad_rows_kernel, at the
+    1e-5 bound against the float64 window correlation, deterministic, and equal within that bound to the generic kernel."""
+    from kernex_b200 import _lib
+    shape, ksize, pad = case
+    rng = np.random.default_rng(sum(shape) + sum(ksize) + mean)
+    border = ko.resolve_padding(pad, ksize)
+    x = rng.standard_normal(shape).astype(np.float32)
+    w = torch.from_numpy(rng.standard_normal(ksize).astype(np.float32)).cuda().requires_grad_()
+    f = kex.kmap(kernel_size=ksize, padding=pad)((lambda v, w: np.mean(v * w)) if mean else (lambda v, w: np.sum(v * w)))
+    y = f(torch.from_numpy(x).cuda(), w)
+    g = rng.standard_normal(tuple(y.shape)).astype(np.float32)
+    gt = torch.from_numpy(g).cuda()
+    (dw,) = torch.autograd.grad(y, w, gt, retain_graph=True)
+    assert _lib.last_kernel() == "wgrad_stage2_kernel", _lib.last_kernel()
+    (dw_again,) = torch.autograd.grad(y, w, gt, retain_graph=True)
+    assert torch.equal(dw, dw_again)
+    taps = list(itertools.product(*[range(k) for k in ksize]))
+    want, mag = dw_reference(x, g, ksize, (1,) * len(shape), border, taps)
+    div = float(len(taps)) if mean else 1.0
+    assert_within(dw.cpu().numpy().reshape(-1), want / div, mag / div, "dW")
+    monkeypatch.setenv("KX_NO_WGRAD_ROWS", "1")
+    (dw_gen,) = torch.autograd.grad(y, w, gt)
+    assert _lib.last_kernel() != "wgrad_stage2_kernel"
+    assert_within(dw_gen.cpu().numpy().reshape(-1), want / div, mag / div, "dW (generic)")
