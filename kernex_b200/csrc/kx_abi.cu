@@ -792,7 +792,7 @@ int kx_map_vjp_input(const KxGeom* geom, const KxProgram* prog, const void* g, c
   DeviceGuard guard(dx);
   {
     int C = 0, NT = 0;
-    if (full_depth_conv(*geom, *prog, C, NT) && C > 4) {   // C <= 4: the conv row ring takes the transposed program
+    if (full_depth_conv(*geom, *prog, C, NT) && (C > 4 || NT != 9)) {   // C <= 4 with 3x3 windows: the conv row ring takes the transposed program
       rc = vjp_input_full_depth(*geom, *prog, C, NT, g, coef_dev, dx, (cudaStream_t)stream);
       if (rc != KX_ERR_UNSUPPORTED) return rc;
     }

@@ -30,7 +30,8 @@ namespace {
 constexpr int kCWX = 2, kCWarps = 8, kCRY = 2;
 constexpr int kCX = 128 * kCWX, kCY = kCWarps / kCWX * kCRY;   // tile 8 x 256
 constexpr int kCThreads = 32 * kCWarps;
-constexpr int kCMaxC = KX_MAX_TAPS / 9;
+constexpr int kCMaxC = KX_MAX_TAPS / 9;      // channels at 3x3; K x K windows: C * K * K <= KX_MAX_TAPS
+constexpr int kCWsm = 1536;                    // floats of staged weights: C * (K * K rounded up to 4) for every admissible (C, K)
 
 template <typename T>
 struct ConvCArgs {
@@ -42,9 +43,9 @@ struct ConvCArgs {
   int ly, lx;
   int tiles_x, ntiles;
   T bias;
-  T coef[kCMaxC * 9];       // host weights (row-major c, ky, kx), absent taps = 0 with `mask` bit clear
+  T coef[KX_MAX_TAPS];      // host weights (row-major c, ky, kx), absent taps = 0 with `mask` bit clear
   uint32_t full;            // 1: every (c, ky, kx) tap is present -> no per-tap mask tests
-  uint32_t mask[kCMaxC];    // 9 bits per channel
+  uint64_t mask[kCMaxC];    // K * K bits per channel
 };
 
 template <int I, int N, typename F>
@@ -64,15 +65,17 @@ __device__ __forceinline__ void c_lds4(const T* p, T (&d)[4]) {
   d[3] = reinterpret_cast<const T&>(raw.w);
 }
 
-template <typename T, int SHIFT, bool FULL, int kCStages>
+template <typename T, int SHIFT, bool FULL, int kCStages, int K>
 __global__ void __launch_bounds__(kCThreads)
 convc_kernel(const __grid_constant__ ConvCArgs<T> a) {
-  constexpr int NV = (SHIFT + 6 + 3) / 4;          // aligned 4-vectors covering the 6 needed columns
+  constexpr int NC = 4 + K - 1;                    // window columns a thread's 4 outputs touch
+  constexpr int KK = K * K, KP = (KK + 3) / 4 * 4;  // weights per plane, padded to whole LDS.128
+  constexpr int NV = (SHIFT + NC + 3) / 4;         // aligned 4-vectors covering them
   constexpr int SW = kCX + 4 * NV;                  // tile width (columns), multiple of 4
-  constexpr int SR = kCY + 2;
+  constexpr int SR = kCY + K - 1;
   extern __shared__ __align__(128) unsigned char dyn_smem[];   // the ring: kCStages * SR * SW elements (dynamic: 6 stages exceed 48 KB)
   T* smem = reinterpret_cast<T*>(dyn_smem);
-  __shared__ __align__(16) T wsm[kCMaxC * 12];       // 9 weights per plane, padded to 12: three LDS.128 per plane
+  __shared__ __align__(16) T wsm[kCWsm];             // K * K weights per plane, padded to KP: KP / 4 LDS.128 per plane
   __shared__ __align__(8) uint64_t bars[kCStages];
 
   const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * 32 + tx;
@@ -87,9 +90,9 @@ convc_kernel(const __grid_constant__ ConvCArgs<T> a) {
 
   // weights -> shared memory (read back as broadcasts); the ring starts out as zeros: rows above / below the array and
   // the columns clipped off the row copies are the same in every plane, so they are never written again = zero padding
-  for (int i = tid; i < a.C * 12; i += kCThreads) {
-    const int c = i / 12, t = i - c * 12;
-    wsm[i] = t < 9 ? (a.coef_dev ? a.coef_dev[c * 9 + t] : a.coef[c * 9 + t]) : T(0);
+  for (int i = tid; i < a.C * KP; i += kCThreads) {
+    const int c = i / KP, t = i - c * KP;
+    wsm[i] = t < KK ? (a.coef_dev ? a.coef_dev[c * KK + t] : a.coef[c * KK + t]) : T(0);
   }
   const unsigned smem_base = (unsigned)__cvta_generic_to_shared(smem);
   for (int i = tid; i < kCStages * SR * SW / 4; i += kCThreads) sts_zero16(smem_base + (unsigned)(i * 16));
@@ -142,12 +145,12 @@ convc_kernel(const __grid_constant__ ConvCArgs<T> a) {
     __syncthreads();            // everybody is done reading the stage that is refilled now
     if (tid == 0 && pl + kCStages - 1 < nplanes) issue(pl + kCStages - 1);
     mbar_wait(bar0 + PH * 8, (unsigned)((pl / kCStages) & 1));      // plane pl has landed
-    // rows iy .. iy+RY+1 of the plane tile: the 6 window columns SHIFT+jx .. SHIFT+jx+5 of each
-    T P[kCRY + 2][6];
+    // rows iy .. iy+RY+K-2 of the plane tile: the NC window columns SHIFT+jx .. SHIFT+jx+NC-1 of each
+    T P[kCRY + K - 1][NC];
     {
       const T* t = smem + PH * SR * SW + iy * SW + jx;
 #pragma unroll
-      for (int r = 0; r < kCRY + 2; ++r) {
+      for (int r = 0; r < kCRY + K - 1; ++r) {
         T w[4 * NV];
 #pragma unroll
         for (int q = 0; q < NV; ++q) {
@@ -157,26 +160,26 @@ convc_kernel(const __grid_constant__ ConvCArgs<T> a) {
           for (int e = 0; e < 4; ++e) w[4 * q + e] = d[e];
         }
 #pragma unroll
-        for (int e = 0; e < 6; ++e) P[r][e] = w[SHIFT + e];
+        for (int e = 0; e < NC; ++e) P[r][e] = w[SHIFT + e];
       }
     }
-    T wk[12];
+    T wk[KP];
 #pragma unroll
-    for (int q = 0; q < 3; ++q) {
+    for (int q = 0; q < KP / 4; ++q) {
       T d[4];
-      c_lds4(wsm + pl * 12 + 4 * q, d);
+      c_lds4(wsm + pl * KP + 4 * q, d);
 #pragma unroll
       for (int e = 0; e < 4; ++e) wk[4 * q + e] = d[e];
     }
-    const uint32_t m = FULL ? 0x1ffu : a.mask[pl];
+    const uint64_t m = FULL ? ~0ull : a.mask[pl];
 #pragma unroll
     for (int r = 0; r < kCRY; ++r) {
 #pragma unroll
-      for (int ky = 0; ky < 3; ++ky) {
+      for (int ky = 0; ky < K; ++ky) {
 #pragma unroll
-        for (int kx = 0; kx < 3; ++kx) {
-          if (FULL || (m & (1u << (ky * 3 + kx)))) {
-            const T w1 = wk[ky * 3 + kx];
+        for (int kx = 0; kx < K; ++kx) {
+          if (FULL || (m & (1ull << (ky * K + kx)))) {
+            const T w1 = wk[ky * K + kx];
             if constexpr (std::is_same<T, float>::value) {   // two packed FMAs instead of four scalar ones
               ffma2(acc[r][0], acc[r][1], w1, w1, P[r + ky][kx], P[r + ky][kx + 1]);
               ffma2(acc[r][2], acc[r][3], w1, w1, P[r + ky][kx + 2], P[r + ky][kx + 3]);
@@ -218,8 +221,9 @@ convc_kernel(const __grid_constant__ ConvCArgs<T> a) {
   }
 }
 
-template <typename T>
+template <typename T, int K>
 int run_convc(const MapArgs& m, const KxProgram& p, int64_t batch, cudaStream_t s) {
+  constexpr int KK = K * K;
   const KxGeom& g = m.g;
   const KxFunc& f = p.func[0];
   const int ac = g.ndim - 3, ay = g.ndim - 2, ax = g.ndim - 1;
@@ -228,15 +232,15 @@ int run_convc(const MapArgs& m, const KxProgram& p, int64_t batch, cudaStream_t 
   memset(&a, 0, sizeof(a));
   int n_present = 0;
   for (int t = f.tap_begin; t < f.tap_end; ++t) {
-    const int c = p.tap_off[t][ac], slot = p.tap_off[t][ay] * 3 + p.tap_off[t][ax];
-    if (a.mask[c] & (1u << slot)) return KX_ERR_UNSUPPORTED;          // duplicate tap: generic kernel
-    a.mask[c] |= 1u << slot;
-    a.coef[c * 9 + slot] = (T)p.coef[t];
+    const int c = p.tap_off[t][ac], slot = p.tap_off[t][ay] * K + p.tap_off[t][ax];
+    if (a.mask[c] & (1ull << slot)) return KX_ERR_UNSUPPORTED;        // duplicate tap: generic kernel
+    a.mask[c] |= 1ull << slot;
+    a.coef[c * KK + slot] = (T)p.coef[t];
     // device weights are indexed by TAP number: only the identity layout (tap t <-> c*9 + slot) is taken
-    if (m.coef_dev && (t - f.tap_begin) != c * 9 + slot) return KX_ERR_UNSUPPORTED;
+    if (m.coef_dev && (t - f.tap_begin) != c * KK + slot) return KX_ERR_UNSUPPORTED;
     ++n_present;
   }
-  a.full = n_present == C * 9 ? 1u : 0u;
+  a.full = n_present == C * KK ? 1u : 0u;
   if (m.coef_dev && !a.full) return KX_ERR_UNSUPPORTED;
   a.in = (const T*)m.in;
   a.out = (T*)m.out;
@@ -262,14 +266,14 @@ int run_convc(const MapArgs& m, const KxProgram& p, int64_t batch, cudaStream_t 
   // ring depth: 3 stages (5 blocks / SM); 6 stages (3 blocks / SM) only when the whole grid is resident anyway -- there
   // a block's C-plane march is one dependent chain of DRAM round trips and depth is all that hides it (measured,
   // benchmarks/convc_probe.py: 4-10 % at <= 512^2, but 1.6x SLOWER at 1024^2 where it costs a second wave)
-  int stages = nblocks <= (int64_t)sm_count() * 3 ? 6 : 3;
-  if (const char* e = getenv("KX_CONVC_STAGES")) stages = atoi(e) == 6 ? 6 : 3;   // tuning knob
-  const int sw = kCX + 4 * ((shift + 6 + 3) / 4);
-  const size_t ring = (size_t)stages * (kCY + 2) * sw * sizeof(T);
+  int stages = (K == 3 && nblocks <= (int64_t)sm_count() * 3) ? 6 : 3;
+  if (const char* e = getenv("KX_CONVC_STAGES")) stages = (atoi(e) == 6 && K == 3) ? 6 : 3;   // tuning knob
+  const int sw = kCX + 4 * ((shift + 4 + K - 1 + 3) / 4);
+  const size_t ring = (size_t)stages * (kCY + K - 1) * sw * sizeof(T);
 #define KX_CONVC2(S, FULLV, ST)                                                                                  \
   {                                                                                                              \
-    auto kern = convc_kernel<T, S, FULLV, ST>;                                                                   \
-    if (ring > 48 * 1024) KX_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring)); \
+    auto kern = convc_kernel<T, S, FULLV, ST, K>;                                                                   \
+    if (ring + 8192 > 48 * 1024) KX_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring)); \
     kern<<<grid, block, ring, s>>>(a);                                                                           \
   }
 #define KX_CONVC(S)                                                    \
@@ -298,8 +302,11 @@ int try_convc(const MapArgs& m, const KxProgram& p, cudaStream_t s) {
   if (g.in_dtype != g.out_dtype || m.fn_elems != 1 || m.use_box) return KX_ERR_UNSUPPORTED;
   const int ac = nd - 3;
   const int C = g.ksize[ac];
-  if (C < 5 || C > kCMaxC || C != g.in_shape[ac] || g.lo[ac] != 0 || g.hi[ac] != 0 || g.stride[ac] != 1) return KX_ERR_UNSUPPORTED;
-  if (g.ksize[nd - 2] != 3 || g.ksize[nd - 1] != 3 || g.stride[nd - 2] != 1 || g.stride[nd - 1] != 1) return KX_ERR_UNSUPPORTED;
+  const int K = g.ksize[nd - 1];
+  if (g.ksize[nd - 2] != K || (K != 3 && K != 5 && K != 7) || g.stride[nd - 2] != 1 || g.stride[nd - 1] != 1) return KX_ERR_UNSUPPORTED;
+  // 3x3 windows with C <= 4 belong to the per-warp row ring of kx_conv2d.cu; wider windows take every C >= 2
+  if (C < (K == 3 ? 5 : 2) || C * K * K > KX_MAX_TAPS || C > kCMaxC || C * ((K * K + 3) / 4 * 4) > kCWsm) return KX_ERR_UNSUPPORTED;
+  if (C != g.in_shape[ac] || g.lo[ac] != 0 || g.hi[ac] != 0 || g.stride[ac] != 1) return KX_ERR_UNSUPPORTED;
   int64_t lead = 1;
   for (int d = 0; d < nd - 3; ++d) {
     if (g.ksize[d] != 1 || g.stride[d] != 1 || g.lo[d] != 0 || g.hi[d] != 0) return KX_ERR_UNSUPPORTED;
@@ -310,8 +317,16 @@ int try_convc(const MapArgs& m, const KxProgram& p, cudaStream_t s) {
   if (g.in_shape[nd - 1] % 4 != 0 || (reinterpret_cast<uintptr_t>(m.in) & 15) != 0) return KX_ERR_UNSUPPORTED;
   if (g.in_shape[nd - 1] > 0x3fffffff || g.in_shape[nd - 2] > 0x3fffffff) return KX_ERR_UNSUPPORTED;
   if (getenv("KX_NO_CONVC")) return KX_ERR_UNSUPPORTED;   // cross-check: the generic kernel
-  if (g.in_dtype == KX_F32) return run_convc<float>(m, p, batch, s);
-  if (g.in_dtype == KX_I32 && p.func[0].coef_is_int) return run_convc<int32_t>(m, p, batch, s);
+  if (g.in_dtype == KX_F32) {
+    if (K == 3) return run_convc<float, 3>(m, p, batch, s);
+    if (K == 5) return run_convc<float, 5>(m, p, batch, s);
+    return run_convc<float, 7>(m, p, batch, s);
+  }
+  if (g.in_dtype == KX_I32 && p.func[0].coef_is_int) {
+    if (K == 3) return run_convc<int32_t, 3>(m, p, batch, s);
+    if (K == 5) return run_convc<int32_t, 5>(m, p, batch, s);
+    return run_convc<int32_t, 7>(m, p, batch, s);
+  }
   return KX_ERR_UNSUPPORTED;
 }
 

@@ -143,3 +143,47 @@ def test_gradient_kernels_of_the_many_channel_conv(kex):
     assert _last_kernel() == "stencil2d_kernel"
     pm.vjp_coef(x, g)
     assert _last_kernel() == "conv_wgrad_finish"
+
+
+@pytest.mark.parametrize("C,K,H,W,pad", [(3, 5, 40, 260, "same"), (2, 7, 33, 132, "same"), (8, 5, 21, 516, "valid"), (6, 7, 50, 64, "same"),
+                                         (3, 5, 64, 64, ((0, 0), (1, 2), (3, 0)))])
+@pytest.mark.parametrize("device_weights", [False, True])
+def test_wide_window_multichannel_conv(kex, C, K, H, W, pad, device_weights):
+    """conv-as-kmap with (C, 5, 5) / (C, 7, 7) windows (convc_kernel<K>): forward against the oracle at the 1e-5 bound, int32
+    bit exact, and both gradients (dx: per-channel flipped-tap 2-D stencils, dW: wgrad_rows_kernel) against float64."""
+    import itertools
+    from kernex_b200 import _lib
+    from vjp_ref import assert_within, dw_reference, dx_reference
+    rng = np.random.default_rng(C * 100 + K + H)
+    padding = ("valid", pad, pad) if isinstance(pad, str) else pad
+    border = ko.resolve_padding(padding, (C, K, K))
+    taps = list(itertools.product(range(C), range(K), range(K)))
+    x = rng.standard_normal((C, H, W)).astype(np.float32)
+    w = rng.standard_normal((C, K, K)).astype(np.float32)
+    xt = torch.from_numpy(x).cuda()
+    if device_weights:
+        wt = torch.from_numpy(w).cuda().requires_grad_()
+        conv = kex.kmap(kernel_size=(C, K, K), padding=padding)(lambda v, w: np.sum(v * w))
+        xt.requires_grad_()
+        y = conv(xt, wt)
+    else:
+        conv = kex.kmap(kernel_size=(C, K, K), padding=padding)(lambda v: np.sum(v * w))
+        y = conv(xt)
+    assert _lib.last_kernel() == "convc_kernel", _lib.last_kernel()
+    coefs = [float(w[t]) for t in taps]
+    want = ko.affine_map(x, (C, K, K), (1, 1, 1), border, taps, coefs)
+    scale = ko.affine_map(np.abs(x), (C, K, K), (1, 1, 1), border, taps, np.abs(coefs))
+    assert np.all(np.abs(y.detach().cpu().numpy().astype(np.float64) - want) <= 1e-5 * scale + 1e-30)
+    if device_weights:
+        g = rng.standard_normal(tuple(y.shape)).astype(np.float32)
+        dx, dw = torch.autograd.grad(y, (xt, wt), torch.from_numpy(g).cuda())
+        dw_want, mag = dw_reference(x, g, (C, K, K), (1, 1, 1), border, taps)
+        assert_within(dw.cpu().numpy().reshape(-1), dw_want, mag, "dW")
+        dx_want, magx = dx_reference(g, (C, H, W), (C, K, K), (1, 1, 1), border, taps, [float(np.float32(c)) for c in coefs])
+        assert_within(dx.cpu().numpy(), dx_want, magx, "dx")
+    else:
+        xi = rng.integers(-9, 10, (C, H, W)).astype(np.int32)
+        wi = rng.integers(-3, 4, (C, K, K)).astype(np.int32)
+        yi = kex.kmap(kernel_size=(C, K, K), padding=padding)(lambda v: np.sum(v * wi))(torch.from_numpy(xi).cuda())
+        wanti = ko.affine_map(xi.astype(np.int64), (C, K, K), (1, 1, 1), border, taps, [int(wi[t]) for t in taps])
+        np.testing.assert_array_equal(yi.cpu().numpy(), wanti.astype(np.int32))
