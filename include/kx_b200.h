@@ -176,7 +176,9 @@ int kx_map_vjp_coef(const KxGeom* geom, const KxProgram* prog, const void* x, co
  * rows are independent given the previous ones and a row-marching kernel
  * parallelises each row; otherwise the wavefront kernels run every hyperplane of
  * mutually independent windows in parallel (warp-skewed for 2-D in-row dependencies),
- * which reproduces the exact sweep order's values.  `reverse` = lax.scan(reverse=True).
+ * which reproduces the exact sweep order's values.  3-D scans whose functions read only the PLANE above the cell they
+ * write (time marching with two space axes, tests/test_interface.py:28-97) run as one 2-D kmap launch per plane.
+ * `reverse` = lax.scan(reverse=True).
  */
 int64_t kx_scan_state_bytes(const KxGeom* geom);
 int kx_scan(const KxGeom* geom, const KxProgram* prog, const void* in, const void* coef_dev,
