@@ -144,8 +144,7 @@ struct WGPlan {
 };
 
 WGPlan plan_wgrad(const KxGeom& g, const KxProgram& p) {
-  WGPlan w;
-  memset(&w, 0, sizeof(w));
+  WGPlan w{};                  // ok = false
   const int nd = g.ndim;
   if (nd < 2 || p.n_funcs != 1 || p.func[0].kind != KX_AFFINE || g.in_dtype != KX_F32 || g.out_dtype != KX_F32) return w;
   if (getenv("KX_NO_WGRAD_ROWS")) return w;
