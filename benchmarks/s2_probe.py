@@ -34,6 +34,24 @@ elif case in ("patch5", "patch7", "patch5_old"):
     n = 4096
     x = torch.randn((n, n), device=dev, generator=g)
     f = kex.kmap(kernel_size=(k, k), padding="same")(lambda v: v)
+elif case == "wgrad5":
+    x = torch.randn((8192, 8192), device=dev, generator=g)
+    w = torch.randn((5, 5), device=dev, generator=g).requires_grad_()
+    f0 = kex.kmap(kernel_size=(5, 5), padding="same")(lambda v, w: np.sum(v * w))
+    yy = f0(x, w)
+    gy = torch.randn(yy.shape, device=dev, generator=g)
+    f = lambda t: torch.autograd.grad(yy, w, gy, retain_graph=True)[0]
+elif case == "poolbwd":
+    x = torch.randn((8192, 8192), device=dev, generator=g).requires_grad_()
+    f0 = kex.kmap(kernel_size=(3, 3), strides=(2, 2))(lambda v: np.mean(v))
+    yy = f0(x)
+    gy = torch.randn(yy.shape, device=dev, generator=g)
+    f = lambda t: torch.autograd.grad(yy, x, gy, retain_graph=True)[0]
+elif case == "conv355":
+    x = torch.randn((3, 4096, 4096), device=dev, generator=g)
+    w = torch.randn((3, 5, 5), device=dev, generator=g)
+    f0 = kex.kmap(kernel_size=(3, 5, 5), padding=("valid", "same", "same"))(lambda v, w: np.sum(v * w))
+    f = lambda t: f0(t, w)
 elif case == "fir15":
     x = torch.randn((1 << 27,), device=dev, generator=g)
     taps = np.hanning(15).astype(np.float32)

@@ -5,7 +5,7 @@ M=gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,sm__inst_exe
 for c in "$@"; do
   echo "== $c" >> $out
   python s2_probe.py $c 2 >> $out 2>&1 || continue
-  ncu --metrics $M --clock-control none -k regex:'stencil|pool|sep2d|convc' -s 4 -c 1 --csv python s2_probe.py $c 2 2>/dev/null | python -c "
+  ncu --metrics $M --clock-control none -k regex:'stencil|pool|sep2d|convc|patch|wgrad_rows|strided_vjp' -s 4 -c 1 --csv python s2_probe.py $c 2 2>/dev/null | python -c "
 import csv,sys
 rows=[r for r in csv.reader(sys.stdin) if len(r)>10]
 for r in rows[1:]:
